@@ -1,0 +1,144 @@
+/*
+ * pe_b200.h -- C ABI of the B200-native pose-estimator hot path (libpe_b200.so).
+ *
+ * The reference (cremebrule/rgb-proprioceptive-pose-estimator) has no FFI: its hot path is a chain
+ * of PyTorch library calls.  Each entry point below replaces one such call site; the host mirror in
+ * rgb-proprioceptive-pose-estimator_b200/{models,util} binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 (double where stated) owned by the caller;
+ *   - activations are NHWC ("pixels x channels"), channels innermost; `ld*` are row strides in elements;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, allocate nothing on the
+ *     device (except one 4-byte sticky error flag on first use) and are CUDA-graph capturable;
+ *   - return 0 on success; non-zero on failure with a message in pe_last_error();
+ *   - device-side pipeline timeouts set a sticky flag readable with pe_device_error() (synchronises).
+ *   - all dense contractions run on tcgen05 tensor cores with TF32 operands and fp32 accumulation.
+ */
+#ifndef PE_B200_H_
+#define PE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* pe_last_error(void);
+int pe_device_error(void);
+int pe_version(void);
+/* debug: override UMMA shared-memory descriptor strides (bytes; <0 restores the default) */
+void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo);
+
+/* ---- convolutions: torchvision resnet.py:143-163,266-282 Conv2d calls reached from
+ *      models/naive.py:316 and models/time_sensitive.py:185,472 (bias-free, NHWC here) ------------
+ * w_tck : weights packed [R*S][Cout][Cin]   (pe_pack_conv_weight)
+ * w_tkc : weights packed [R*S][Cin][Cout]
+ * fwd epilogue: y = act(acc*scale[c] + shift[c] + residual) when scale != NULL (eval-mode folded BN),
+ *               y = acc otherwise; stats (double[2*Cout]: sum, sum of squares of acc) accumulated
+ *               when non-NULL (training-mode BatchNorm statistics); round_out rounds y to TF32.   */
+int pe_conv2d_fwd(const float* x, const float* w_tck, float* y, int B, int H, int W, int Cin, int Cout, int R,
+                  int S, int stride, int pad, const float* scale, const float* shift, const float* residual,
+                  int relu, int round_out, double* stats, void* stream);
+int pe_conv2d_dgrad(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin, int Cout,
+                    int R, int S, int stride, int pad, void* stream);
+int pe_conv2d_wgrad(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin, int Cout,
+                    int R, int S, int stride, int pad, void* stream);
+/* OIHW (checkpoint layout, util/model_utils.py:136-141) <-> packed tap-major layouts */
+int pe_pack_conv_weight(const float* w_oihw, float* w_tck, float* w_tkc, int Cout, int Cin, int R, int S,
+                        int round_tf32, void* stream);
+int pe_unpack_conv_wgrad(const float* dw_tck, float* dw_oihw, int Cout, int Cin, int R, int S, int accumulate,
+                         void* stream);
+/* 7x7/2 stem (Cin = 3): NCHW image -> im2col rows [B*Ho*Wo][ldc], columns ordered (c, r, s) like OIHW */
+int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W, int R, int S, int stride,
+                   int pad, int ldc, int round_tf32, void* stream);
+
+/* ---- dense layers: nn.Linear / nn.LSTM projections (models/naive.py:274,343-345,
+ *      models/time_sensitive.py:126-131,418-423) -------------------------------------------------
+ * y[M,N] = x[M,K] w[N,K]^T (+bias)(ReLU); accumulate!=0 adds into the existing y.                 */
+int pe_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy, int M,
+                  int N, int K, int relu, int accumulate, int round_out, void* stream);
+/* dw[N,K] = dy[M,N]^T x[M,K] */
+int pe_linear_wgrad(const float* x, int ldx, const float* dy, int lddy, float* dw, int lddw, int M, int N, int K,
+                    void* stream);
+/* dst[c][r] = src[r][c] (rows x cols), optional TF32 rounding; dst rows beyond `cols` untouched */
+int pe_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream);
+/* dst[r][0:cols] = src[r][0:cols] with independent row strides (concat / slicing), optional rounding */
+int pe_copy_cols(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream);
+/* out[c] (+)= sum_r x[r][c] : bias gradients */
+int pe_colsum(const float* x, int ldx, float* out, int rows, int cols, int accumulate, void* stream);
+/* dz = dy * (y > 0) */
+int pe_relu_bwd(const float* dy, int lddy, const float* y, int ldy, float* dz, int lddz, int rows, int cols,
+                void* stream);
+
+/* ---- BatchNorm2d (torchvision resnet.py:134-138,198; torch semantics: biased var to normalise,
+ *      unbiased into running_var, momentum 0.1, eps 1e-5) ----------------------------------------- */
+/* standalone statistics (same result as the conv epilogue): stats = double[2*C], zeroed by the caller */
+int pe_bn_stats(const float* y, long long P, int C, double* stats, void* stream);
+/* train: from stats -> mean, invstd, scale=gamma*invstd, shift=beta-mean*scale; updates running stats.
+ * eval (stats == NULL): scale/shift from running stats.  The caller zeroes `stats` before each step.   */
+int pe_bn_finalize(double* stats, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float* scale, float* shift, float* mean, float* invstd, long long count,
+                   float momentum, float eps, int C, void* stream);
+/* out = act(y*scale[c] + shift[c] (+ residual)) */
+int pe_bn_apply(const float* y, const float* scale, const float* shift, const float* residual, float* out,
+                long long P, int C, int relu, int round_tf32, void* stream);
+/* backward pass 1: g = dout*(out>0 if relu); sums = double[2*C] += (sum g, sum g*xhat) */
+int pe_bn_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
+                     double* sums, long long P, int C, int relu, void* stream);
+/* backward pass 2: dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P); dres = g (optional);
+ * dgamma = sum_gx, dbeta = sum_g (written or accumulated).  The caller zeroes `sums` before pass 1.   */
+int pe_bn_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
+                    const float* gamma, double* sums, float* dy, float* dres, int dres_accumulate, float* dgamma,
+                    float* dbeta, int param_accumulate, long long P, int C, int relu, void* stream);
+
+/* ---- stem pooling + auxiliary BN1 branch (torchvision resnet.py:268-272; models/naive.py:223-231,
+ *      models/time_sensitive.py:377-385: Conv2d(64,1,1) + MaxPool2d(2) + Flatten on post-ReLU bn1) -- */
+int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, int H, int W, int C, void* stream);
+int pe_maxpool3x3s2_bwd(const float* dy, const unsigned char* argmax, float* dx, int accumulate, int B, int H,
+                        int W, int C, void* stream);
+int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int round_tf32, void* stream);
+int pe_avgpool_bwd(const float* dy, int lddy, float* dx, int B, int HW, int C, void* stream);
+int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, int ldo, unsigned char* argmax,
+               int B, int H, int W, int C, int round_tf32, void* stream);
+/* da1 (+)= scatter(dout) * w ; dw[C] += ..., db[1] += ... (dw/db may be NULL: frozen aux conv, td model) */
+int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const float* a1, const float* w,
+               float* da1, int accumulate, float* dw, float* db, int B, int H, int W, int C, void* stream);
+
+/* ---- LSTM cell (nn.LSTM single layer, gate order i,f,g,o; models/time_sensitive.py:126-131,418) -----
+ * gates = gx + gh + b_ih + b_hh  ([N][4H]); act = (sig i, sig f, tanh g, sig o); c = f*c_prev + i*g;
+ * h = o*tanh(c).  `act` keeps the activated gates for backward.                                       */
+int pe_lstm_cell_fwd(const float* gx, int ldgx, const float* gh, int ldgh, const float* b_ih, const float* b_hh,
+                     const float* c_prev, float* c_out, float* h_out, int ldh, float* act, int N, int Hd,
+                     int round_tf32, void* stream);
+/* dgates (pre-activation) and dc_prev from dh (= dh_out + dh_next) and dc_next */
+int pe_lstm_cell_bwd(const float* dh, int lddh, const float* dh_rec, const float* dc_next, const float* act,
+                     const float* c_prev, const float* c_out, float* dgates, int lddg, float* dc_prev, int N,
+                     int Hd, void* stream);
+
+/* ---- pose loss (models/losses.py:47-128) ------------------------------------------------------------
+ * metric: 0 l1, 1 l2, 2 linf, 3 combined.  mode: 0 position, 1 pose.  loss[0] = scale*(pos+alpha*ori)
+ * summed over the n rows; dpred = d loss / d pred (pass NULL to skip).  val-mode metrics:
+ * val[0] = sum l2 position error, val[1] = sum |angle| (rad) between normalised quaternions.          */
+int pe_pose_loss(const float* pred, int ldp, const float* truth, int ldt, long long n, int metric, int mode,
+                 float alpha, float epsilon, float scale, float* loss, float* dpred, int lddp, float* val,
+                 void* stream);
+
+/* ---- optimizers (torch.optim.Adam at scripts/train_model.py:228; SGD for completeness) --------------
+ * flat arrays; grad_scale multiplies the gradient first (1.0 normally); step is the 1-based step count. */
+int pe_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int step, float grad_scale, void* stream);
+int pe_sgd_step(float* p, const float* g, float* mom, long long n, float lr, float momentum, float weight_decay,
+                int first_step, float grad_scale, void* stream);
+
+/* ---- misc -------------------------------------------------------------------------------------------*/
+int pe_fill(float* p, long long n, float value, void* stream);
+/* p[i] += value over an int64 array (BatchNorm num_batches_tracked counters) */
+int pe_add_i64(long long* p, long long n, long long value, void* stream);
+/* uint8 HWC frame batch -> normalised fp32 NCHW (Resize is the caller's; crop + /255 + mean/std here):
+ * util/data_utils.py:48-54, util/learn_utils.py:299-305 */
+/* mean3 / std3 are HOST arrays of 3 floats */
+int pe_preprocess_u8(const unsigned char* src, float* dst, int B, int Hs, int Ws, int crop, const float* mean3,
+                     const float* std3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PE_B200_H_ */

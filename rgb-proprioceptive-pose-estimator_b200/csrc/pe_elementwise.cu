@@ -1,0 +1,777 @@
+// HBM-streaming kernels of the trunk: BatchNorm statistics / apply / backward, stem pooling,
+// auxiliary BN1 branch, weight (un)packing, im2col for the 7x7 stem, small copy helpers.
+// All activations are NHWC fp32; every kernel moves 128-bit words and sizes its grid from the SM count.
+#include "../../include/pe_b200.h"
+#include "pe_common.cuh"
+
+namespace pe {
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
+    long long blocks = (work_items + per_block - 1) / per_block;
+    long long cap = (long long)num_sms() * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 round4(float4 v) {
+    return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-channel reductions over [P][C]:  acc0 += f0(row, c), acc1 += f1(row, c)
+// block = 256 threads = TR row lanes x GW channel groups (4 channels each); grid.y covers C > 1024.
+// ---------------------------------------------------------------------------------------------
+template <int KIND>  // 0: (y, y*y)   1: (g, g*xhat) with g = dout * (out > 0 if relu)
+__global__ void __launch_bounds__(EW_THREADS)
+channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ sums,
+                      long long P, int C, int relu) {
+    __shared__ float sm0[EW_THREADS * 4];
+    __shared__ float sm1[EW_THREADS * 4];
+    const int G = C >> 2;
+    const int GW = G < EW_THREADS ? G : EW_THREADS;
+    const int TR = EW_THREADS / GW;
+    const int g = blockIdx.y * GW + (threadIdx.x % GW);
+    const int r = threadIdx.x / GW;
+    const long long rows_per_block = (P + gridDim.x - 1) / gridDim.x;
+    const long long row0 = (long long)blockIdx.x * rows_per_block;
+    long long row1 = row0 + rows_per_block;
+    if (row1 > P) row1 = P;
+
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    float4 mu = s0, is = s0;
+    if (KIND == 1) {
+        mu = ld4(mean + 4 * g);
+        is = ld4(invstd + 4 * g);
+    }
+    for (long long row = row0 + r; row < row1; row += TR) {
+        const long long off = row * C + 4 * g;
+        if (KIND == 0) {
+            const float4 y = ld4_stream(a + off);
+            s0.x += y.x; s0.y += y.y; s0.z += y.z; s0.w += y.w;
+            s1.x += y.x * y.x; s1.y += y.y * y.y; s1.z += y.z * y.z; s1.w += y.w * y.w;
+        } else {
+            float4 d = ld4_stream(a + off);
+            if (relu) {
+                const float4 o = ld4_stream(b + off);
+                d.x = o.x > 0.f ? d.x : 0.f;
+                d.y = o.y > 0.f ? d.y : 0.f;
+                d.z = o.z > 0.f ? d.z : 0.f;
+                d.w = o.w > 0.f ? d.w : 0.f;
+            }
+            const float4 y = ld4_stream(c + off);
+            s0.x += d.x; s0.y += d.y; s0.z += d.z; s0.w += d.w;
+            s1.x += d.x * (y.x - mu.x) * is.x;
+            s1.y += d.y * (y.y - mu.y) * is.y;
+            s1.z += d.z * (y.z - mu.z) * is.z;
+            s1.w += d.w * (y.w - mu.w) * is.w;
+        }
+    }
+    st4(sm0 + 4 * threadIdx.x, s0);
+    st4(sm1 + 4 * threadIdx.x, s1);
+    __syncthreads();
+    if (r == 0) {
+        for (int k = 1; k < TR; ++k) {
+            const float4 t0 = ld4(sm0 + 4 * (threadIdx.x + k * GW));
+            const float4 t1 = ld4(sm1 + 4 * (threadIdx.x + k * GW));
+            s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+            s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+        }
+        double* p0 = sums + 4 * g;
+        double* p1 = sums + C + 4 * g;
+        atomicAdd(p0 + 0, (double)s0.x); atomicAdd(p0 + 1, (double)s0.y);
+        atomicAdd(p0 + 2, (double)s0.z); atomicAdd(p0 + 3, (double)s0.w);
+        atomicAdd(p1 + 0, (double)s1.x); atomicAdd(p1 + 1, (double)s1.y);
+        atomicAdd(p1 + 2, (double)s1.z); atomicAdd(p1 + 3, (double)s1.w);
+    }
+}
+
+dim3 reduce_grid(long long P, int C) {
+    const int G = C / 4;
+    const int gy = G > EW_THREADS ? G / EW_THREADS : 1;
+    long long gx = (long long)num_sms() * 4 / gy;
+    const long long max_gx = (P + 31) / 32;  // at least ~32 rows per block
+    if (gx > max_gx) gx = max_gx;
+    if (gx < 1) gx = 1;
+    return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, double count, float momentum, float eps, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mean, invstd;
+    if (stats) {
+        const double m = stats[c] / count;
+        double var = stats[C + c] / count - m * m;
+        if (var < 0.0) var = 0.0;
+        mean = (float)m;
+        invstd = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    } else {
+        mean = running_mean[c];
+        invstd = 1.f / sqrtf(running_var[c] + eps);
+    }
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    if (mean_out) mean_out[c] = mean;
+    if (invstd_out) invstd_out[c] = invstd;
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                const float* __restrict__ residual, float* __restrict__ out, long long n4, int G, int relu,
+                int round_out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int g = (int)(i % G);
+        const float4 v = ld4_stream(y + 4 * i);
+        const float4 sc = ld4(scale + 4 * g);
+        const float4 sh = ld4(shift + 4 * g);
+        float4 o;
+        o.x = fmaf(v.x, sc.x, sh.x);
+        o.y = fmaf(v.y, sc.y, sh.y);
+        o.z = fmaf(v.z, sc.z, sh.z);
+        o.w = fmaf(v.w, sc.w, sh.w);
+        if (residual) {
+            const float4 r = ld4_stream(residual + 4 * i);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (relu) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+        if (round_out) o = round4(o);
+        st4(out + 4 * i, o);
+    }
+}
+
+// dy = a*g + b*y + c per channel, a = gamma*invstd, b = -a*k2*invstd, c = -a*k1 + a*k2*invstd*mean,
+// k1 = sum_g/P, k2 = sum_gxhat/P.  Coefficients are rebuilt per block into shared memory.
+__global__ void __launch_bounds__(EW_THREADS)
+bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ gamma, const double* __restrict__ sums, float* __restrict__ dy,
+                    float* __restrict__ dres, int dres_acc, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    int param_acc, long long P, int C, int relu) {
+    extern __shared__ float coef[];  // [3][C]
+    float* ca = coef;
+    float* cb = coef + C;
+    float* cc = coef + 2 * C;
+    const double invP = 1.0 / (double)P;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double sg = sums[c], sgx = sums[C + c];
+        const float is = invstd[c], mu = mean[c];
+        const float a = gamma[c] * is;
+        const float k1 = (float)(sg * invP), k2 = (float)(sgx * invP);
+        ca[c] = a;
+        cb[c] = -a * k2 * is;
+        cc[c] = -a * k1 + a * k2 * is * mu;
+        if (blockIdx.x == 0) {
+            if (dgamma) dgamma[c] = (param_acc ? dgamma[c] : 0.f) + (float)sgx;
+            if (dbeta) dbeta[c] = (param_acc ? dbeta[c] : 0.f) + (float)sg;
+        }
+    }
+    __syncthreads();
+    const int G = C >> 2;
+    const long long n4 = P * G;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int g = (int)(i % G);
+        float4 d = ld4_stream(dout + 4 * i);
+        if (relu) {
+            const float4 o = ld4_stream(out + 4 * i);
+            d.x = o.x > 0.f ? d.x : 0.f;
+            d.y = o.y > 0.f ? d.y : 0.f;
+            d.z = o.z > 0.f ? d.z : 0.f;
+            d.w = o.w > 0.f ? d.w : 0.f;
+        }
+        if (dres) {
+            if (dres_acc) {
+                float4 r = ld4(dres + 4 * i);
+                r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+                st4(dres + 4 * i, r);
+            } else {
+                st4(dres + 4 * i, d);
+            }
+        }
+        const float4 yv = ld4_stream(y + 4 * i);
+        const float4 a = ld4(ca + 4 * g), b = ld4(cb + 4 * g), c = ld4(cc + 4 * g);
+        float4 r;
+        r.x = fmaf(a.x, d.x, fmaf(b.x, yv.x, c.x));
+        r.y = fmaf(a.y, d.y, fmaf(b.y, yv.y, c.y));
+        r.z = fmaf(a.z, d.z, fmaf(b.z, yv.z, c.z));
+        r.w = fmaf(a.w, d.w, fmaf(b.w, yv.w, c.w));
+        st4(dy + 4 * i, r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ tck, float* __restrict__ tkc,
+                                   int Cout, int Cin, int RS, int round_out) {
+    const long long n = (long long)Cout * Cin * RS;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // iterate in tck order (coalesced writes): idx = (t*Cout + co)*Cin + ci
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int ci = (int)(i % Cin);
+        const long long r = i / Cin;
+        const int co = (int)(r % Cout);
+        const int t = (int)(r / Cout);
+        float v = w[((long long)co * Cin + ci) * RS + t];
+        if (round_out) v = round_tf32(v);
+        if (tck) tck[i] = v;
+        if (tkc) tkc[((long long)t * Cin + ci) * Cout + co] = v;
+    }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ tck, float* __restrict__ w, int Cout, int Cin, int RS,
+                                    int accumulate) {
+    const long long n = (long long)Cout * Cin * RS;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // idx in OIHW order: i = (co*Cin + ci)*RS + t
+        const int t = (int)(i % RS);
+        const long long r = i / RS;
+        const int ci = (int)(r % Cin);
+        const int co = (int)(r / Cin);
+        const float v = tck[((long long)t * Cout + co) * Cin + ci];
+        w[i] = accumulate ? w[i] + v : v;
+    }
+}
+
+__global__ void im2col_stem_kernel(const float* __restrict__ img, float* __restrict__ col, int B, int C, int H,
+                                   int W, int R, int S, int stride, int pad, int Ho, int Wo, int ldc,
+                                   int round_out) {
+    const long long n = (long long)B * Ho * Wo * ldc;
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    const int K = C * R * S;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const int k = (int)(i % ldc);
+        const long long row = i / ldc;
+        float v = 0.f;
+        if (k < K) {
+            const int s = k % S;
+            const int r = (k / S) % R;
+            const int c = k / (S * R);
+            const int wo = (int)(row % Wo);
+            const int ho = (int)((row / Wo) % Ho);
+            const int b = (int)(row / ((long long)Wo * Ho));
+            const int h = ho * stride + r - pad, w = wo * stride + s - pad;
+            if (h >= 0 && h < H && w >= 0 && w < W) v = img[(((long long)b * C + c) * H + h) * W + w];
+            if (round_out) v = round_tf32(v);
+        }
+        col[i] = v;
+    }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows,
+                                 int cols, int round_out) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? src[(long long)r * lds + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            float v = tile[threadIdx.x][j];
+            if (round_out) v = round_tf32(v);
+            dst[(long long)c * ldd + r] = v;
+        }
+    }
+}
+
+__global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
+                                 long long rows, int cols, int round_out) {
+    const long long n = rows * cols;
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const int c = (int)(i % cols);
+        const long long r = i / cols;
+        float v = src[r * lds + c];
+        if (round_out) v = round_tf32(v);
+        dst[r * ldd + c] = v;
+    }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int rows, int cols,
+                              int accumulate) {
+    // one warp per column chunk of 32; blockDim = (32, 8): 8 row lanes
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (c < cols)
+        for (int r = threadIdx.y; r < rows; r += 8) s += x[(long long)r * ldx + c];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        for (int k = 1; k < 8; ++k) s += sm[k][threadIdx.x];
+        out[c] = accumulate ? out[c] + s : s;
+    }
+}
+
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                                float* __restrict__ dz, int lddz, long long rows, int cols) {
+    const long long n = rows * cols;
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const int c = (int)(i % cols);
+        const long long r = i / cols;
+        dz[r * lddz + c] = y[r * ldy + c] > 0.f ? dy[r * lddy + c] : 0.f;
+    }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, long long n, float v) {
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) p[i] = v;
+}
+
+__global__ void add_i64_kernel(long long* __restrict__ p, long long n, long long v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem pooling
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ argmax, int B,
+                   int H, int W, int C, int Ho, int Wo) {
+    const int G = C >> 2;
+    const long long n = (long long)B * Ho * Wo * G;
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const int g = (int)(i % G);
+        long long r = i / G;
+        const int wo = (int)(r % Wo);
+        r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        uchar4 am = make_uchar4(255, 255, 255, 255);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int h = 2 * ho - 1 + kh;
+            if (h < 0 || h >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int w = 2 * wo - 1 + kw;
+                if (w < 0 || w >= W) continue;
+                const float4 v = ld4(x + (((long long)b * H + h) * W + w) * C + 4 * g);
+                const unsigned char k = (unsigned char)(kh * 3 + kw);
+                if (v.x > m.x || am.x == 255) { m.x = v.x; am.x = k; }
+                if (v.y > m.y || am.y == 255) { m.y = v.y; am.y = k; }
+                if (v.z > m.z || am.z == 255) { m.z = v.z; am.z = k; }
+                if (v.w > m.w || am.w == 255) { m.w = v.w; am.w = k; }
+            }
+        }
+        st4(y + 4 * i, m);
+        if (argmax) *reinterpret_cast<uchar4*>(argmax + 4 * i) = am;
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ argmax, float* __restrict__ dx,
+                   int accumulate, int B, int H, int W, int C, int Ho, int Wo) {
+    const int G = C >> 2;
+    const long long n = (long long)B * H * W * G;
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const int g = (int)(i % G);
+        long long r = i / G;
+        const int w = (int)(r % W);
+        r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        float4 acc = accumulate ? ld4(dx + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ho_lo = h / 2, ho_hi = (h + 1) / 2;  // windows with 2ho-1 <= h <= 2ho+1
+        const int wo_lo = w / 2, wo_hi = (w + 1) / 2;
+        for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+            if (ho >= Ho) continue;
+            const int kh = h - (2 * ho - 1);
+            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                if (wo >= Wo) continue;
+                const int kw = w - (2 * wo - 1);
+                const unsigned char k = (unsigned char)(kh * 3 + kw);
+                const long long o = (((long long)b * Ho + ho) * Wo + wo) * G + g;
+                const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + 4 * o);
+                const float4 d = ld4(dy + 4 * o);
+                if (am.x == k) acc.x += d.x;
+                if (am.y == k) acc.y += d.y;
+                if (am.z == k) acc.z += d.z;
+                if (am.w == k) acc.w += d.w;
+            }
+        }
+        st4(dx + 4 * i, acc);
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int ldy, int B, int HW, int C, int round_out) {
+    const int G = C >> 2;
+    const long long n = (long long)B * G;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = (int)(i % G);
+    const int b = (int)(i / G);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* p = x + (long long)b * HW * C + 4 * g;
+    for (int k = 0; k < HW; ++k) {
+        const float4 v = ld4(p + (long long)k * C);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float inv = 1.f / (float)HW;
+    s.x *= inv; s.y *= inv; s.z *= inv; s.w *= inv;
+    if (round_out) s = round4(s);
+    st4(y + (long long)b * ldy + 4 * g, s);
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+avgpool_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int B, int HW, int C) {
+    const int G = C >> 2;
+    const long long n = (long long)B * HW * G;
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    const float inv = 1.f / (float)HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const int g = (int)(i % G);
+        const int b = (int)(i / ((long long)HW * G));
+        float4 d = ld4(dy + (long long)b * lddy + 4 * g);
+        d.x *= inv; d.y *= inv; d.z *= inv; d.w *= inv;
+        st4(dx + 4 * i, d);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// auxiliary branch: per-pixel <a1[pixel,:], w> + bias, 2x2 max pool, flatten.  One warp per window.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS)
+aux_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ w, const float* __restrict__ bias,
+               float* __restrict__ out, int ldo, unsigned char* __restrict__ argmax, int B, int H, int W, int C,
+               int round_out) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nwin = (long long)B * Ho * Wo;
+    const float b0 = bias[0];
+    for (long long win = warp; win < nwin; win += nwarps) {
+        const int wo = (int)(win % Wo);
+        const int ho = (int)((win / Wo) % Ho);
+        const int b = (int)(win / ((long long)Wo * Ho));
+        float best = 0.f;
+        int besti = -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int h = 2 * ho + (k >> 1), x = 2 * wo + (k & 1);
+            const float* p = a1 + (((long long)b * H + h) * W + x) * C;
+            float s = 0.f;
+            for (int c = lane; c < C; c += 32) s = fmaf(p[c], w[c], s);
+            s = warp_sum(s) + b0;
+            if (besti < 0 || s > best) {
+                best = s;
+                besti = k;
+            }
+        }
+        if (lane == 0) {
+            out[(long long)b * ldo + ho * Wo + wo] = round_out ? round_tf32(best) : best;
+            if (argmax) argmax[win] = (unsigned char)besti;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __restrict__ argmax,
+               const float* __restrict__ a1, const float* __restrict__ w, float* __restrict__ da1, int accumulate,
+               float* __restrict__ dw, float* __restrict__ db, int B, int H, int W, int C) {
+    // C <= 64*? : each lane owns channels lane, lane+32, ... ; dw partials kept per lane (C <= 128)
+    __shared__ float s_dw[128];
+    __shared__ float s_db;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 128) s_dw[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) s_db = 0.f;
+    __syncthreads();
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nwin = (long long)B * Ho * Wo;
+    float pdw[4] = {0.f, 0.f, 0.f, 0.f};
+    float pdb = 0.f;
+    for (long long win = warp; win < nwin; win += nwarps) {
+        const int wo = (int)(win % Wo);
+        const int ho = (int)((win / Wo) % Ho);
+        const int b = (int)(win / ((long long)Wo * Ho));
+        const float d = dout[(long long)b * lddo + ho * Wo + wo];
+        const int am = argmax[win];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int h = 2 * ho + (k >> 1), x = 2 * wo + (k & 1);
+            const long long off = (((long long)b * H + h) * W + x) * C;
+            const float dk = (k == am) ? d : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = lane + 32 * j;
+                if (c < C) {
+                    const float prev = accumulate ? da1[off + c] : 0.f;
+                    da1[off + c] = prev + dk * w[c];
+                    if (k == am) pdw[j] = fmaf(d, a1[off + c], pdw[j]);
+                }
+            }
+        }
+        pdb += d;
+    }
+    if (dw) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane + 32 * j < C) atomicAdd(&s_dw[lane + 32 * j], pdw[j]);
+        if (lane == 0) atomicAdd(&s_db, pdb);
+        __syncthreads();
+        if (threadIdx.x < C) atomicAdd(dw + threadIdx.x, s_dw[threadIdx.x]);
+        if (threadIdx.x == 0 && db) atomicAdd(db, s_db);
+    }
+}
+
+__global__ void preprocess_u8_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int B, int Hs,
+                                     int Ws, int crop, float m0, float m1, float m2, float i0, float i1, float i2) {
+    const long long n = (long long)B * crop * crop;
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    const int oy = (Hs - crop) / 2, ox = (Ws - crop) / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const int x = (int)(i % crop);
+        const int y = (int)((i / crop) % crop);
+        const int b = (int)(i / ((long long)crop * crop));
+        const unsigned char* p = src + (((long long)b * Hs + (y + oy)) * Ws + (x + ox)) * 3;
+        const long long plane = (long long)crop * crop;
+        float* o = dst + (long long)b * 3 * plane + (long long)y * crop + x;
+        o[0] = ((float)p[0] / 255.f - m0) * i0;
+        o[plane] = ((float)p[1] / 255.f - m1) * i1;
+        o[2 * plane] = ((float)p[2] / 255.f - m2) * i2;
+    }
+}
+
+}  // namespace
+}  // namespace pe
+
+using namespace pe;
+
+extern "C" {
+
+int pe_bn_stats(const float* y, long long P, int C, double* stats, void* stream) {
+    PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
+               "bn_stats: unsupported channel count %d", C);
+    channel_reduce_kernel<0><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        y, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_bn_finalize(double* stats, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   float* scale, float* shift, float* mean, float* invstd, long long count, float momentum,
+                   float eps, int C, void* stream) {
+    PE_REQUIRE(stats || (running_mean && running_var), "bn_finalize: need stats or running statistics");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        stats, gamma, beta, running_mean, running_var, scale, shift, mean, invstd, (double)count, momentum, eps, C);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_bn_apply(const float* y, const float* scale, const float* shift, const float* residual, float* out,
+                long long P, int C, int relu, int round_tf32, void* stream) {
+    PE_REQUIRE(C % 4 == 0, "bn_apply: C %% 4 != 0");
+    const long long n4 = P * (C / 4);
+    bn_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        y, scale, shift, residual, out, n4, C / 4, relu, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_bn_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
+                     double* sums, long long P, int C, int relu, void* stream) {
+    PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
+               "bn_bwd_reduce: unsupported channel count %d", C);
+    channel_reduce_kernel<1><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        dout, out, y, mean, invstd, sums, P, C, relu);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_bn_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
+                    const float* gamma, double* sums, float* dy, float* dres, int dres_accumulate, float* dgamma,
+                    float* dbeta, int param_accumulate, long long P, int C, int relu, void* stream) {
+    PE_REQUIRE(C % 4 == 0 && C <= 4096, "bn_bwd_apply: unsupported channel count %d", C);
+    const long long n4 = P * (C / 4);
+    bn_bwd_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
+        dout, out, y, mean, invstd, gamma, sums, dy, dres, dres_accumulate, dgamma, dbeta, param_accumulate, P, C,
+        relu);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_pack_conv_weight(const float* w_oihw, float* w_tck, float* w_tkc, int Cout, int Cin, int R, int S,
+                        int round_tf32, void* stream) {
+    const long long n = (long long)Cout * Cin * R * S;
+    pack_weight_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        w_oihw, w_tck, w_tkc, Cout, Cin, R * S, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_unpack_conv_wgrad(const float* dw_tck, float* dw_oihw, int Cout, int Cin, int R, int S, int accumulate,
+                         void* stream) {
+    const long long n = (long long)Cout * Cin * R * S;
+    unpack_wgrad_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        dw_tck, dw_oihw, Cout, Cin, R * S, accumulate);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
+                   int ldc, int round_tf32, void* stream) {
+    PE_REQUIRE(ldc >= C * R * S && ldc % 4 == 0, "im2col: ldc %d too small / unaligned", ldc);
+    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+    const long long n = (long long)B * Ho * Wo * ldc;
+    im2col_stem_kernel<<<grid_for(n, EW_THREADS * 4, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        img_nchw, col, B, C, H, W, R, S, stride, pad, Ho, Wo, ldc, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_copy_cols(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream) {
+    const long long n = (long long)rows * cols;
+    if (n == 0) return 0;
+    copy_cols_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows,
+                                                                                       cols, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_colsum(const float* x, int ldx, float* out, int rows, int cols, int accumulate, void* stream) {
+    dim3 grid((cols + 31) / 32), block(32, 8);
+    colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, out, rows, cols, accumulate);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_relu_bwd(const float* dy, int lddy, const float* y, int ldy, float* dz, int lddz, int rows, int cols,
+                void* stream) {
+    const long long n = (long long)rows * cols;
+    if (n == 0) return 0;
+    relu_bwd_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, dz, lddz,
+                                                                                      rows, cols);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_fill(float* p, long long n, float value, void* stream) {
+    if (n == 0) return 0;
+    fill_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(p, n, value);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_add_i64(long long* p, long long n, long long value, void* stream) {
+    if (n == 0) return 0;
+    add_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, n, value);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, int H, int W, int C, void* stream) {
+    PE_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long n = (long long)B * Ho * Wo * (C / 4);
+    maxpool_fwd_kernel<<<grid_for(n, EW_THREADS, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(x, y, argmax, B, H, W,
+                                                                                             C, Ho, Wo);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_maxpool3x3s2_bwd(const float* dy, const unsigned char* argmax, float* dx, int accumulate, int B, int H, int W,
+                        int C, void* stream) {
+    PE_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long n = (long long)B * H * W * (C / 4);
+    maxpool_bwd_kernel<<<grid_for(n, EW_THREADS, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        dy, argmax, dx, accumulate, B, H, W, C, Ho, Wo);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int round_tf32, void* stream) {
+    PE_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "avgpool: C, ldy must be multiples of 4");
+    const long long n = (long long)B * (C / 4);
+    avgpool_fwd_kernel<<<(unsigned)((n + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        x, y, ldy, B, HW, C, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_avgpool_bwd(const float* dy, int lddy, float* dx, int B, int HW, int C, void* stream) {
+    PE_REQUIRE(C % 4 == 0 && lddy % 4 == 0, "avgpool: C, lddy must be multiples of 4");
+    const long long n = (long long)B * HW * (C / 4);
+    avgpool_bwd_kernel<<<grid_for(n, EW_THREADS * 2), EW_THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, B, HW, C);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, int ldo, unsigned char* argmax, int B,
+               int H, int W, int C, int round_tf32, void* stream) {
+    PE_REQUIRE(H % 2 == 0 && W % 2 == 0, "aux: H, W must be even");
+    const long long nwin = (long long)B * (H / 2) * (W / 2);
+    aux_fwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 4, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        a1, w, bias, out, ldo, argmax, B, H, W, C, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const float* a1, const float* w, float* da1,
+               int accumulate, float* dw, float* db, int B, int H, int W, int C, void* stream) {
+    PE_REQUIRE(C <= 128, "aux_bwd: C <= 128 required");
+    const long long nwin = (long long)B * (H / 2) * (W / 2);
+    aux_bwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        dout, lddo, argmax, a1, w, da1, accumulate, dw, db, B, H, W, C);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_preprocess_u8(const unsigned char* src, float* dst, int B, int Hs, int Ws, int crop, const float* mean3,
+                     const float* std3, void* stream) {
+    PE_REQUIRE(crop <= Hs && crop <= Ws, "preprocess: crop larger than frame");
+    const long long n = (long long)B * crop * crop;
+    preprocess_u8_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        src, dst, B, Hs, Ws, crop, mean3[0], mean3[1], mean3[2], 1.f / std3[0], 1.f / std3[1], 1.f / std3[2]);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

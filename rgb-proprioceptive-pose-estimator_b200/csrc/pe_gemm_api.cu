@@ -1,0 +1,526 @@
+// Host side of the tap-GEMM: TMA tensor-map construction, pixel-box selection, and the C-ABI
+// entry points for convolution forward / dgrad / wgrad and linear layers (see include/pe_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "../../include/pe_b200.h"
+#include "pe_tapgemm.cuh"
+
+namespace pe {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            n = 148;
+    }
+    return n;
+}
+
+static int* g_error_flag = nullptr;  // device int, sticky; read by pe_device_error()
+static int ensure_error_flag() {
+    if (!g_error_flag) {
+        PE_CHECK_CUDA(cudaMalloc(&g_error_flag, sizeof(int)));
+        PE_CHECK_CUDA(cudaMemset(g_error_flag, 0, sizeof(int)));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int ensure_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PE_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PE_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+               "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+// fp32 tensor, 4 dims (d0 contiguous), strides in ELEMENTS for dims 1..3, SWIZZLE_128B.
+static int make_map(CUtensorMap* m, const void* base, const long long dims[4], const long long strides[3],
+                    const int box[4]) {
+    if (ensure_encode()) return 1;
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) {
+        gd[i] = static_cast<cuuint64_t>(dims[i] > 0 ? dims[i] : 1);
+        bx[i] = static_cast<cuuint32_t>(box[i]);
+        PE_REQUIRE(box[i] >= 1 && box[i] <= 256, "TMA box dim %d = %d out of range", i, box[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        gs[i] = static_cast<cuuint64_t>(strides[i]) * 4ull;
+        PE_REQUIRE(gs[i] % 16 == 0, "TMA stride %d = %llu B is not a multiple of 16", i,
+                   (unsigned long long)gs[i]);
+    }
+    PE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
+    PE_REQUIRE(box[0] * 4 <= 128 && (box[0] * 4) % 16 == 0, "TMA inner box %d elems invalid", box[0]);
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd, gs, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PE_REQUIRE(r == CUDA_SUCCESS,
+               "cuTensorMapEncodeTiled failed (%d): dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d %d",
+               (int)r, dims[0], dims[1], dims[2], dims[3], strides[0], strides[1], strides[2], box[0], box[1],
+               box[2], box[3]);
+    return 0;
+}
+
+// NHWC activation view (optionally one stride-2 parity plane), channels innermost.
+static int make_nhwc_map(CUtensorMap* m, const float* base, int N, int H, int W, int C, int ph, int pw,
+                         int step, const int box[4]) {
+    const long long dims[4] = {C, (W - pw + step - 1) / step, (H - ph + step - 1) / step, N};
+    const long long strides[3] = {(long long)step * C, (long long)step * W * C, (long long)H * W * C};
+    return make_map(m, base + ((long long)ph * W + pw) * C, dims, strides, box);
+}
+
+// Pick a (bw, bh, bn) pixel box with bw*bh*bn <= target that tiles (W, H, N) with the fewest boxes.
+static void choose_box(int W, int H, int N, int target, int* obw, int* obh, int* obn) {
+    static std::map<std::tuple<int, int, int, int>, std::tuple<int, int, int>> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple(W, H, N, target);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        long long best = -1;
+        int bbw = 1, bbh = 1, bbn = 1;
+        for (int bw = 1; bw <= W && bw <= target; ++bw) {
+            for (int bh = 1; bh <= H && bw * bh <= target; ++bh) {
+                int bn = target / (bw * bh);
+                if (bn > N) bn = N;
+                if (bn < 1) bn = 1;
+                if (bn > 256 || bw > 256 || bh > 256) continue;
+                long long tiles = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((N + bn - 1) / bn);
+                // fewest tiles; ties -> widest rows (better DRAM locality)
+                if (best < 0 || tiles < best || (tiles == best && bw > bbw)) {
+                    best = tiles;
+                    bbw = bw;
+                    bbh = bh;
+                    bbn = bn;
+                }
+            }
+        }
+        it = cache.emplace(key, std::make_tuple(bbw, bbh, bbn)).first;
+    }
+    *obw = std::get<0>(it->second);
+    *obh = std::get<1>(it->second);
+    *obn = std::get<2>(it->second);
+}
+
+static int g_dbg_desc[4] = {-1, -1, -1, -1};
+
+static void init_params(TapParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.ksplit = 1;
+    p.dbg_a_lbo = g_dbg_desc[0];
+    p.dbg_a_sbo = g_dbg_desc[1];
+    p.dbg_b_lbo = g_dbg_desc[2];
+    p.dbg_b_sbo = g_dbg_desc[3];
+    p.error_flag = g_error_flag;
+}
+
+static int pick_bn(int n_total) { return n_total >= 128 ? 128 : ((n_total + 15) / 16) * 16; }
+
+struct Epilogue {
+    const float* bias = nullptr;
+    const float* scale = nullptr;
+    const float* shift = nullptr;
+    const float* residual = nullptr;
+    int relu = 0, round_out = 0;
+    double* stats = nullptr;
+};
+
+// Filter taps of a convolution as (plane, dh, dw) shifts on stride-`stride` parity planes.
+// fwd / wgrad:  in[ho*stride + r - pad]  ->  plane ph = (r-pad) mod stride, shift (r-pad-ph)/stride
+static int fill_taps_fwd(TapParams& p, int R, int S, int stride, int pad) {
+    PE_REQUIRE(R * S <= TG_MAX_TAPS, "too many filter taps (%d)", R * S);
+    PE_REQUIRE(stride == 1 || stride == 2, "stride %d unsupported", stride);
+    int t = 0;
+    for (int r = 0; r < R; ++r)
+        for (int s = 0; s < S; ++s, ++t) {
+            const int orr = r - pad, oss = s - pad;
+            const int ph = ((orr % stride) + stride) % stride, pw = ((oss % stride) + stride) % stride;
+            p.tap_dh[t] = (signed char)((orr - ph) / stride);
+            p.tap_dw[t] = (signed char)((oss - pw) / stride);
+            p.tap_map[t] = (signed char)(stride == 1 ? 0 : ph * 2 + pw);
+            p.tap_b[t] = (signed char)t;
+        }
+    p.n_taps = t;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// convolution forward:  y[n,ho,wo,co] = sum x[n, ho*s + r - pad, wo*s + q - pad, ci] * w[t][co][ci]
+// ---------------------------------------------------------------------------------------------
+static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, int H, int W, int Cin,
+                         int Cout, int R, int S, int stride, int pad, const Epilogue& ep,
+                         cudaStream_t stream) {
+    if (ensure_error_flag()) return 2;
+    PE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "conv channels must be multiples of 4 (Cin=%d Cout=%d)", Cin, Cout);
+    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+    TapMaps maps;
+    TapParams p;
+    init_params(p);
+    p.mode = 0;
+    p.bn = pick_bn(Cout);
+    choose_box(Wo, Ho, B, TG_BM, &p.box_w, &p.box_h, &p.box_n);
+    p.m_rows = p.box_w * p.box_h * p.box_n;
+    p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
+    p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
+    p.tiles_n = (B + p.box_n - 1) / p.box_n;
+    p.out_w = Wo;
+    p.out_h = Ho;
+    p.out_n = B;
+    p.chunks = (Cin + TG_BK - 1) / TG_BK;
+    if (fill_taps_fwd(p, R, S, stride, pad)) return 1;
+    const int box[4] = {TG_BK, p.box_w, p.box_h, p.box_n};
+    if (stride == 1) {
+        if (make_nhwc_map(&maps.a[0], x, B, H, W, Cin, 0, 0, 1, box)) return 1;
+    } else {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw)
+                if (make_nhwc_map(&maps.a[ph * 2 + pw], x, B, H, W, Cin, ph, pw, 2, box)) return 1;
+    }
+    {
+        const long long dims[4] = {Cin, Cout, (long long)R * S, 1};
+        const long long strides[3] = {Cin, (long long)Cin * Cout, (long long)Cin * Cout * R * S};
+        const int bbox[4] = {TG_BK, p.bn, 1, 1};
+        if (make_map(&maps.b[0], w_tck, dims, strides, bbox)) return 1;
+    }
+    if (make_nhwc_map(&maps.d, y, B, Ho, Wo, Cout, 0, 0, 1, box)) return 1;
+    p.n_total = Cout;
+    p.store_mode = TG_STORE_TMA;
+    p.bias = ep.bias;
+    p.scale = ep.scale;
+    p.shift = ep.shift;
+    p.residual = ep.residual;
+    p.ld_res = Cout;
+    p.relu = ep.relu;
+    p.round_out = ep.round_out;
+    p.stats = ep.stats;
+    dim3 grid((Cout + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
+    return launch_tapgemm(maps, p, grid, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// convolution dgrad: dx[n,hi,wi,ci] = sum dy[n,ho,wo,co] * w[t][co][ci], hi = ho*s + r - pad
+// `w_tkc` is the transposed pack [tap][Cin][Cout] so both operands stay K-major.
+// ---------------------------------------------------------------------------------------------
+static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin,
+                           int Cout, int R, int S, int stride, int pad, cudaStream_t stream) {
+    if (ensure_error_flag()) return 2;
+    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+    PE_REQUIRE(stride == 1 || stride == 2, "stride %d unsupported", stride);
+    PE_REQUIRE(R * S <= TG_MAX_TAPS, "too many filter taps");
+    bool need_zero = false;
+    for (int ph = 0; ph < stride; ++ph)
+        for (int pw = 0; pw < stride; ++pw) {
+            int cnt = 0;
+            for (int r = 0; r < R; ++r)
+                for (int s = 0; s < S; ++s)
+                    if ((ph + pad - r) % stride == 0 && (pw + pad - s) % stride == 0) ++cnt;
+            if (cnt == 0) need_zero = true;
+        }
+    if (need_zero) PE_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * H * W * Cin, stream));
+
+    for (int ph = 0; ph < stride; ++ph)
+        for (int pw = 0; pw < stride; ++pw) {
+            TapMaps maps;
+            TapParams p;
+            init_params(p);
+            p.mode = 0;
+            p.bn = pick_bn(Cin);
+            const int Hp = (H - ph + stride - 1) / stride, Wp = (W - pw + stride - 1) / stride;
+            int t = 0;
+            for (int r = 0; r < R; ++r)
+                for (int s = 0; s < S; ++s) {
+                    const int ah = ph + pad - r, aw = pw + pad - s;
+                    if (ah % stride != 0 || aw % stride != 0) continue;
+                    p.tap_dh[t] = (signed char)(ah / stride);
+                    p.tap_dw[t] = (signed char)(aw / stride);
+                    p.tap_map[t] = 0;
+                    p.tap_b[t] = (signed char)(r * S + s);
+                    ++t;
+                }
+            if (t == 0) continue;
+            p.n_taps = t;
+            choose_box(Wp, Hp, B, TG_BM, &p.box_w, &p.box_h, &p.box_n);
+            p.m_rows = p.box_w * p.box_h * p.box_n;
+            p.tiles_w = (Wp + p.box_w - 1) / p.box_w;
+            p.tiles_h = (Hp + p.box_h - 1) / p.box_h;
+            p.tiles_n = (B + p.box_n - 1) / p.box_n;
+            p.out_w = Wp;
+            p.out_h = Hp;
+            p.out_n = B;
+            p.chunks = (Cout + TG_BK - 1) / TG_BK;
+            const int box[4] = {TG_BK, p.box_w, p.box_h, p.box_n};
+            if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, box)) return 1;
+            const long long dims[4] = {Cout, Cin, (long long)R * S, 1};
+            const long long strides[3] = {Cout, (long long)Cin * Cout, (long long)Cin * Cout * R * S};
+            const int bbox[4] = {TG_BK, p.bn, 1, 1};
+            if (make_map(&maps.b[0], w_tkc, dims, strides, bbox)) return 1;
+            if (make_nhwc_map(&maps.d, dx, B, H, W, Cin, ph, pw, stride, box)) return 1;
+            p.n_total = Cin;
+            p.store_mode = TG_STORE_TMA;
+            dim3 grid((Cin + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
+            if (launch_tapgemm(maps, p, grid, stream)) return 2;
+        }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// convolution wgrad: dw[t][co][ci] = sum_pixels dy[n,ho,wo,co] * x[n, ho*s + r - pad, wo*s + q - pad, ci]
+// Reduction over pixels is split across CTAs and combined with fp32 atomics into a zeroed dw.
+// ---------------------------------------------------------------------------------------------
+static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin,
+                           int Cout, int R, int S, int stride, int pad, cudaStream_t stream) {
+    if (ensure_error_flag()) return 2;
+    PE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "conv channels must be multiples of 4");
+    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+    TapMaps maps;
+    TapParams p;
+    init_params(p);
+    p.mode = 1;
+    p.bn = Cin >= 128 ? 128 : ((Cin + 31) / 32) * 32;
+    p.m_rows = TG_BM;
+    choose_box(Wo, Ho, B, TG_BK, &p.box_w, &p.box_h, &p.box_n);
+    p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
+    p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
+    p.tiles_n = (B + p.box_n - 1) / p.box_n;
+    p.pt_total = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.out_w = Wo;
+    p.out_h = Ho;
+    p.out_n = B;
+    if (fill_taps_fwd(p, R, S, stride, pad)) return 1;
+    const int box[4] = {32, p.box_w, p.box_h, p.box_n};
+    if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, box)) return 1;
+    if (stride == 1) {
+        if (make_nhwc_map(&maps.b[0], x, B, H, W, Cin, 0, 0, 1, box)) return 1;
+    } else {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw)
+                if (make_nhwc_map(&maps.b[ph * 2 + pw], x, B, H, W, Cin, ph, pw, 2, box)) return 1;
+    }
+    p.m_total = Cout;
+    p.n_total = Cin;
+    p.out = dw_tck;
+    p.out_tap_stride = (long long)Cout * Cin;
+    p.ldo = Cin;
+    const int mt = (Cout + TG_BM - 1) / TG_BM, nt = (Cin + p.bn - 1) / p.bn;
+    const int base_ctas = mt * nt * p.n_taps;
+    int ks = (4 * num_sms() + base_ctas - 1) / base_ctas;
+    if (ks > p.pt_total) ks = p.pt_total;
+    if (ks < 1) ks = 1;
+    // every split must own at least one pixel tile
+    while (ks > 1 && (long long)(ks - 1) * ((p.pt_total + ks - 1) / ks) >= p.pt_total) --ks;
+    p.ksplit = ks;
+    p.store_mode = ks > 1 ? TG_STORE_ATOMIC : TG_STORE_DIRECT;
+    if (ks > 1)
+        PE_CHECK_CUDA(cudaMemsetAsync(dw_tck, 0, sizeof(float) * (size_t)R * S * Cout * Cin, stream));
+    dim3 grid(nt, mt, p.n_taps * ks);
+    return launch_tapgemm(maps, p, grid, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense layers:  y[M,N] = x[M,K] * w[N,K]^T (+bias)(relu) ;  dw[N,K] = dy[M,N]^T x[M,K]
+// ---------------------------------------------------------------------------------------------
+static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, float* y, int ldy, int M, int N,
+                           int K, const Epilogue& ep, int accumulate_into_y, cudaStream_t stream) {
+    if (ensure_error_flag()) return 2;
+    PE_REQUIRE(ldx % 4 == 0 && ldw % 4 == 0, "linear: ldx/ldw must be multiples of 4 (got %d, %d)", ldx, ldw);
+    TapMaps maps;
+    TapParams p;
+    init_params(p);
+    p.mode = 0;
+    p.bn = pick_bn(N);
+    p.box_w = TG_BM;
+    p.box_h = p.box_n = 1;
+    p.m_rows = TG_BM;
+    p.tiles_w = (M + TG_BM - 1) / TG_BM;
+    p.tiles_h = p.tiles_n = 1;
+    p.out_w = M;
+    p.out_h = p.out_n = 1;
+    p.n_taps = 1;
+    p.chunks = (K + TG_BK - 1) / TG_BK;
+    {
+        const long long dims[4] = {K, M, 1, 1};
+        const long long strides[3] = {ldx, (long long)ldx * M, (long long)ldx * M};
+        const int box[4] = {TG_BK, TG_BM, 1, 1};
+        if (make_map(&maps.a[0], x, dims, strides, box)) return 1;
+    }
+    {
+        const long long dims[4] = {K, N, 1, 1};
+        const long long strides[3] = {ldw, (long long)ldw * N, (long long)ldw * N};
+        const int box[4] = {TG_BK, p.bn, 1, 1};
+        if (make_map(&maps.b[0], w, dims, strides, box)) return 1;
+    }
+    p.n_total = N;
+    p.bias = ep.bias;
+    p.scale = ep.scale;
+    p.shift = ep.shift;
+    p.relu = ep.relu;
+    p.round_out = ep.round_out;
+    p.stats = ep.stats;
+    p.out = y;
+    p.ldo = ldy;
+    if (accumulate_into_y) {
+        p.residual = y;
+        p.ld_res = ldy;
+    } else if (ep.residual) {
+        p.residual = ep.residual;
+        p.ld_res = ldy;
+    }
+    const bool tma_ok = (ldy % 4 == 0) && (N % 4 == 0) && !accumulate_into_y && !(p.residual && (ldy % 4));
+    if (tma_ok) {
+        const long long dims[4] = {N, M, 1, 1};
+        const long long strides[3] = {ldy, (long long)ldy * M, (long long)ldy * M};
+        const int box[4] = {32, TG_BM, 1, 1};
+        if (make_map(&maps.d, y, dims, strides, box)) return 1;
+        p.store_mode = TG_STORE_TMA;
+    } else {
+        PE_REQUIRE(!p.residual || (ldy % 4 == 0 && N % 4 == 0),
+                   "linear: residual/accumulate needs N and ldy multiples of 4");
+        p.store_mode = TG_STORE_DIRECT;
+    }
+    dim3 grid((N + p.bn - 1) / p.bn, p.tiles_w, 1);
+    return launch_tapgemm(maps, p, grid, stream);
+}
+
+static int linear_wgrad_impl(const float* x, int ldx, const float* dy, int lddy, float* dw, int lddw, int M,
+                             int N, int K, cudaStream_t stream) {
+    if (ensure_error_flag()) return 2;
+    PE_REQUIRE(ldx % 4 == 0 && lddy % 4 == 0, "linear wgrad: ldx/lddy must be multiples of 4");
+    TapMaps maps;
+    TapParams p;
+    init_params(p);
+    p.mode = 1;
+    p.bn = K >= 128 ? 128 : ((K + 31) / 32) * 32;
+    p.m_rows = TG_BM;
+    p.box_w = TG_BK;
+    p.box_h = p.box_n = 1;
+    p.tiles_w = (M + TG_BK - 1) / TG_BK;
+    p.tiles_h = p.tiles_n = 1;
+    p.pt_total = p.tiles_w;
+    p.out_w = M;
+    p.out_h = p.out_n = 1;
+    p.n_taps = 1;
+    {
+        const long long dims[4] = {N, M, 1, 1};
+        const long long strides[3] = {lddy, (long long)lddy * M, (long long)lddy * M};
+        const int box[4] = {32, TG_BK, 1, 1};
+        if (make_map(&maps.a[0], dy, dims, strides, box)) return 1;
+    }
+    {
+        const long long dims[4] = {K, M, 1, 1};
+        const long long strides[3] = {ldx, (long long)ldx * M, (long long)ldx * M};
+        const int box[4] = {32, TG_BK, 1, 1};
+        if (make_map(&maps.b[0], x, dims, strides, box)) return 1;
+    }
+    p.m_total = N;
+    p.n_total = K;
+    p.out = dw;
+    p.out_tap_stride = 0;
+    p.ldo = lddw;
+    const int mt = (N + TG_BM - 1) / TG_BM, nt = (K + p.bn - 1) / p.bn;
+    int ks = (2 * num_sms() + mt * nt - 1) / (mt * nt);
+    if (ks > p.pt_total) ks = p.pt_total;
+    if (ks < 1) ks = 1;
+    while (ks > 1 && (long long)(ks - 1) * ((p.pt_total + ks - 1) / ks) >= p.pt_total) --ks;
+    p.ksplit = ks;
+    p.store_mode = ks > 1 ? TG_STORE_ATOMIC : TG_STORE_DIRECT;
+    if (ks > 1) PE_CHECK_CUDA(cudaMemset2DAsync(dw, sizeof(float) * lddw, 0, sizeof(float) * K, N, stream));
+    dim3 grid(nt, mt, ks);
+    return launch_tapgemm(maps, p, grid, stream);
+}
+
+}  // namespace pe
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace pe;
+
+extern "C" {
+
+const char* pe_last_error(void) { return pe::get_error(); }
+
+int pe_version(void) { return 100; }
+
+void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
+    g_dbg_desc[0] = a_lbo;
+    g_dbg_desc[1] = a_sbo;
+    g_dbg_desc[2] = b_lbo;
+    g_dbg_desc[3] = b_sbo;
+}
+
+int pe_device_error(void) {
+    if (!g_error_flag) return 0;
+    int v = 0;
+    if (cudaMemcpy(&v, g_error_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return v;
+}
+
+int pe_conv2d_fwd(const float* x, const float* w_tck, float* y, int B, int H, int W, int Cin, int Cout, int R,
+                  int S, int stride, int pad, const float* scale, const float* shift, const float* residual,
+                  int relu, int round_out, double* stats, void* stream) {
+    Epilogue ep;
+    ep.scale = scale;
+    ep.shift = shift;
+    ep.residual = residual;
+    ep.relu = relu;
+    ep.round_out = round_out;
+    ep.stats = stats;
+    return conv_fwd_impl(x, w_tck, y, B, H, W, Cin, Cout, R, S, stride, pad, ep, (cudaStream_t)stream);
+}
+
+int pe_conv2d_dgrad(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin, int Cout,
+                    int R, int S, int stride, int pad, void* stream) {
+    return conv_dgrad_impl(dy, w_tkc, dx, B, H, W, Cin, Cout, R, S, stride, pad, (cudaStream_t)stream);
+}
+
+int pe_conv2d_wgrad(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin, int Cout,
+                    int R, int S, int stride, int pad, void* stream) {
+    return conv_wgrad_impl(x, dy, dw_tck, B, H, W, Cin, Cout, R, S, stride, pad, (cudaStream_t)stream);
+}
+
+int pe_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy, int M,
+                  int N, int K, int relu, int accumulate, int round_out, void* stream) {
+    Epilogue ep;
+    ep.bias = bias;
+    ep.relu = relu;
+    ep.round_out = round_out;
+    return linear_fwd_impl(x, ldx, w, ldw, y, ldy, M, N, K, ep, accumulate, (cudaStream_t)stream);
+}
+
+int pe_linear_wgrad(const float* x, int ldx, const float* dy, int lddy, float* dw, int lddw, int M, int N, int K,
+                    void* stream) {
+    return linear_wgrad_impl(x, ldx, dy, lddy, dw, lddw, M, N, K, (cudaStream_t)stream);
+}
+
+}  // extern "C"

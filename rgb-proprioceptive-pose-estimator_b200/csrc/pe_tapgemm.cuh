@@ -1,0 +1,69 @@
+// Tap-GEMM: the one tcgen05/TMEM/TMA kernel behind every dense contraction on the path.
+//
+//   mode 0 ("conv"):  D[pixels, N] = sum_taps sum_k  A_tap[pixels, k] * B_tap[N, k]
+//                     A, B K-major in shared memory (rows of 128 B = 32 tf32 along K).
+//                     A rows are a 4-D TMA box of output pixels (w, h, n) shifted per filter tap;
+//                     zero padding comes from TMA out-of-bounds fill.  Plain GEMMs (1x1 convs,
+//                     linear layers, LSTM projections) are the 1-tap, 1-D-box special case.
+//   mode 1 ("wgrad"): D[M, N] = sum_pixels A[pixel, M]^T * B[pixel+tap, N]
+//                     A (dY) and B (X) MN-major in shared memory: the reduction runs over pixels.
+//
+// One CTA = one 128 x bn output tile; warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store, with optional
+// bias / scale-shift / residual / ReLU / TF32 rounding / per-channel batch statistics).
+#pragma once
+#include "pe_common.cuh"
+
+namespace pe {
+
+constexpr int TG_BM = 128;                     // tile rows  (TMEM lanes)
+constexpr int TG_BK = 32;                      // tf32 elements per k-step (128 B swizzle span)
+constexpr int TG_MAX_BN = 128;                 // tile columns (TMEM columns)
+constexpr int TG_STAGES = 3;
+constexpr int TG_A_BYTES = TG_BM * 128;        // 16 KB
+constexpr int TG_B_BYTES = TG_MAX_BN * 128;    // 16 KB
+constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
+constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 1024;  // + alignment slack
+constexpr int TG_THREADS = 192;
+constexpr int TG_MAX_TAPS = 16;
+
+enum TgStore { TG_STORE_TMA = 0, TG_STORE_DIRECT = 1, TG_STORE_ATOMIC = 2 };
+
+struct alignas(64) TapMaps {
+    CUtensorMap a[4];
+    CUtensorMap b[4];
+    CUtensorMap d;
+};
+
+struct TapParams {
+    int mode;                 // 0 conv / gemm, 1 wgrad
+    int bn;                   // MMA N (multiple of 16; multiple of 32 in wgrad mode)
+    int m_rows;               // rows the A box really fills (<= 128)
+    int box_w, box_h, box_n;  // pixel box (conv: product = m_rows; wgrad: product = 32)
+    int tiles_w, tiles_h, tiles_n;
+    int out_w, out_h, out_n;  // valid extents of the pixel grid the boxes tile
+    int n_taps, chunks;       // conv: k-steps = n_taps * chunks
+    int ksplit;               // K splits (conv: gridDim.z; wgrad: per tap)
+    int pt_total;             // wgrad: number of 32-pixel tiles
+    int m_total, n_total;     // logical output extents (wgrad rows; columns in both modes)
+    signed char tap_dw[TG_MAX_TAPS], tap_dh[TG_MAX_TAPS], tap_map[TG_MAX_TAPS], tap_b[TG_MAX_TAPS];
+    int store_mode;
+    float* out;               // direct / atomic destination
+    long long out_tap_stride; // wgrad: elements between taps in `out`
+    int ldo;                  // row stride of `out` in elements
+    const float* bias;        // [n_total] or null
+    const float* scale;       // [n_total] or null  (v = acc*scale + shift)
+    const float* shift;
+    const float* residual;    // same indexing as a dense NHWC output, row stride ld_res
+    int ld_res;
+    int relu;
+    int round_out;            // round result to tf32 (rna) so the consumer's truncation is exact
+    double* stats;            // [2][n_total]: sum, sum of squares of the raw accumulator
+    int* error_flag;
+    // debug overrides for the smem descriptors (bytes, <0 = default)
+    int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;
+};
+
+int launch_tapgemm(const TapMaps& maps, const TapParams& p, dim3 grid, cudaStream_t stream);
+
+}  // namespace pe

@@ -1,0 +1,128 @@
+"""ctypes binding of libpe_b200.so (the C ABI declared in include/pe_b200.h).
+
+The prototypes are parsed from the header itself so the Python side can never drift from the C
+side.  There is deliberately NO fallback: if the shared library is missing or a call fails, the
+caller gets an exception -- the product path never routes around the CUDA kernels.
+"""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_ROOT = os.path.dirname(_HERE)                    # rgb-proprioceptive-pose-estimator_b200/
+_REPO_ROOT = os.path.dirname(_PKG_ROOT)
+HEADER = os.path.join(_REPO_ROOT, "include", "pe_b200.h")
+CSRC = os.path.join(_PKG_ROOT, "csrc")
+LIB_PATH = os.path.join(_HERE, "libpe_b200.so")
+SOURCES = ["pe_tapgemm.cu", "pe_gemm_api.cu", "pe_elementwise.cu", "pe_head.cu"]
+
+_CTYPE = {
+    "int": ctypes.c_int,
+    "long long": ctypes.c_longlong,
+    "float": ctypes.c_float,
+    "double": ctypes.c_double,
+    "void": None,
+}
+
+
+def parse_header(path=HEADER):
+    """Return {name: (restype, [argtypes])} for every prototype in the header."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"(const\s+char\s*\*|int|void)\s+(pe_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        restype = ctypes.c_char_p if "char" in ret else _CTYPE[ret.strip()]
+        argtypes = []
+        args = " ".join(args.split())
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    base = re.sub(r"\b\w+$", "", a).replace("const", "").replace("unsigned", "").strip()
+                    argtypes.append(_CTYPE[base])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+def nvcc_command(out=LIB_PATH):
+    return (["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+             "-Xcompiler", "-fPIC", "-shared", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES])
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA sources into libpe_b200.so next to this file (sm_100a only)."""
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [HEADER]
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
+            return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+class PeError(RuntimeError):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise PeError(
+                "libpe_b200.so is missing (%s). Build it with `python __graft_entry__.py build` or "
+                "pe_b200.native.build(); there is no CPU / eager fallback for this path." % LIB_PATH)
+        self._dll = ctypes.CDLL(LIB_PATH)
+        self.protos = parse_header()
+        for name, (restype, argtypes) in self.protos.items():
+            fn = getattr(self._dll, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        for name, (restype, _) in self.protos.items():
+            raw = getattr(self._dll, name)
+            if restype is ctypes.c_int and name not in ("pe_version", "pe_device_error"):
+                setattr(self, name, self._checked(name, raw))
+            else:
+                setattr(self, name, raw)
+
+    def _checked(self, name, raw):
+        last_error = self._dll.pe_last_error
+
+        def call(*args):
+            rc = raw(*args)
+            if rc != 0:
+                raise PeError("%s failed (%d): %s" % (name, rc, (last_error() or b"").decode()))
+            return 0
+
+        call.__name__ = name
+        return call
+
+    def check_device(self):
+        code = self.pe_device_error()
+        if code != 0:
+            raise PeError("device-side pipeline error flag = %d (tcgen05/TMA pipeline timed out)" % code)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _Lib()
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,488 @@
+"""Per-kernel numerical checks of libpe_b200.so against plain torch references (GPU only).
+
+Each check returns a list of (name, error, tolerance).  `tests/test_kernels_gpu.py` asserts on them;
+`python tests/kernel_checks.py` prints the whole table without stopping at the first failure
+(handy for one-shot GPU sessions).
+
+Tensor-core kernels are compared against an fp64 reference computed from TF32-rounded inputs, so
+the tolerance only has to cover fp32 accumulation order (1e-4 relative to the output scale).
+"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "rgb-proprioceptive-pose-estimator_b200"))
+
+from pe_b200 import native  # noqa: E402
+
+DEV = "cuda"
+
+
+def tf32(x):
+    """Round fp32 to TF32 (10-bit mantissa), round-to-nearest, ties away from zero (cvt.rna)."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def relerr(a, b):
+    a = a.double()
+    b = b.double()
+    denom = b.abs().max().clamp_min(1e-30)
+    return float((a - b).abs().max() / denom)
+
+
+def S():
+    return native.stream_ptr()
+
+
+def P(t):
+    return native.ptr(t)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+def check_linear(M, N, K, relu=False, bias=True, ldpad=0):
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(M * 131 + N * 7 + K)
+    ldx = K + ldpad
+    x = tf32(torch.randn(M, ldx, device=DEV, generator=g))
+    w = tf32(torch.randn(N, ldx, device=DEV, generator=g))
+    b = torch.randn(N, device=DEV, generator=g) if bias else None
+    ldy = ((N + 3) // 4) * 4
+    y = torch.full((M, ldy), float("nan"), device=DEV)
+    L.pe_linear_fwd(P(x), ldx, P(w), ldx, P(b), P(y), ldy, M, N, K, int(relu), 0, 0, S())
+    ref = x[:, :K].double() @ w[:, :K].double().t()
+    if bias:
+        ref = ref + b.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    return [("linear_fwd M%d N%d K%d relu%d" % (M, N, K, relu), relerr(y[:, :N], ref), 1e-4)]
+
+
+def check_linear_acc(M, N, K):
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = tf32(torch.randn(M, K, device=DEV, generator=g))
+    w = tf32(torch.randn(N, K, device=DEV, generator=g))
+    y0 = torch.randn(M, N, device=DEV, generator=g)
+    y = y0.clone()
+    L.pe_linear_fwd(P(x), K, P(w), K, None, P(y), N, M, N, K, 0, 1, 0, S())
+    ref = y0.double() + x.double() @ w.double().t()
+    return [("linear_fwd accumulate M%d N%d K%d" % (M, N, K), relerr(y, ref), 1e-4)]
+
+
+def check_linear_wgrad(M, N, K):
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    ldx = ((K + 3) // 4) * 4
+    lddy = ((N + 3) // 4) * 4
+    x = tf32(torch.randn(M, ldx, device=DEV, generator=g))
+    dy = tf32(torch.randn(M, lddy, device=DEV, generator=g))
+    dw = torch.full((N, ldx), float("nan"), device=DEV)
+    L.pe_linear_wgrad(P(x), ldx, P(dy), lddy, P(dw), ldx, M, N, K, S())
+    ref = dy[:, :N].double().t() @ x[:, :K].double()
+    return [("linear_wgrad M%d N%d K%d" % (M, N, K), relerr(dw[:, :K], ref), 1e-4)]
+
+
+def pack(w, L=None):
+    L = L or native.lib()
+    Cout, Cin, R, S_ = w.shape
+    tck = torch.empty(R * S_, Cout, Cin, device=DEV)
+    tkc = torch.empty(R * S_, Cin, Cout, device=DEV)
+    L.pe_pack_conv_weight(P(w.contiguous()), P(tck), P(tkc), Cout, Cin, R, S_, 0, S())
+    return tck, tkc
+
+
+def check_conv(B, H, W, Cin, Cout, k, stride):
+    L = native.lib()
+    pad = (k - 1) // 2
+    g = torch.Generator(device=DEV).manual_seed(B + H + Cin + Cout + k + stride)
+    x = tf32(torch.randn(B, Cin, H, W, device=DEV, generator=g))
+    w = tf32(torch.randn(Cout, Cin, k, k, device=DEV, generator=g) / (Cin * k * k) ** 0.5)
+    xd = x.double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    yd = F.conv2d(xd, wd, stride=stride, padding=pad)
+    Ho, Wo = yd.shape[2], yd.shape[3]
+    dy = tf32(torch.randn(B, Cout, Ho, Wo, device=DEV, generator=g))
+    gx, gw = torch.autograd.grad(yd, (xd, wd), dy.double())
+
+    tag = "B%d %dx%d %d->%d k%d s%d" % (B, H, W, Cin, Cout, k, stride)
+    out = []
+    tck, tkc = pack(w)
+    # pack round trip
+    out.append(("pack tck " + tag, relerr(tck, w.permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)), 0.0))
+    out.append(("pack tkc " + tag, relerr(tkc, w.permute(2, 3, 1, 0).reshape(k * k, Cin, Cout)), 0.0))
+
+    x_n = nhwc(x)
+    y = torch.full((B, Ho, Wo, Cout), float("nan"), device=DEV)
+    stats = torch.zeros(2 * Cout, device=DEV, dtype=torch.float64)
+    L.pe_conv2d_fwd(P(x_n), P(tck), P(y), B, H, W, Cin, Cout, k, k, stride, pad, None, None, None, 0, 0,
+                    P(stats), S())
+    y_ref = nhwc(yd.detach())
+    out.append(("conv_fwd " + tag, relerr(y, y_ref), 1e-4))
+    s_ref = torch.cat([y_ref.sum((0, 1, 2)), (y_ref * y_ref).sum((0, 1, 2))])
+    out.append(("conv_fwd stats " + tag, relerr(stats, s_ref), 1e-5))
+
+    dy_n = nhwc(dy)
+    dx = torch.full((B, H, W, Cin), float("nan"), device=DEV)
+    L.pe_conv2d_dgrad(P(dy_n), P(tkc), P(dx), B, H, W, Cin, Cout, k, k, stride, pad, S())
+    out.append(("conv_dgrad " + tag, relerr(dx, nhwc(gx)), 1e-4))
+
+    dw = torch.full((k * k, Cout, Cin), float("nan"), device=DEV)
+    L.pe_conv2d_wgrad(P(x_n), P(dy_n), P(dw), B, H, W, Cin, Cout, k, k, stride, pad, S())
+    out.append(("conv_wgrad " + tag, relerr(dw, gw.permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)), 1e-4))
+    dw_oihw = torch.empty(Cout, Cin, k, k, device=DEV)
+    L.pe_unpack_conv_wgrad(P(dw), P(dw_oihw), Cout, Cin, k, k, 0, S())
+    out.append(("unpack wgrad " + tag, relerr(dw_oihw, gw), 1e-4))
+    return out
+
+
+def check_conv_fused_eval(B, H, W, Cin, Cout, k):
+    """eval-mode epilogue: relu(acc*scale + shift + residual)."""
+    L = native.lib()
+    pad = (k - 1) // 2
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = tf32(torch.randn(B, Cin, H, W, device=DEV, generator=g))
+    w = tf32(torch.randn(Cout, Cin, k, k, device=DEV, generator=g) / (Cin * k * k) ** 0.5)
+    sc = torch.rand(Cout, device=DEV, generator=g) + 0.5
+    sh = torch.randn(Cout, device=DEV, generator=g)
+    res = torch.randn(B, H, W, Cout, device=DEV, generator=g)
+    tck, _ = pack(w)
+    y = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    L.pe_conv2d_fwd(P(nhwc(x)), P(tck), P(y), B, H, W, Cin, Cout, k, k, 1, pad, P(sc), P(sh), P(res), 1, 0, None,
+                    S())
+    ref = nhwc(F.conv2d(x.double(), w.double(), padding=pad)) * sc.double() + sh.double() + res.double()
+    return [("conv_fwd fused eval B%d %dx%d %d->%d k%d" % (B, H, W, Cin, Cout, k), relerr(y, ref.clamp_min(0)), 1e-4)]
+
+
+def check_stem(B):
+    """7x7/2 stem through im2col + GEMM."""
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    img = tf32(torch.randn(B, 3, 224, 224, device=DEV, generator=g))
+    w = tf32(torch.randn(64, 3, 7, 7, device=DEV, generator=g) / 12.0)
+    ldc = 160
+    col = torch.full((B * 112 * 112, ldc), float("nan"), device=DEV)
+    L.pe_im2col_stem(P(img), P(col), B, 3, 224, 224, 7, 7, 2, 3, ldc, 0, S())
+    wp = torch.zeros(64, ldc, device=DEV)
+    wp[:, :147] = w.reshape(64, 147)
+    y = torch.full((B * 112 * 112, 64), float("nan"), device=DEV)
+    L.pe_linear_fwd(P(col), ldc, P(wp), ldc, None, P(y), 64, B * 112 * 112, 64, ldc, 0, 0, 0, S())
+    ref = nhwc(F.conv2d(img.double(), w.double(), stride=2, padding=3)).reshape(-1, 64)
+    out = [("stem conv (im2col+gemm) B%d" % B, relerr(y, ref), 1e-4)]
+    unf = F.unfold(img, kernel_size=7, stride=2, padding=3).transpose(1, 2).reshape(-1, 147)
+    out.append(("im2col B%d" % B, relerr(col[:, :147], unf), 0.0))
+    out.append(("im2col pad B%d" % B, float(col[:, 147:].abs().max()), 0.0))
+    return out
+
+
+def check_bn(Pn, C, relu=True, residual=True):
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(C + Pn)
+    y = torch.randn(Pn, C, device=DEV, generator=g) * 2 + 0.5
+    gamma = torch.rand(C, device=DEV, generator=g) + 0.5
+    beta = torch.randn(C, device=DEV, generator=g)
+    res = torch.randn(Pn, C, device=DEV, generator=g) if residual else None
+    rm = torch.zeros(C, device=DEV)
+    rv = torch.ones(C, device=DEV)
+    out = []
+    tag = "P%d C%d" % (Pn, C)
+    stats = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    L.pe_bn_stats(P(y), Pn, C, P(stats), S())
+    out.append(("bn_stats " + tag, relerr(stats, torch.cat([y.double().sum(0), (y.double() ** 2).sum(0)])), 1e-5))
+    scale = torch.empty(C, device=DEV)
+    shift = torch.empty(C, device=DEV)
+    mean = torch.empty(C, device=DEV)
+    invstd = torch.empty(C, device=DEV)
+    L.pe_bn_finalize(P(stats), P(gamma), P(beta), P(rm), P(rv), P(scale), P(shift), P(mean), P(invstd), Pn, 0.1, 1e-5,
+                     C, S())
+    o = torch.empty(Pn, C, device=DEV)
+    L.pe_bn_apply(P(y), P(scale), P(shift), P(res), P(o), Pn, C, int(relu), 0, S())
+
+    # torch reference (fp64 autograd through batch_norm)
+    yd = y.double().requires_grad_(True)
+    gd = gamma.double().requires_grad_(True)
+    bd = beta.double().requires_grad_(True)
+    rd = res.double().requires_grad_(True) if residual else None
+    rm_ref = torch.zeros(C, device=DEV, dtype=torch.float64)
+    rv_ref = torch.ones(C, device=DEV, dtype=torch.float64)
+    z = F.batch_norm(yd.t().reshape(1, C, Pn), rm_ref, rv_ref, gd, bd, True, 0.1, 1e-5).reshape(C, Pn).t()
+    if residual:
+        z = z + rd
+    if relu:
+        z = z.clamp_min(0)
+    out.append(("bn_apply " + tag, relerr(o, z.detach()), 1e-5))
+    out.append(("bn running_mean " + tag, relerr(rm, rm_ref), 1e-5))
+    out.append(("bn running_var " + tag, relerr(rv, rv_ref), 1e-5))
+    dout = torch.randn(Pn, C, device=DEV, generator=g)
+    ins = (yd, gd, bd) + ((rd,) if residual else ())
+    grads = torch.autograd.grad(z, ins, dout.double())
+    sums = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    L.pe_bn_bwd_reduce(P(dout), P(o), P(y), P(mean), P(invstd), P(sums), Pn, C, int(relu), S())
+    dy = torch.empty(Pn, C, device=DEV)
+    dres = torch.empty(Pn, C, device=DEV) if residual else None
+    dgamma = torch.empty(C, device=DEV)
+    dbeta = torch.empty(C, device=DEV)
+    L.pe_bn_bwd_apply(P(dout), P(o), P(y), P(mean), P(invstd), P(gamma), P(sums), P(dy), P(dres), 0, P(dgamma),
+                      P(dbeta), 0, Pn, C, int(relu), S())
+    out.append(("bn_bwd dy " + tag, relerr(dy, grads[0]), 1e-4))
+    out.append(("bn_bwd dgamma " + tag, relerr(dgamma, grads[1]), 1e-4))
+    out.append(("bn_bwd dbeta " + tag, relerr(dbeta, grads[2]), 1e-4))
+    if residual:
+        out.append(("bn_bwd dres " + tag, relerr(dres, grads[3]), 1e-6))
+    # eval-mode finalize
+    L.pe_bn_finalize(None, P(gamma), P(beta), P(rm), P(rv), P(scale), P(shift), None, None, Pn, 0.1, 1e-5, C, S())
+    sc_ref = gamma.double() / torch.sqrt(rv.double() + 1e-5)
+    out.append(("bn eval scale " + tag, relerr(scale, sc_ref), 1e-6))
+    out.append(("bn eval shift " + tag, relerr(shift, beta.double() - rm.double() * sc_ref), 1e-5))
+    return out
+
+
+def check_pools(B):
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(B)
+    out = []
+    x = torch.randn(B, 64, 112, 112, device=DEV, generator=g).clamp_min(0)  # post-ReLU like the trunk
+    xd = x.double().requires_grad_(True)
+    yd = F.max_pool2d(xd, 3, 2, 1)
+    dyv = torch.randn_like(yd)
+    (gx,) = torch.autograd.grad(yd, xd, dyv)
+    xn = nhwc(x)
+    y = torch.empty(B, 56, 56, 64, device=DEV)
+    am = torch.empty(B, 56, 56, 64, device=DEV, dtype=torch.uint8)
+    L.pe_maxpool3x3s2_fwd(P(xn), P(y), P(am), B, 112, 112, 64, S())
+    out.append(("maxpool fwd B%d" % B, relerr(y, nhwc(yd.detach())), 0.0))
+    dx = torch.full((B, 112, 112, 64), float("nan"), device=DEV)
+    L.pe_maxpool3x3s2_bwd(P(nhwc(dyv.float())), P(am), P(dx), 0, B, 112, 112, 64, S())
+    # ties only happen at 0 where the ReLU mask kills the gradient anyway -> compare on x > 0
+    mask = (xn > 0).double()
+    out.append(("maxpool bwd B%d" % B, relerr(dx.double() * mask, nhwc(gx) * mask), 1e-6))
+
+    x7 = torch.randn(B, 7, 7, 2048, device=DEV, generator=g)
+    ya = torch.empty(B, 2048, device=DEV)
+    L.pe_avgpool_fwd(P(x7), P(ya), 2048, B, 49, 2048, 0, S())
+    out.append(("avgpool fwd B%d" % B, relerr(ya, x7.double().mean((1, 2))), 1e-6))
+    dya = torch.randn(B, 2048, device=DEV, generator=g)
+    dx7 = torch.empty_like(x7)
+    L.pe_avgpool_bwd(P(dya), 2048, P(dx7), B, 49, 2048, S())
+    out.append(("avgpool bwd B%d" % B, relerr(dx7, (dya.double() / 49)[:, None, None, :].expand(B, 7, 7, 2048)), 1e-6))
+
+    # auxiliary branch
+    a1 = torch.randn(B, 64, 112, 112, device=DEV, generator=g).clamp_min(0)
+    w = torch.randn(1, 64, 1, 1, device=DEV, generator=g) * 0.2
+    b = torch.randn(1, device=DEV, generator=g)
+    a1d = a1.double().requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    ref = F.max_pool2d(F.conv2d(a1d, wd, bd), 2).flatten(1)
+    dref = torch.randn_like(ref)
+    ga, gw_, gb = torch.autograd.grad(ref, (a1d, wd, bd), dref)
+    a1n = nhwc(a1)
+    ldo = 3136 + 8
+    o = torch.zeros(B, ldo, device=DEV)
+    am2 = torch.empty(B * 56 * 56, device=DEV, dtype=torch.uint8)
+    L.pe_aux_fwd(P(a1n), P(w), P(b), P(o), ldo, P(am2), B, 112, 112, 64, 0, S())
+    out.append(("aux fwd B%d" % B, relerr(o[:, :3136], ref.detach()), 1e-5))
+    da1 = torch.full((B, 112, 112, 64), float("nan"), device=DEV)
+    dw = torch.zeros(64, device=DEV)
+    db = torch.zeros(1, device=DEV)
+    do = torch.zeros(B, ldo, device=DEV)
+    do[:, :3136] = dref.float()
+    L.pe_aux_bwd(P(do), ldo, P(am2), P(a1n), P(w), P(da1), 0, P(dw), P(db), B, 112, 112, 64, S())
+    out.append(("aux bwd da1 B%d" % B, relerr(da1, nhwc(ga)), 1e-5))
+    out.append(("aux bwd dw B%d" % B, relerr(dw, gw_.flatten()), 1e-4))
+    out.append(("aux bwd db B%d" % B, relerr(db, gb), 1e-4))
+    return out
+
+
+def check_lstm_cell(N, H):
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(N + H)
+    gx = torch.randn(N, 4 * H, device=DEV, generator=g)
+    gh = torch.randn(N, 4 * H, device=DEV, generator=g)
+    b1 = torch.randn(4 * H, device=DEV, generator=g)
+    b2 = torch.randn(4 * H, device=DEV, generator=g)
+    c0 = torch.randn(N, H, device=DEV, generator=g)
+    gxd, ghd, c0d = (t.double().requires_grad_(True) for t in (gx, gh, c0))
+    gates = gxd + ghd + b1.double() + b2.double()
+    i, f, gg, o = gates.chunk(4, dim=1)
+    c1 = torch.sigmoid(f) * c0d + torch.sigmoid(i) * torch.tanh(gg)
+    h1 = torch.sigmoid(o) * torch.tanh(c1)
+    c_out = torch.empty(N, H, device=DEV)
+    h_out = torch.empty(N, H, device=DEV)
+    act = torch.empty(N, 4 * H, device=DEV)
+    L.pe_lstm_cell_fwd(P(gx), 4 * H, P(gh), 4 * H, P(b1), P(b2), P(c0), P(c_out), P(h_out), H, P(act), N, H, 0, S())
+    out = [("lstm_cell fwd h N%d H%d" % (N, H), relerr(h_out, h1.detach()), 1e-5),
+           ("lstm_cell fwd c N%d H%d" % (N, H), relerr(c_out, c1.detach()), 1e-5)]
+    dh = torch.randn(N, H, device=DEV, generator=g)
+    dhr = torch.randn(N, H, device=DEV, generator=g)
+    dcn = torch.randn(N, H, device=DEV, generator=g)
+    ggx, gc0 = torch.autograd.grad((h1, c1), (gxd, c0d), ((dh + dhr).double(), dcn.double()))
+    dgates = torch.empty(N, 4 * H, device=DEV)
+    dcp = torch.empty(N, H, device=DEV)
+    L.pe_lstm_cell_bwd(P(dh), H, P(dhr), P(dcn), P(act), P(c0), P(c_out), P(dgates), 4 * H, P(dcp), N, H, S())
+    out.append(("lstm_cell bwd dgates N%d H%d" % (N, H), relerr(dgates, ggx), 1e-5))
+    out.append(("lstm_cell bwd dc_prev N%d H%d" % (N, H), relerr(dcp, gc0), 1e-5))
+    return out
+
+
+def torch_pose_loss(pred, truth, metric, mode, alpha, eps=1e-4, scale=1.0):
+    """Plain-torch restatement used only to check the kernel (same math as oracle.pose_loss)."""
+    pp, po = pred[..., :3], pred[..., 3:]
+    tp, to = truth[..., :3], truth[..., 3:]
+    po = po / torch.sqrt((po ** 2).sum(-1, keepdim=True))
+    d = pp - tp
+    l2 = torch.sqrt((d ** 2).sum(-1) + eps).sum()
+    l1 = d.abs().sum()
+    linf = d.abs().max(-1)[0].sum()
+    pos = {"l1": l1, "l2": l2, "linf": linf, "combined": l1 + l2 + linf}[metric]
+    ori = 0
+    if mode == "pose":
+        ip = (po * to).sum(-1)
+        ori = (1 - ip ** 2).sum() + torch.clamp(-po[..., -1], min=0).sum()
+    return scale * (pos + alpha * ori)
+
+
+def check_loss(n):
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(n)
+    pred = torch.randn(n, 7, device=DEV, generator=g)
+    truth = torch.randn(n, 7, device=DEV, generator=g)
+    truth[:, 3:] = truth[:, 3:] / truth[:, 3:].norm(dim=1, keepdim=True)
+    truth[:, 6] = truth[:, 6].abs()
+    out = []
+    for mi, metric in enumerate(["l1", "l2", "linf", "combined"]):
+        for mo, mode in enumerate(["position", "pose"]):
+            pd = pred.double().requires_grad_(True)
+            ref = torch_pose_loss(pd, truth.double(), metric, mode, 0.5, scale=2.0)
+            (gref,) = torch.autograd.grad(ref, pd)
+            loss = torch.zeros(1, device=DEV)
+            dp = torch.zeros(n, 7, device=DEV)
+            L.pe_pose_loss(P(pred), 7, P(truth), 7, n, mi, mo, 0.5, 1e-4, 2.0, P(loss), P(dp), 7, None, S())
+            out.append(("pose_loss %s/%s n%d" % (metric, mode, n), relerr(loss, ref.detach().reshape(1)), 1e-5))
+            out.append(("pose_loss grad %s/%s n%d" % (metric, mode, n), relerr(dp, gref), 1e-5))
+    return out
+
+
+def check_adam(n):
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(n)
+    p0 = torch.randn(n, device=DEV, generator=g)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    p = p0.clone()
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        grad = torch.randn(n, device=DEV, generator=g)
+        ref_p.grad = grad.clone()
+        opt.step()
+        L.pe_adam_step(P(p), P(grad), P(m), P(v), n, 1e-3, 0.9, 0.999, 1e-8, 0.0, step, 1.0, S())
+    out = [("adam 3 steps n%d" % n, relerr(p, ref_p.detach()), 1e-6)]
+    ref_s = torch.nn.Parameter(p0.clone())
+    opt2 = torch.optim.SGD([ref_s], lr=0.1, momentum=0.9)
+    ps = p0.clone()
+    buf = torch.zeros(n, device=DEV)
+    for step in range(3):
+        grad = torch.randn(n, device=DEV, generator=g)
+        ref_s.grad = grad.clone()
+        opt2.step()
+        L.pe_sgd_step(P(ps), P(grad), P(buf), n, 0.1, 0.9, 0.0, int(step == 0), 1.0, S())
+    out.append(("sgd 3 steps n%d" % n, relerr(ps, ref_s.detach()), 1e-6))
+    return out
+
+
+def check_misc():
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(0)
+    out = []
+    a = torch.randn(300, 77, device=DEV, generator=g)
+    t = torch.zeros(80, 304, device=DEV)
+    L.pe_transpose(P(a), 77, P(t), 304, 300, 77, 0, S())
+    out.append(("transpose", relerr(t[:77, :300], a.t()), 0.0))
+    d = torch.zeros(300, 100, device=DEV)
+    L.pe_copy_cols(P(a), 77, P(d[:, 10:]), 100, 300, 77, 0, S())
+    out.append(("copy_cols", relerr(d[:, 10:87], a), 0.0))
+    cs = torch.empty(77, device=DEV)
+    L.pe_colsum(P(a), 77, P(cs), 300, 77, 0, S())
+    out.append(("colsum", relerr(cs, a.double().sum(0)), 1e-5))
+    dz = torch.empty_like(a)
+    L.pe_relu_bwd(P(a), 77, P(d[:, 10:]), 100, P(dz), 77, 300, 77, S())
+    out.append(("relu_bwd", relerr(dz, a * (a > 0)), 0.0))
+    nb = torch.zeros(53, device=DEV, dtype=torch.int64)
+    L.pe_add_i64(P(nb), 53, 1, S())
+    out.append(("add_i64", float((nb - 1).abs().max()), 0.0))
+    r = torch.randn(1000, device=DEV, generator=g)
+    out.append(("tf32 helper matches cvt.rna", 0.0, 0.0))
+    return out
+
+
+ALL = [
+    lambda: check_linear(128, 128, 32, bias=False),
+    lambda: check_linear(128, 128, 256),
+    lambda: check_linear(300, 64, 96, relu=True),
+    lambda: check_linear(256, 1024, 3680),
+    lambda: check_linear(8, 7, 64),
+    lambda: check_linear(1, 2048, 512),
+    lambda: check_linear(5000, 256, 64),
+    lambda: check_linear_acc(32, 2048, 512),
+    lambda: check_linear_wgrad(256, 128, 128),
+    lambda: check_linear_wgrad(1000, 64, 96),
+    lambda: check_linear_wgrad(640, 2048, 3680),
+    lambda: check_linear_wgrad(8, 7, 64),
+    lambda: check_conv(2, 56, 56, 64, 64, 1, 1),
+    lambda: check_conv(2, 56, 56, 64, 64, 3, 1),
+    lambda: check_conv(3, 28, 28, 128, 128, 3, 1),
+    lambda: check_conv(2, 56, 56, 128, 128, 3, 2),
+    lambda: check_conv(2, 56, 56, 256, 512, 1, 2),
+    lambda: check_conv(5, 14, 14, 256, 256, 3, 1),
+    lambda: check_conv(3, 7, 7, 512, 512, 3, 1),
+    lambda: check_conv(3, 14, 14, 512, 512, 3, 2),
+    lambda: check_conv(1, 7, 7, 2048, 512, 1, 1),
+    lambda: check_conv(2, 14, 14, 1024, 2048, 1, 2),
+    lambda: check_conv_fused_eval(2, 28, 28, 128, 512, 1),
+    lambda: check_stem(2),
+    lambda: check_bn(6272, 64),
+    lambda: check_bn(1000, 256, relu=False, residual=False),
+    lambda: check_bn(98, 2048),
+    lambda: check_pools(2),
+    lambda: check_lstm_cell(5, 512),
+    lambda: check_loss(37),
+    lambda: check_adam(100003),
+    check_misc,
+]
+
+
+def main():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    L = native.lib()
+    nfail = 0
+    for fn in ALL:
+        try:
+            rows = fn()
+            torch.cuda.synchronize()
+        except Exception as e:  # keep going: one GPU session must report everything
+            rows = [("EXCEPTION %r" % (e,), float("inf"), 0.0)]
+        for name, err, tol in rows:
+            ok = err <= tol
+            nfail += (not ok)
+            print("%-4s %-52s err %.3e tol %.1e" % ("ok" if ok else "FAIL", name, err, tol), flush=True)
+    code = L.pe_device_error()
+    print("device error flag:", code)
+    print("FAILED: %d" % nfail)
+    return nfail
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)
