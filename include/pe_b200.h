@@ -22,7 +22,8 @@ extern "C" {
 #endif
 
 const char* pe_last_error(void);
-int pe_device_error(void);
+int pe_device_error(void);      /* bitmask: 1 conv producer, 2 wgrad producer, 4 MMA issuer, 8 epilogue */
+void pe_device_error_clear(void);
 int pe_version(void);
 /* debug: override UMMA shared-memory descriptor strides (bytes; <0 restores the default) */
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo);

@@ -1,0 +1,317 @@
+"""CPU oracle for the pose-estimator hot path.  TEST INFRASTRUCTURE ONLY.
+
+A plain-PyTorch (CPU, fp32) restatement of the reference's algorithm for the one accelerated path:
+ResNet-50 trunk -> auxiliary BN1 branch -> concat proprioception -> MLP / LSTM head -> pose loss ->
+Adam.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+legs may import this file; the product path (rgb-proprioceptive-pose-estimator_b200/) never does.
+
+Parity pinning: the reference ships no tests or golden vectors for this path, so
+this restatement is pinned against (a) the reference's own modules imported from /root/reference in
+the build container (tests/test_oracle_vs_reference.py, skipped where the reference is absent) and
+(b) the fixtures under tests/golden/ that oracle/make_golden.py generated from those modules.
+
+Third-party arithmetic that is not under /root/reference (requirements.txt leaves torch/torchvision
+unpinned): torchvision.models.resnet50 (ResNet v1.5, stride on the 3x3) and torch.nn.{Conv2d,
+BatchNorm2d,LSTM,Linear}; restated here functionally from their published definitions and checked
+against torch 2.11.0 / torchvision 0.26.0 as installed.
+
+Each function cites the reference lines it follows (paths relative to /root/reference).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# torchvision resnet50: (planes, blocks, stride) per stage -- torchvision/models/resnet.py:266-282
+RESNET50_STAGES = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))
+
+
+# --------------------------------------------------------------------------------------------
+# trunk
+# --------------------------------------------------------------------------------------------
+def _bn(x, sd, prefix, training, momentum=0.1, eps=1e-5):
+    """nn.BatchNorm2d forward incl. running-stat update (torchvision resnet.py:134-138,198)."""
+    rm, rv = sd[prefix + "running_mean"], sd[prefix + "running_var"]
+    if training:
+        sd[prefix + "num_batches_tracked"] += 1
+    return F.batch_norm(x, rm, rv, sd[prefix + "weight"], sd[prefix + "bias"], training, momentum, eps)
+
+
+def _bottleneck(x, sd, prefix, stride, training):
+    """torchvision Bottleneck.forward (resnet.py:143-163), stride on conv2 (v1.5)."""
+    identity = x
+    out = F.conv2d(x, sd[prefix + "conv1.weight"])
+    out = F.relu(_bn(out, sd, prefix + "bn1.", training))
+    out = F.conv2d(out, sd[prefix + "conv2.weight"], stride=stride, padding=1)
+    out = F.relu(_bn(out, sd, prefix + "bn2.", training))
+    out = F.conv2d(out, sd[prefix + "conv3.weight"])
+    out = _bn(out, sd, prefix + "bn3.", training)
+    if prefix + "downsample.0.weight" in sd:
+        identity = F.conv2d(x, sd[prefix + "downsample.0.weight"], stride=stride)
+        identity = _bn(identity, sd, prefix + "downsample.1.", training)
+    return F.relu(out + identity)
+
+
+def resnet50_forward(sd, prefix, img, training):
+    """ResNet._forward_impl (torchvision resnet.py:266-282) with fc = Linear(2048, latent)
+    (util/model_utils.py:139-141).  Returns (latent features, post-ReLU bn1 map).
+
+    The second output is what the reference's bn1 forward hook ends up holding: the hooked tensor
+    is overwritten by relu(inplace=True) (models/naive.py:211,282-283)."""
+    x = F.conv2d(img, sd[prefix + "conv1.weight"], stride=2, padding=3)
+    x = F.relu(_bn(x, sd, prefix + "bn1.", training))
+    early = x
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for li, (_, blocks, stride) in enumerate(RESNET50_STAGES, start=1):
+        for b in range(blocks):
+            x = _bottleneck(x, sd, "%slayer%d.%d." % (prefix, li, b), stride if b == 0 else 1, training)
+    x = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
+    return F.linear(x, sd[prefix + "fc.weight"], sd[prefix + "fc.bias"]), early
+
+
+def aux_forward(early, w, b):
+    """Conv2d(64,1,1) + MaxPool2d(2) + Flatten (models/naive.py:225-229, time_sensitive.py:379-383)."""
+    return torch.flatten(F.max_pool2d(F.conv2d(early, w, b), 2), 1)
+
+
+def lstm_forward(x, sd, prefix, state=None):
+    """Single-layer nn.LSTM, seq-major input (S, N, F), gates (i, f, g, o)
+    (models/time_sensitive.py:126-131,418; torch.nn.LSTM definition)."""
+    w_ih, w_hh = sd[prefix + "weight_ih_l0"], sd[prefix + "weight_hh_l0"]
+    b_ih, b_hh = sd[prefix + "bias_ih_l0"], sd[prefix + "bias_hh_l0"]
+    S, N, _ = x.shape
+    H = w_hh.shape[1]
+    if state is None:
+        h = x.new_zeros(N, H)
+        c = x.new_zeros(N, H)
+    else:
+        h, c = state[0][0], state[1][0]
+    outs = []
+    for t in range(S):
+        gates = F.linear(x[t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+        i, f, g, o = gates.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    return torch.stack(outs), (h.unsqueeze(0), c.unsqueeze(0))
+
+
+# --------------------------------------------------------------------------------------------
+# the four estimators
+# --------------------------------------------------------------------------------------------
+def naive_object_forward(sd, img, x0bar, training, n_fc, use_proprio=True):
+    """NaiveObjectStateEstimator.forward (models/naive.py:298-352); ReLU after EVERY fc incl. the
+    last one (quirk Q2, models/naive.py:343-345)."""
+    feats, early = resnet50_forward(sd, "feature_net.module.", img, training)
+    aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"])
+    out = torch.cat((feats, aux), dim=-1).view(img.shape[0], -1)
+    if use_proprio:
+        out = torch.cat((out, x0bar), dim=-1)
+    for i in range(n_fc):
+        out = F.relu(F.linear(out, sd["fc%d.module.weight" % i], sd["fc%d.module.bias" % i]))
+    return out
+
+
+def naive_eef_forward(sd, img, x0bar, training, n_pre, n_post):
+    """NaiveEndEffectorStateEstimator.forward (models/naive.py:68-112): no aux branch."""
+    feats, _ = resnet50_forward(sd, "feature_net.", img, training)
+    pre = feats
+    for i in range(n_pre):
+        pre = F.relu(F.linear(pre, sd["pre_fc%d.weight" % i], sd["pre_fc%d.bias" % i]))
+    post = torch.cat([feats, pre - x0bar], dim=1)
+    for i in range(n_post):
+        post = F.relu(F.linear(post, sd["post_fc%d.weight" % i], sd["post_fc%d.bias" % i]))
+    return pre, post
+
+
+def tdo_forward(sd, img, x0bar, training, state=None, use_proprio=True):
+    """TemporallyDependentObjectStateEstimator.forward (models/time_sensitive.py:453-517); head is
+    Linear(H, H//4) -> Linear(H//4, 7) with no nonlinearity (quirk Q6, :420-423).
+    `state` = (h, c) each (1, N, H) for rollout mode; returns (out, new_state)."""
+    S, N = img.shape[0], img.shape[1]
+    feats, early = resnet50_forward(sd, "feature_net.module.", img.reshape(S * N, *img.shape[2:]), training)
+    aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"])
+    f = torch.cat((feats, aux), dim=-1).view(S, N, -1)
+    if use_proprio:
+        f = torch.cat((f, x0bar), dim=-1)
+    h, new_state = lstm_forward(f, sd, "rnn.module.", state)
+    out = F.linear(F.linear(h, sd["fc.module.0.weight"], sd["fc.module.0.bias"]),
+                   sd["fc.module.1.weight"], sd["fc.module.1.bias"])
+    return out, new_state
+
+
+def td_forward(sd, img, x0bar, training, aux_w, aux_b, state=None):
+    """TemporallyDependentStateEstimator.forward (models/time_sensitive.py:165-254).  The aux conv is
+    NOT part of the state_dict (plain python list, quirk Q4, :77-78,102-115) so it is passed in.
+    `state` = ((h_pre, c_pre), (h_post, c_post)) for rollout mode."""
+    S, N = img.shape[0], img.shape[1]
+    feats, early = resnet50_forward(sd, "feature_net.", img.reshape(S * N, *img.shape[2:]), training)
+    aux = aux_forward(early, aux_w, aux_b)
+    f = torch.cat((feats, aux), dim=-1).view(S, N, -1)
+    h_pre, st_pre = lstm_forward(f, sd, "pre_measurement_rnn.", None if state is None else state[0])
+    pre_out = F.linear(h_pre, sd["pre_measurement_fc.weight"], sd["pre_measurement_fc.bias"])
+    post_in = torch.cat([f, pre_out - x0bar], dim=-1)
+    h_post, st_post = lstm_forward(post_in, sd, "post_measurement_rnn.", None if state is None else state[1])
+    post_out = F.linear(h_post, sd["post_measurement_fc.weight"], sd["post_measurement_fc.bias"])
+    return pre_out, post_out, (st_pre, st_post)
+
+
+# --------------------------------------------------------------------------------------------
+# loss (models/losses.py:47-128)
+# --------------------------------------------------------------------------------------------
+def pose_loss(prediction, truth, distance_metric="l2", scale_factor=1.0, alpha=1.0, epsilon=1e-4, mode="pose"):
+    """PoseDistanceLoss.forward for modes 'position' / 'pose': a SUM over samples (quirk Q7)."""
+    pp, po = torch.split(prediction, (3, 4), dim=-1)
+    tp, to = torch.split(truth, (3, 4), dim=-1)
+    po = po / torch.sqrt(torch.sum(po.pow(2), dim=-1, keepdim=True))          # losses.py:68-69
+    d = pp - tp
+    l2 = torch.sum(torch.sqrt(torch.sum(d.pow(2), dim=-1) + epsilon))           # losses.py:74-75
+    l1 = torch.sum(torch.abs(d))                                                # losses.py:80
+    linf = torch.sum(torch.max(torch.abs(d), dim=-1)[0])                        # losses.py:82
+    if distance_metric == "l2":
+        pos = l2
+    elif distance_metric == "l1":
+        pos = l1
+    elif distance_metric == "linf":
+        pos = linf
+    elif distance_metric == "combined":
+        pos = l2 + l1 + linf                                                    # losses.py:85-92
+    else:
+        raise ValueError(distance_metric)
+    if mode == "pose":
+        ip = torch.sum(po * to, dim=-1)
+        ori = torch.sum(1 - ip.pow(2)) + torch.sum(torch.clamp(-po[..., -1], min=0))   # losses.py:117-122
+    elif mode == "position":
+        ori = 0
+    else:
+        raise ValueError(mode)
+    return scale_factor * (pos + alpha * ori)                                   # losses.py:128
+
+
+def pose_val_metrics(prediction, truth, distance_metric="l2", epsilon=1e-4):
+    """'val' mode (models/losses.py:95-113): (position distance, summed |angle| in radians).
+    robosuite v1.0 semantics: angle = 2*acos(w) of q_pred * conj(q_true), 0 when sqrt(1-w^2) ~ 0,
+    wrapped into [-pi, pi] before abs().  For unit quaternions w = <q_pred_normalised, q_true>."""
+    pos = pose_loss(prediction, truth, distance_metric, 1.0, 0.0, epsilon, "position")
+    po = prediction[..., 3:] / torch.sqrt(torch.sum(prediction[..., 3:].pow(2), dim=-1, keepdim=True))
+    to = truth[..., 3:]
+    total = 0.0
+    for p, t in zip(po.reshape(-1, 4).tolist(), to.reshape(-1, 4).tolist()):
+        w = max(-1.0, min(1.0, sum(a * b for a, b in zip(p, t)) / max(sum(b * b for b in t), 1e-300)))
+        den = math.sqrt(max(1.0 - w * w, 0.0))
+        angle = 0.0 if math.isclose(den, 0.0) else 2.0 * math.acos(w)
+        if angle > math.pi:
+            angle -= 2 * math.pi
+        total += abs(angle)
+    return float(pos), total
+
+
+# --------------------------------------------------------------------------------------------
+# Adam (torch.optim.Adam defaults; scripts/train_model.py:228, util/learn_utils.py:179)
+# --------------------------------------------------------------------------------------------
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In-place Adam update of lists of tensors; `step` is the 1-based step count."""
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        if g is None:
+            continue
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+        p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+# --------------------------------------------------------------------------------------------
+# convenience: one training step of any estimator on CPU
+# --------------------------------------------------------------------------------------------
+class OracleEstimator:
+    """Holds a reference-layout state_dict and runs forward / loss / backward / Adam on CPU."""
+
+    def __init__(self, kind, state_dict, extra=None):
+        assert kind in ("no", "n", "td", "tdo")
+        self.kind = kind
+        self.sd = {k: v.detach().clone() for k, v in state_dict.items()}
+        self.extra = {k: v.detach().clone() for k, v in (extra or {}).items()}  # td: aux conv (frozen)
+        self.param_names = [k for k, v in self.sd.items()
+                            if v.dtype.is_floating_point and "running_" not in k]
+        self.state = None
+        self.adam_m = None
+        self.adam_v = None
+        self.adam_t = 0
+
+    def _count(self, pattern):
+        return len([k for k in self.sd if k.startswith(pattern) and k.endswith("weight")])
+
+    def forward(self, img, x0bar, training=True, rollout=False):
+        sd = self.sd
+        if self.kind == "no":
+            return naive_object_forward(sd, img, x0bar, training, self._count("fc"))
+        if self.kind == "n":
+            return naive_eef_forward(sd, img, x0bar, training, self._count("pre_fc"), self._count("post_fc"))
+        if self.kind == "tdo":
+            out, st = tdo_forward(sd, img, x0bar, training, self.state if rollout else None)
+            if rollout:
+                self.state = st
+            return out
+        pre, post, st = td_forward(sd, img, x0bar, training, self.extra["aux_w"], self.extra["aux_b"],
+                                   self.state if rollout else None)
+        if rollout:
+            self.state = st
+        return pre, post
+
+    def reset_state(self, n):
+        h = self.sd["rnn.module.weight_hh_l0"].shape[1] if self.kind == "tdo" else None
+        if self.kind == "tdo":
+            self.state = (torch.zeros(1, n, h), torch.zeros(1, n, h))
+        elif self.kind == "td":
+            hp = self.sd["pre_measurement_rnn.weight_hh_l0"].shape[1]
+            hq = self.sd["post_measurement_rnn.weight_hh_l0"].shape[1]
+            self.state = ((torch.zeros(1, n, hp), torch.zeros(1, n, hp)),
+                          (torch.zeros(1, n, hq), torch.zeros(1, n, hq)))
+
+    def loss_and_grads(self, img, x0bar, target, loss_kwargs, which=-1):
+        """Returns (outputs, loss, {param name: grad}).  `which` picks the output the loss applies to
+        for two-headed models (util/learn_utils.py:160-176 trains on the object / post output)."""
+        for k in self.param_names:
+            self.sd[k].requires_grad_(True)
+            self.sd[k].grad = None
+        out = self.forward(img, x0bar, training=True)
+        pred = out[which] if isinstance(out, tuple) else out
+        loss = pose_loss(pred, target, **loss_kwargs)
+        loss.backward()
+        grads = {k: (None if self.sd[k].grad is None else self.sd[k].grad.detach().clone())
+                 for k in self.param_names}
+        for k in self.param_names:
+            self.sd[k].requires_grad_(False)
+        outs = tuple(o.detach() for o in out) if isinstance(out, tuple) else out.detach()
+        return outs, loss.detach(), grads
+
+    def train_step(self, img, x0bar, target, loss_kwargs, lr=1e-3, which=-1):
+        outs, loss, grads = self.loss_and_grads(img, x0bar, target, loss_kwargs, which)
+        if self.adam_m is None:
+            self.adam_m = {k: torch.zeros_like(self.sd[k]) for k in self.param_names}
+            self.adam_v = {k: torch.zeros_like(self.sd[k]) for k in self.param_names}
+        self.adam_t += 1
+        names = [k for k in self.param_names if grads[k] is not None]
+        with torch.no_grad():
+            adam_step([self.sd[k] for k in names], [grads[k] for k in names], [self.adam_m[k] for k in names],
+                      [self.adam_v[k] for k in names], self.adam_t, lr=lr)
+        return outs, loss
+
+
+def synthetic_batch(kind, n, s=None, seed=1, hw=224):
+    """Synthetic inputs of SURVEY 8(d): img ~ N(0,1); positions U(-0.5,0.5)^3; unit quaternions with
+    w >= 0 (util/data_utils.py:207-211).  Returns (img, x0bar, target) as CPU fp32 tensors."""
+    g = torch.Generator().manual_seed(seed)
+    lead = (n,) if kind in ("no", "n") else (s, n)
+    img = torch.randn(*lead, 3, hw, hw, generator=g)
+
+    def pose():
+        pos = torch.rand(*lead, 3, generator=g) - 0.5
+        q = torch.randn(*lead, 4, generator=g)
+        q = q / q.norm(dim=-1, keepdim=True)
+        q[..., 3] = q[..., 3].abs()
+        return torch.cat([pos, q], dim=-1)
+
+    return img, pose(), pose()

@@ -81,12 +81,12 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return done;
 }
-// Bounded wait: returns false after ~2^31 SM cycles (about a second) instead of hanging the GPU.
+// Bounded wait: returns false after ~2^31 SM cycles (~0.15 s) instead of hanging the GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (1ll << 31)) return false;
+        if (clock64() - t0 > (1ll << 28)) return false;
     }
     return true;
 }
@@ -181,18 +181,21 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+// Shared-memory matrix descriptor (sm_100 "version 1").
 //  K-major : rows of 128 B (32 tf32 along K), 8-row groups SBO bytes apart.
-//  MN-major: rows of 128 B (32 tf32 along M/N), one MMA (K=8) reads 8 rows = 1024 B;
-//            32-wide M/N atoms are LBO bytes apart.
+//  MN-major: rows of 128 B (32 tf32 along M/N), one MMA (K=8) reads 8 rows = two 4-row swizzle
+//            atoms SBO (= 512) bytes apart; 32-wide M/N atoms are LBO bytes apart.
+//  layout_type: 2 = SWIZZLE_128B (16 B atoms; K-major operands),
+//               1 = SWIZZLE_128B_BASE32B (32 B atoms, 4-row period; the only layout tcgen05
+//                   accepts for MN-major TF32 operands -- TMA mode SWIZZLE_128B_ATOM_32B).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= 1ull << 46;  // descriptor version (Blackwell)
-    d |= 2ull << 61;  // SWIZZLE_128B
+    d |= static_cast<uint64_t>(layout_type) << 61;
     return d;
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate.

@@ -66,7 +66,7 @@ static int ensure_encode() {
 
 // fp32 tensor, 4 dims (d0 contiguous), strides in ELEMENTS for dims 1..3, SWIZZLE_128B.
 static int make_map(CUtensorMap* m, const void* base, const long long dims[4], const long long strides[3],
-                    const int box[4]) {
+                    const int box[4], bool mn_major = false) {
     if (ensure_encode()) return 1;
     cuuint64_t gd[4], gs[3];
     cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
@@ -83,7 +83,8 @@ static int make_map(CUtensorMap* m, const void* base, const long long dims[4], c
     PE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
     PE_REQUIRE(box[0] * 4 <= 128 && (box[0] * 4) % 16 == 0, "TMA inner box %d elems invalid", box[0]);
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd, gs, bx, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PE_REQUIRE(r == CUDA_SUCCESS,
                "cuTensorMapEncodeTiled failed (%d): dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d %d",
@@ -94,27 +95,33 @@ static int make_map(CUtensorMap* m, const void* base, const long long dims[4], c
 
 // NHWC activation view (optionally one stride-2 parity plane), channels innermost.
 static int make_nhwc_map(CUtensorMap* m, const float* base, int N, int H, int W, int C, int ph, int pw,
-                         int step, const int box[4]) {
+                         int step, const int box[4], bool mn_major = false) {
     const long long dims[4] = {C, (W - pw + step - 1) / step, (H - ph + step - 1) / step, N};
     const long long strides[3] = {(long long)step * C, (long long)step * W * C, (long long)H * W * C};
-    return make_map(m, base + ((long long)ph * W + pw) * C, dims, strides, box);
+    return make_map(m, base + ((long long)ph * W + pw) * C, dims, strides, box, mn_major);
 }
 
 // Pick a (bw, bh, bn) pixel box with bw*bh*bn <= target that tiles (W, H, N) with the fewest boxes.
-static void choose_box(int W, int H, int N, int target, int* obw, int* obh, int* obn) {
+// exact=true: bw*bh*bn == target exactly (boxes may overhang the tensor; TMA zero-fills), needed when
+// the box rows are the reduction dimension (wgrad) and every shared-memory row must be defined.
+static void choose_box(int W, int H, int N, int target, int* obw, int* obh, int* obn, bool exact = false) {
     static std::map<std::tuple<int, int, int, int>, std::tuple<int, int, int>> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    auto key = std::make_tuple(W, H, N, target);
+    auto key = std::make_tuple(W, H, N, exact ? -target : target);
     auto it = cache.find(key);
     if (it == cache.end()) {
         long long best = -1;
         int bbw = 1, bbh = 1, bbn = 1;
-        for (int bw = 1; bw <= W && bw <= target; ++bw) {
-            for (int bh = 1; bh <= H && bw * bh <= target; ++bh) {
+        for (int bw = 1; bw <= target && (exact || bw <= W); ++bw) {
+            for (int bh = 1; bw * bh <= target && (exact || bh <= H); ++bh) {
                 int bn = target / (bw * bh);
-                if (bn > N) bn = N;
-                if (bn < 1) bn = 1;
+                if (exact) {
+                    if (bw * bh * bn != target) continue;
+                } else {
+                    if (bn > N) bn = N;
+                    if (bn < 1) bn = 1;
+                }
                 if (bn > 256 || bw > 256 || bh > 256) continue;
                 long long tiles = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((N + bn - 1) / bn);
                 // fewest tiles; ties -> widest rows (better DRAM locality)
@@ -309,7 +316,7 @@ static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B
     p.mode = 1;
     p.bn = Cin >= 128 ? 128 : ((Cin + 31) / 32) * 32;
     p.m_rows = TG_BM;
-    choose_box(Wo, Ho, B, TG_BK, &p.box_w, &p.box_h, &p.box_n);
+    choose_box(Wo, Ho, B, TG_BK, &p.box_w, &p.box_h, &p.box_n, true);
     p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
     p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
     p.tiles_n = (B + p.box_n - 1) / p.box_n;
@@ -319,13 +326,13 @@ static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B
     p.out_n = B;
     if (fill_taps_fwd(p, R, S, stride, pad)) return 1;
     const int box[4] = {32, p.box_w, p.box_h, p.box_n};
-    if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, box)) return 1;
+    if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, box, true)) return 1;
     if (stride == 1) {
-        if (make_nhwc_map(&maps.b[0], x, B, H, W, Cin, 0, 0, 1, box)) return 1;
+        if (make_nhwc_map(&maps.b[0], x, B, H, W, Cin, 0, 0, 1, box, true)) return 1;
     } else {
         for (int ph = 0; ph < 2; ++ph)
             for (int pw = 0; pw < 2; ++pw)
-                if (make_nhwc_map(&maps.b[ph * 2 + pw], x, B, H, W, Cin, ph, pw, 2, box)) return 1;
+                if (make_nhwc_map(&maps.b[ph * 2 + pw], x, B, H, W, Cin, ph, pw, 2, box, true)) return 1;
     }
     p.m_total = Cout;
     p.n_total = Cin;
@@ -434,13 +441,13 @@ static int linear_wgrad_impl(const float* x, int ldx, const float* dy, int lddy,
         const long long dims[4] = {N, M, 1, 1};
         const long long strides[3] = {lddy, (long long)lddy * M, (long long)lddy * M};
         const int box[4] = {32, TG_BK, 1, 1};
-        if (make_map(&maps.a[0], dy, dims, strides, box)) return 1;
+        if (make_map(&maps.a[0], dy, dims, strides, box, true)) return 1;
     }
     {
         const long long dims[4] = {K, M, 1, 1};
         const long long strides[3] = {ldx, (long long)ldx * M, (long long)ldx * M};
         const int box[4] = {32, TG_BK, 1, 1};
-        if (make_map(&maps.b[0], x, dims, strides, box)) return 1;
+        if (make_map(&maps.b[0], x, dims, strides, box, true)) return 1;
     }
     p.m_total = N;
     p.n_total = K;
@@ -484,6 +491,10 @@ int pe_device_error(void) {
     int v = 0;
     if (cudaMemcpy(&v, g_error_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return v;
+}
+
+void pe_device_error_clear(void) {
+    if (g_error_flag) cudaMemset(g_error_flag, 0, sizeof(int));
 }
 
 int pe_conv2d_fwd(const float* x, const float* w_tck, float* y, int B, int H, int W, int Cin, int Cout, int R,

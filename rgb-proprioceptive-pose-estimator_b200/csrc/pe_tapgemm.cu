@@ -108,7 +108,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     const int s = it % TG_STAGES;
                     const uint32_t ph = (it / TG_STAGES) & 1;
                     if (!mbar_wait(smem_u32(&s_empty[s]), ph ^ 1)) {
-                        atomicExch(p.error_flag, 101);
+                        atomicOr(p.error_flag, 1);
                         break;
                     }
                     const int k = k_begin + it;
@@ -132,7 +132,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     const int s = it % TG_STAGES;
                     const uint32_t ph = (it / TG_STAGES) & 1;
                     if (!mbar_wait(smem_u32(&s_empty[s]), ph ^ 1)) {
-                        atomicExch(p.error_flag, 102);
+                        atomicOr(p.error_flag, 2);
                         break;
                     }
                     const TileOrigin o = tile_origin(p, k_begin + it);
@@ -154,18 +154,19 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TG_BM, p.bn, p.mode, p.mode);
             // K-major: LBO unused (16 B), SBO = 8 rows * 128 B.  MN-major: LBO = one 32-wide
-            // atom column (32 k-rows * 128 B), SBO = 8 k-rows * 128 B.
+            // atom column (32 k-rows * 128 B), SBO = 4 k-rows * 128 B (128B_BASE32B atoms).
             const uint32_t a_lbo = p.dbg_a_lbo >= 0 ? p.dbg_a_lbo : (p.mode ? 4096 : 16);
-            const uint32_t a_sbo = p.dbg_a_sbo >= 0 ? p.dbg_a_sbo : 1024;
+            const uint32_t a_sbo = p.dbg_a_sbo >= 0 ? p.dbg_a_sbo : (p.mode ? 512 : 1024);
             const uint32_t b_lbo = p.dbg_b_lbo >= 0 ? p.dbg_b_lbo : (p.mode ? 4096 : 16);
-            const uint32_t b_sbo = p.dbg_b_sbo >= 0 ? p.dbg_b_sbo : 1024;
+            const uint32_t b_sbo = p.dbg_b_sbo >= 0 ? p.dbg_b_sbo : (p.mode ? 512 : 1024);
+            const uint32_t ltype = p.mode ? 1u : 2u;
             const uint32_t kstep_bytes = p.mode ? 1024u : 32u;  // 8 tf32 along K
             bool ok = true;
             for (int it = 0; it < nk; ++it) {
                 const int s = it % TG_STAGES;
                 const uint32_t ph = (it / TG_STAGES) & 1;
                 if (!mbar_wait(smem_u32(&s_full[s]), ph)) {
-                    atomicExch(p.error_flag, 103);
+                    atomicOr(p.error_flag, 4);
                     ok = false;
                     break;
                 }
@@ -174,8 +175,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                 const uint32_t sb = sa + TG_A_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < TG_BK / 8; ++kk) {
-                    const uint64_t ad = make_smem_desc(sa + kk * kstep_bytes, a_lbo, a_sbo);
-                    const uint64_t bd = make_smem_desc(sb + kk * kstep_bytes, b_lbo, b_sbo);
+                    const uint64_t ad = make_smem_desc(sa + kk * kstep_bytes, a_lbo, a_sbo, ltype);
+                    const uint64_t bd = make_smem_desc(sb + kk * kstep_bytes, b_lbo, b_sbo, ltype);
                     tc_mma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
                 }
                 tc_commit(smem_u32(&s_empty[s]));  // frees the stage when these MMAs retire
@@ -191,7 +192,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         bool ok = true;
         if (nk > 0) {
             ok = mbar_wait(smem_u32(&s_tmem_full), 0);
-            if (!ok) atomicExch(p.error_flag, 104);
+            if (!ok) atomicOr(p.error_flag, 8);
         }
         tc_fence_after();
 

@@ -131,7 +131,7 @@ def check_conv(B, H, W, Cin, Cout, k, stride):
     y_ref = nhwc(yd.detach())
     out.append(("conv_fwd " + tag, relerr(y, y_ref), 1e-4))
     s_ref = torch.cat([y_ref.sum((0, 1, 2)), (y_ref * y_ref).sum((0, 1, 2))])
-    out.append(("conv_fwd stats " + tag, relerr(stats, s_ref), 1e-5))
+    out.append(("conv_fwd stats " + tag, relerr(stats, s_ref), 1e-4))
 
     dy_n = nhwc(dy)
     dx = torch.full((B, H, W, Cin), float("nan"), device=DEV)

@@ -15,18 +15,19 @@ def main():
         for name, err, tol in fn():
             print("%-40s err %.3e" % (name, err))
     print("== MN-major sweep (wgrad) ==")
-    for lbo in (16, 128, 1024, 2048, 4096, 8192):
-        for sbo in (16, 128, 1024, 4096):
+    for lbo in (4096, 512, 1024, 128):
+        for sbo in (512, 1024, 256, 4096):
             L.pe_debug_desc_override(lbo, sbo, lbo, sbo)
+            L.pe_device_error_clear()
             try:
                 (name, err, tol), = kc.check_linear_wgrad(256, 128, 128)
             except Exception as e:
                 err = float("nan")
             torch.cuda.synchronize()
-            print("wgrad lbo %5d sbo %5d -> err %.3e" % (lbo, sbo, err), flush=True)
+            print("wgrad lbo %5d sbo %5d -> err %.3e flag %d" % (lbo, sbo, err, L.pe_device_error()), flush=True)
     print("== K-major sweep (fwd) ==")
     for lbo in (0, 16, 1024):
-        for sbo in (128, 1024, 2048):
+        for sbo in (1024,):
             L.pe_debug_desc_override(lbo, sbo, lbo, sbo)
             (name, err, tol), = kc.check_linear(256, 128, 128)
             torch.cuda.synchronize()
