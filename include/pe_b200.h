@@ -53,9 +53,12 @@ int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W
 
 /* ---- dense layers: nn.Linear / nn.LSTM projections (models/naive.py:274,343-345,
  *      models/time_sensitive.py:126-131,418-423) -------------------------------------------------
- * y[M,N] = x[M,K] w[N,K]^T (+bias)(ReLU); accumulate!=0 adds into the existing y.                 */
-int pe_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy, int M,
-                  int N, int K, int relu, int accumulate, int round_out, void* stream);
+ * y[M,N] = act(x[M,K] w[N,K]^T * scale[n] + bias[n]); scale NULL -> 1; accumulate!=0 adds into the
+ * existing y; stats (double[2*N]) accumulates column sums / sums of squares of the raw product
+ * (the 7x7 stem runs through this entry as im2col + GEMM and needs BatchNorm statistics).          */
+int pe_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, const float* scale, float* y,
+                  int ldy, int M, int N, int K, int relu, int accumulate, int round_out, double* stats,
+                  void* stream);
 /* dw[N,K] = dy[M,N]^T x[M,K] */
 int pe_linear_wgrad(const float* x, int ldx, const float* dy, int lddy, float* dw, int lddw, int M, int N, int K,
                     void* stream);
@@ -63,6 +66,10 @@ int pe_linear_wgrad(const float* x, int ldx, const float* dy, int lddy, float* d
 int pe_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream);
 /* dst[r][0:cols] = src[r][0:cols] with independent row strides (concat / slicing), optional rounding */
 int pe_copy_cols(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream);
+/* out[r][c] = alpha*a[r][c] + beta*b[r][c] (out may alias a or b): measurement_diff = pre_out - x0bar
+ * (models/naive.py:95, models/time_sensitive.py:224) and gradient joins of the two-headed models */
+int pe_axpby_cols(const float* a, int lda, const float* b, int ldb, float* out, int ldo, int rows, int cols,
+                  float alpha, float beta, int round_tf32, void* stream);
 /* out[c] (+)= sum_r x[r][c] : bias gradients */
 int pe_colsum(const float* x, int ldx, float* out, int rows, int cols, int accumulate, void* stream);
 /* dz = dy * (y > 0) */
@@ -81,20 +88,22 @@ int pe_bn_finalize(double* stats, const float* gamma, const float* beta, float* 
 /* out = act(y*scale[c] + shift[c] (+ residual)) */
 int pe_bn_apply(const float* y, const float* scale, const float* shift, const float* residual, float* out,
                 long long P, int C, int relu, int round_tf32, void* stream);
-/* backward pass 1: g = dout*(out>0 if relu); sums = double[2*C] += (sum g, sum g*xhat) */
-int pe_bn_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                     double* sums, long long P, int C, int relu, void* stream);
+/* backward pass 1: g = (dout + dout2)*(out>0 if relu); sums = double[2*C] += (sum g, sum g*xhat).
+ * dout2 (optional) is the second gradient branch of a residual join, summed on the fly.              */
+int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
+                     const float* invstd, double* sums, long long P, int C, int relu, void* stream);
 /* backward pass 2: dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P); dres = g (optional);
  * dgamma = sum_gx, dbeta = sum_g (written or accumulated).  The caller zeroes `sums` before pass 1.   */
-int pe_bn_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                    const float* gamma, double* sums, float* dy, float* dres, int dres_accumulate, float* dgamma,
-                    float* dbeta, int param_accumulate, long long P, int C, int relu, void* stream);
+int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
+                    const float* invstd, const float* gamma, double* sums, float* dy, float* dres,
+                    int dres_accumulate, float* dgamma, float* dbeta, int param_accumulate, long long P, int C,
+                    int relu, int round_tf32, void* stream);
 
 /* ---- stem pooling + auxiliary BN1 branch (torchvision resnet.py:268-272; models/naive.py:223-231,
  *      models/time_sensitive.py:377-385: Conv2d(64,1,1) + MaxPool2d(2) + Flatten on post-ReLU bn1) -- */
 int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, int H, int W, int C, void* stream);
-int pe_maxpool3x3s2_bwd(const float* dy, const unsigned char* argmax, float* dx, int accumulate, int B, int H,
-                        int W, int C, void* stream);
+int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* argmax, float* dx, int accumulate,
+                        int B, int H, int W, int C, void* stream);
 int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int round_tf32, void* stream);
 int pe_avgpool_bwd(const float* dy, int lddy, float* dx, int B, int HW, int C, void* stream);
 int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, int ldo, unsigned char* argmax,

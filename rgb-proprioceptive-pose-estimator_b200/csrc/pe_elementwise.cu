@@ -36,9 +36,9 @@ __device__ __forceinline__ float4 round4(float4 v) {
 // ---------------------------------------------------------------------------------------------
 template <int KIND>  // 0: (y, y*y)   1: (g, g*xhat) with g = dout * (out > 0 if relu)
 __global__ void __launch_bounds__(EW_THREADS)
-channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
-                      const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ sums,
-                      long long P, int C, int relu) {
+channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ a2, const float* __restrict__ b,
+                      const float* __restrict__ c, const float* __restrict__ mean,
+                      const float* __restrict__ invstd, double* __restrict__ sums, long long P, int C, int relu) {
     __shared__ float sm0[EW_THREADS * 4];
     __shared__ float sm1[EW_THREADS * 4];
     const int G = C >> 2;
@@ -65,6 +65,10 @@ channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, 
             s1.x += y.x * y.x; s1.y += y.y * y.y; s1.z += y.z * y.z; s1.w += y.w * y.w;
         } else {
             float4 d = ld4_stream(a + off);
+            if (a2) {
+                const float4 e = ld4_stream(a2 + off);
+                d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+            }
             if (relu) {
                 const float4 o = ld4_stream(b + off);
                 d.x = o.x > 0.f ? d.x : 0.f;
@@ -169,11 +173,12 @@ bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, co
 // dy = a*g + b*y + c per channel, a = gamma*invstd, b = -a*k2*invstd, c = -a*k1 + a*k2*invstd*mean,
 // k1 = sum_g/P, k2 = sum_gxhat/P.  Coefficients are rebuilt per block into shared memory.
 __global__ void __launch_bounds__(EW_THREADS)
-bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y,
-                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ gamma, const double* __restrict__ sums, float* __restrict__ dy,
-                    float* __restrict__ dres, int dres_acc, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                    int param_acc, long long P, int C, int relu) {
+bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ dout2,
+                    const float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const double* __restrict__ sums, float* __restrict__ dy, float* __restrict__ dres,
+                    int dres_acc, float* __restrict__ dgamma, float* __restrict__ dbeta, int param_acc,
+                    long long P, int C, int relu, int round_out) {
     extern __shared__ float coef[];  // [3][C]
     float* ca = coef;
     float* cb = coef + C;
@@ -199,6 +204,10 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ ou
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const int g = (int)(i % G);
         float4 d = ld4_stream(dout + 4 * i);
+        if (dout2) {
+            const float4 e = ld4_stream(dout2 + 4 * i);
+            d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+        }
         if (relu) {
             const float4 o = ld4_stream(out + 4 * i);
             d.x = o.x > 0.f ? d.x : 0.f;
@@ -222,6 +231,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ ou
         r.y = fmaf(a.y, d.y, fmaf(b.y, yv.y, c.y));
         r.z = fmaf(a.z, d.z, fmaf(b.z, yv.z, c.z));
         r.w = fmaf(a.w, d.w, fmaf(b.w, yv.w, c.w));
+        if (round_out) r = round4(r);
         st4(dy + 4 * i, r);
     }
 }
@@ -318,6 +328,20 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* 
     }
 }
 
+__global__ void axpby_cols_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                  float* __restrict__ out, int ldo, long long rows, int cols, float alpha,
+                                  float beta, int round_out) {
+    const long long n = rows * cols;
+    const long long gs = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        const int c = (int)(i % cols);
+        const long long r = i / cols;
+        float v = alpha * a[r * lda + c] + beta * b[r * ldb + c];
+        if (round_out) v = round_tf32(v);
+        out[r * ldo + c] = v;
+    }
+}
+
 __global__ void colsum_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int rows, int cols,
                               int accumulate) {
     // one warp per column chunk of 32; blockDim = (32, 8): 8 row lanes
@@ -395,8 +419,9 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned 
 }
 
 __global__ void __launch_bounds__(EW_THREADS)
-maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ argmax, float* __restrict__ dx,
-                   int accumulate, int B, int H, int W, int C, int Ho, int Wo) {
+maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
+                   const unsigned char* __restrict__ argmax, float* __restrict__ dx, int accumulate, int B, int H,
+                   int W, int C, int Ho, int Wo) {
     const int G = C >> 2;
     const long long n = (long long)B * H * W * G;
     const long long gs = (long long)gridDim.x * blockDim.x;
@@ -419,7 +444,11 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict
                 const unsigned char k = (unsigned char)(kh * 3 + kw);
                 const long long o = (((long long)b * Ho + ho) * Wo + wo) * G + g;
                 const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + 4 * o);
-                const float4 d = ld4(dy + 4 * o);
+                float4 d = ld4(dy + 4 * o);
+                if (dy2) {
+                    const float4 e = ld4(dy2 + 4 * o);
+                    d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+                }
                 if (am.x == k) acc.x += d.x;
                 if (am.y == k) acc.y += d.y;
                 if (am.z == k) acc.z += d.z;
@@ -583,7 +612,7 @@ int pe_bn_stats(const float* y, long long P, int C, double* stats, void* stream)
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_stats: unsupported channel count %d", C);
     channel_reduce_kernel<0><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        y, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
+        y, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -608,24 +637,25 @@ int pe_bn_apply(const float* y, const float* scale, const float* shift, const fl
     return 0;
 }
 
-int pe_bn_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                     double* sums, long long P, int C, int relu, void* stream) {
+int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
+                     const float* invstd, double* sums, long long P, int C, int relu, void* stream) {
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_bwd_reduce: unsupported channel count %d", C);
     channel_reduce_kernel<1><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dout, out, y, mean, invstd, sums, P, C, relu);
+        dout, dout2, out, y, mean, invstd, sums, P, C, relu);
     PE_LAUNCH_CHECK();
     return 0;
 }
 
-int pe_bn_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                    const float* gamma, double* sums, float* dy, float* dres, int dres_accumulate, float* dgamma,
-                    float* dbeta, int param_accumulate, long long P, int C, int relu, void* stream) {
+int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
+                    const float* invstd, const float* gamma, double* sums, float* dy, float* dres,
+                    int dres_accumulate, float* dgamma, float* dbeta, int param_accumulate, long long P, int C,
+                    int relu, int round_tf32, void* stream) {
     PE_REQUIRE(C % 4 == 0 && C <= 4096, "bn_bwd_apply: unsupported channel count %d", C);
     const long long n4 = P * (C / 4);
     bn_bwd_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
-        dout, out, y, mean, invstd, gamma, sums, dy, dres, dres_accumulate, dgamma, dbeta, param_accumulate, P, C,
-        relu);
+        dout, dout2, out, y, mean, invstd, gamma, sums, dy, dres, dres_accumulate, dgamma, dbeta, param_accumulate,
+        P, C, relu, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -675,6 +705,17 @@ int pe_copy_cols(const float* src, int lds, float* dst, int ldd, int rows, int c
     return 0;
 }
 
+int pe_axpby_cols(const float* a, int lda, const float* b, int ldb, float* out, int ldo, int rows, int cols,
+                  float alpha, float beta, int round_tf32, void* stream) {
+    const long long n = (long long)rows * cols;
+    if (n == 0) return 0;
+    axpby_cols_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, out, ldo,
+                                                                                        rows, cols, alpha, beta,
+                                                                                        round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
 int pe_colsum(const float* x, int ldx, float* out, int rows, int cols, int accumulate, void* stream) {
     dim3 grid((cols + 31) / 32), block(32, 8);
     colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, out, rows, cols, accumulate);
@@ -716,13 +757,13 @@ int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, 
     return 0;
 }
 
-int pe_maxpool3x3s2_bwd(const float* dy, const unsigned char* argmax, float* dx, int accumulate, int B, int H, int W,
-                        int C, void* stream) {
+int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* argmax, float* dx, int accumulate,
+                        int B, int H, int W, int C, void* stream) {
     PE_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * H * W * (C / 4);
     maxpool_bwd_kernel<<<grid_for(n, EW_THREADS, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dy, argmax, dx, accumulate, B, H, W, C, Ho, Wo);
+        dy, dy2, argmax, dx, accumulate, B, H, W, C, Ho, Wo);
     PE_LAUNCH_CHECK();
     return 0;
 }

@@ -520,12 +520,20 @@ int pe_conv2d_wgrad(const float* x, const float* dy, float* dw_tck, int B, int H
     return conv_wgrad_impl(x, dy, dw_tck, B, H, W, Cin, Cout, R, S, stride, pad, (cudaStream_t)stream);
 }
 
-int pe_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy, int M,
-                  int N, int K, int relu, int accumulate, int round_out, void* stream) {
+int pe_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, const float* scale, float* y,
+                  int ldy, int M, int N, int K, int relu, int accumulate, int round_out, double* stats,
+                  void* stream) {
     Epilogue ep;
-    ep.bias = bias;
+    if (scale) {
+        PE_REQUIRE(bias != nullptr, "linear_fwd: scale needs a shift vector in `bias`");
+        ep.scale = scale;
+        ep.shift = bias;
+    } else {
+        ep.bias = bias;
+    }
     ep.relu = relu;
     ep.round_out = round_out;
+    ep.stats = stats;
     return linear_fwd_impl(x, ldx, w, ldw, y, ldy, M, N, K, ep, accumulate, (cudaStream_t)stream);
 }
 

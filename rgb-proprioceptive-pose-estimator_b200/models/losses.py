@@ -1,0 +1,90 @@
+"""Drop-in mirror of the reference's models/losses.py: PoseDistanceLoss on the sm_100a loss kernel.
+
+Same constructor, same `forward(prediction, truth)` contract and error behaviour
+(reference models/losses.py:11-128): modes 'position' / 'pose' return a differentiable scalar (a SUM over
+samples), mode 'val' returns (position error as numpy float32, summed |angle| in radians as float).
+One warp-shuffle reduction kernel (pe_pose_loss) produces the loss, its gradient and the val metrics.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from pe_b200 import native
+
+DISTANCE_METRICS = {"l1", "l2", "linf", "combined"}
+POSE_LOSS_MODES = {"position", "pose", "val"}
+_METRIC_ID = {"l1": 0, "l2": 1, "linf": 2, "combined": 3}
+
+
+class _PoseLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, truth, metric, mode, alpha, eps, scale):
+        n = pred.numel() // 7
+        p = pred.reshape(n, 7)
+        if p.stride(1) != 1:
+            p = p.contiguous()
+        t = truth.reshape(n, 7)
+        if t.stride(1) != 1 or t.dtype != torch.float32:
+            t = t.contiguous().float()
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+        dpred = torch.empty(n, 7, device=pred.device, dtype=torch.float32)
+        L.pe_pose_loss(P(p), p.stride(0), P(t), t.stride(0), n, metric, mode, alpha, eps, scale, P(loss), P(dpred), 7,
+                       None, st)
+        ctx.dpred = dpred
+        ctx.shape = pred.shape
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.dpred.reshape(ctx.shape)
+        return d * g, None, None, None, None, None, None
+
+
+class PoseDistanceLoss(nn.Module):
+    """
+    Simple class to compute pose distance (position distance + orientation distance)
+    """
+
+    def __init__(self, distance_metric="l2", scale_factor=1.0, alpha=1.0, epsilon=1e-4, mode="pose"):
+        super(PoseDistanceLoss, self).__init__()
+        if distance_metric in DISTANCE_METRICS:
+            self.distance_metric = distance_metric
+        else:
+            raise ValueError("Invalid distance metric specified; available are: {}, requested {}.".format(
+                DISTANCE_METRICS, distance_metric))
+        self.scale_factor = scale_factor
+        self.alpha = alpha
+        self.epsilon = epsilon
+        if mode in POSE_LOSS_MODES:
+            self.mode = mode
+        else:
+            raise ValueError("Invalid loss mode specified; available are: {}, requested {}.".format(
+                POSE_LOSS_MODES, mode))
+
+    def forward(self, prediction, truth):
+        if isinstance(prediction, np.ndarray):            # the rollout loop hands numpy arrays in (Q9)
+            prediction = torch.as_tensor(prediction)
+        if isinstance(truth, np.ndarray):
+            truth = torch.as_tensor(truth)
+        if not prediction.is_cuda:
+            raise native.PeError("PoseDistanceLoss (B200 path) needs CUDA tensors; there is no CPU fallback")
+        truth = truth.to(prediction.device)
+        if prediction.dtype != torch.float32:
+            raise native.PeError("prediction must be float32")
+        metric = _METRIC_ID[self.distance_metric]
+        if self.mode == "val":
+            n = prediction.numel() // 7
+            p = prediction.detach().reshape(n, 7)
+            if p.stride(1) != 1:
+                p = p.contiguous()
+            t = truth.detach().reshape(n, 7).contiguous().float()
+            L, st, P = native.lib(), native.stream_ptr(), native.ptr
+            val = torch.empty(2, device=p.device, dtype=torch.float32)
+            L.pe_pose_loss(P(p), p.stride(0), P(t), 7, n, metric, 0, 0.0, float(self.epsilon), 1.0, None, None, 7,
+                           P(val), st)
+            v = val.cpu().numpy()
+            return np.float32(v[0]), float(v[1])
+        mode = 1 if self.mode == "pose" else 0
+        return _PoseLossFn.apply(prediction, truth, metric, mode, float(self.alpha), float(self.epsilon),
+                                 float(self.scale_factor))

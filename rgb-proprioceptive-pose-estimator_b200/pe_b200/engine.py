@@ -1,0 +1,568 @@
+"""Host-side sequencing of the sm_100a kernels for the pose-estimator hot path.
+
+`TrunkEngine` runs the ResNet-50 trunk + auxiliary BN1 branch (forward in train / eval mode, and the
+full backward) on NHWC fp32 activations; `MLPHead`, `LSTMLayer` and friends run the fusion heads.
+Parameters stay in the reference's own module tree / checkpoint layout (OIHW conv weights etc.);
+the engine keeps TF32-rounded packed shadows that are refreshed whenever a parameter changes.
+
+Everything here only *sequences* C-ABI calls (pe_b200.native); there is no torch compute on the
+path and no fallback when the library is missing.
+"""
+import torch
+
+from . import native
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _dev_check(t):
+    if not t.is_cuda:
+        raise native.PeError("the B200 pose-estimator path needs CUDA tensors (got %s); there is no CPU fallback"
+                             % t.device)
+
+
+class Act:
+    """An NHWC activation: tensor [B*H*W, C] (contiguous) plus its geometry."""
+    __slots__ = ("t", "B", "H", "W", "C")
+
+    def __init__(self, t, B, H, W, C):
+        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+
+    @property
+    def P(self):
+        return self.B * self.H * self.W
+
+
+class GradSlots:
+    """Up to two gradient contributions per activation (residual joins are summed by the consumer)."""
+
+    def __init__(self):
+        self.d = {}
+
+    def add(self, act, g):
+        self.d.setdefault(id(act), []).append(g)
+
+    def pop(self, act):
+        gs = self.d.pop(id(act), [])
+        if len(gs) > 2:
+            raise native.PeError("internal: more than two gradient branches for one activation")
+        return (gs + [None, None])[:2]
+
+
+def _params_version(params):
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class TrunkEngine:
+    """ResNet-50 trunk (torchvision layout: conv1, bn1, layer1..4, fc) + optional aux 1x1 conv branch."""
+
+    def __init__(self, net, aux_conv=None, aux_trainable=True):
+        self.net = net
+        self.aux_conv = aux_conv
+        self.aux_trainable = aux_trainable
+        # execution-ordered (conv, bn) pairs
+        self.convs = [(net.conv1, net.bn1)]
+        self.blocks = []
+        for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+            for blk in layer:
+                ids = {}
+                for k in (1, 2, 3):
+                    ids[k] = len(self.convs)
+                    self.convs.append((getattr(blk, "conv%d" % k), getattr(blk, "bn%d" % k)))
+                if blk.downsample is not None:
+                    ids["d"] = len(self.convs)
+                    self.convs.append((blk.downsample[0], blk.downsample[1]))
+                self.blocks.append((blk, ids))
+        self.bn_off = []
+        off = 0
+        for _, bn in self.convs:
+            self.bn_off.append(off)
+            off += bn.num_features
+        self.bn_total = off
+        self._dev = None
+        self._packed_version = None
+        self._eval_version = None
+        self.round_tf32 = 1
+
+    # ------------------------------------------------------------------------------------------
+    def _ensure_device(self, dev):
+        if self._dev == dev:
+            return
+        self._dev = dev
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.scale = torch.empty(self.bn_total, **f32)
+        self.shift = torch.empty(self.bn_total, **f32)
+        self.mean = torch.empty(self.bn_total, **f32)
+        self.invstd = torch.empty(self.bn_total, **f32)
+        self.stats = torch.zeros(2 * self.bn_total, device=dev, dtype=torch.float64)
+        self.sums = torch.zeros(2 * self.bn_total, device=dev, dtype=torch.float64)
+        self.w_tck, self.w_tkc = [], []
+        for i, (conv, _) in enumerate(self.convs):
+            co, ci, r, s = conv.weight.shape
+            if i == 0:
+                self.w_tck.append(torch.zeros(co, 160, **f32))   # stem: [64][160] im2col-ordered, zero padded
+                self.w_tkc.append(None)
+            else:
+                self.w_tck.append(torch.empty(r * s, co, ci, **f32))
+                self.w_tkc.append(torch.empty(r * s, ci, co, **f32))
+        fc = self.net.fc
+        self.fc_w = torch.empty(fc.out_features, fc.in_features, **f32)
+        self.fc_wt = torch.empty(fc.in_features, fc.out_features, **f32)
+        self._packed_version = None
+        self._eval_version = None
+
+    def _weights(self):
+        return [c.weight for c, _ in self.convs] + [self.net.fc.weight]
+
+    def invalidate(self):
+        """Call after parameters were modified behind torch's back (e.g. by the fused optimizer kernel)."""
+        self._packed_version = None
+        self._eval_version = None
+
+    def pack_weights(self, need_dgrad, force=False):
+        """Refresh the TF32-rounded packed shadows if any weight changed since the last call."""
+        ver = (_params_version(self._weights()), need_dgrad)
+        if ver == self._packed_version and not force:
+            return
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        for i, (conv, _) in enumerate(self.convs):
+            w = conv.weight
+            _dev_check(w)
+            co, ci, r, s = w.shape
+            if i == 0:
+                L.pe_copy_cols(P(w), ci * r * s, P(self.w_tck[0]), 160, co, ci * r * s, self.round_tf32, st)
+            else:
+                L.pe_pack_conv_weight(P(w), P(self.w_tck[i]), P(self.w_tkc[i]) if need_dgrad else None, co, ci, r, s,
+                                      self.round_tf32, st)
+        fc = self.net.fc
+        L.pe_copy_cols(P(fc.weight), fc.in_features, P(self.fc_w), fc.in_features, fc.out_features, fc.in_features,
+                       self.round_tf32, st)
+        if need_dgrad:
+            L.pe_transpose(P(fc.weight), fc.in_features, P(self.fc_wt), fc.out_features, fc.out_features,
+                           fc.in_features, self.round_tf32, st)
+        self._packed_version = ver
+
+    def _bn_views(self, i):
+        C = self.convs[i][1].num_features
+        o = self.bn_off[i]
+        return (self.scale[o:o + C], self.shift[o:o + C], self.mean[o:o + C], self.invstd[o:o + C],
+                self.stats[2 * o:2 * o + 2 * C], self.sums[2 * o:2 * o + 2 * C])
+
+    def prepare_eval(self):
+        """Fold running statistics into per-channel scale / shift (cached until a BN tensor changes)."""
+        tensors = []
+        for _, bn in self.convs:
+            tensors += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        ver = _params_version(tensors)
+        if ver == self._eval_version:
+            return
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        for i, (_, bn) in enumerate(self.convs):
+            sc, sh, _, _, _, _ = self._bn_views(i)
+            L.pe_bn_finalize(None, P(bn.weight), P(bn.bias), P(bn.running_mean), P(bn.running_var), P(sc), P(sh),
+                             None, None, 1, BN_MOMENTUM, bn.eps, bn.num_features, st)
+        self._eval_version = ver
+
+    # ------------------------------------------------------------------------------------------
+    def _conv_train(self, x, i, tape):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        conv, bn = self.convs[i]
+        co, ci, r, s = conv.weight.shape
+        stride, pad = conv.stride[0], conv.padding[0]
+        Ho = (x.H + 2 * pad - r) // stride + 1
+        Wo = (x.W + 2 * pad - s) // stride + 1
+        y = Act(torch.empty(x.B * Ho * Wo, co, device=x.t.device, dtype=torch.float32), x.B, Ho, Wo, co)
+        stats = self._bn_views(i)[4]
+        L.pe_conv2d_fwd(P(x.t), P(self.w_tck[i]), P(y.t), x.B, x.H, x.W, ci, co, r, s, stride, pad, None, None, None,
+                        0, 0, P(stats), st)
+        if tape is not None:
+            tape.append(("conv", i, x, y))
+        return y
+
+    def _bn_train(self, y, i, relu, residual, tape, update_running=True):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        _, bn = self.convs[i]
+        sc, sh, mean, invstd, stats, _ = self._bn_views(i)
+        L.pe_bn_finalize(P(stats), P(bn.weight), P(bn.bias), P(bn.running_mean) if update_running else None,
+                         P(bn.running_var) if update_running else None, P(sc), P(sh), P(mean), P(invstd), y.P,
+                         bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps, y.C, st)
+        out = Act(torch.empty_like(y.t), y.B, y.H, y.W, y.C)
+        L.pe_bn_apply(P(y.t), P(sc), P(sh), P(residual.t) if residual is not None else None, P(out.t), y.P, y.C,
+                      int(relu), self.round_tf32, st)
+        if tape is not None:
+            tape.append(("bn", i, y, out, relu, residual))
+        return out
+
+    def _conv_eval(self, x, i, relu, residual):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        conv, bn = self.convs[i]
+        co, ci, r, s = conv.weight.shape
+        stride, pad = conv.stride[0], conv.padding[0]
+        Ho = (x.H + 2 * pad - r) // stride + 1
+        Wo = (x.W + 2 * pad - s) // stride + 1
+        y = Act(torch.empty(x.B * Ho * Wo, co, device=x.t.device, dtype=torch.float32), x.B, Ho, Wo, co)
+        sc, sh = self._bn_views(i)[:2]
+        L.pe_conv2d_fwd(P(x.t), P(self.w_tck[i]), P(y.t), x.B, x.H, x.W, ci, co, r, s, stride, pad, P(sc), P(sh),
+                        P(residual.t) if residual is not None else None, int(relu), self.round_tf32, None, st)
+        return y
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, img, training, need_grad, feat_out, ld_feat, aux_out=None, ld_aux=0):
+        """img: (B,3,224,224) NCHW fp32 CUDA.  Writes latent features into feat_out[:, :latent] (row stride
+        ld_feat) and, when the aux branch exists, its 3136-vector into aux_out (row stride ld_aux).
+        Returns a context for backward (None unless need_grad)."""
+        _dev_check(img)
+        if img.dtype != torch.float32:
+            raise native.PeError("image tensor must be float32")
+        img = img.contiguous()
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        self._ensure_device(img.device)
+        self.pack_weights(need_grad, force=training)
+        if training:
+            self._eval_version = None   # scale/shift arenas are about to hold batch statistics
+        B, Cimg, H, W = img.shape
+        conv1 = self.net.conv1
+        r, s = conv1.weight.shape[2:]
+        stride, pad = conv1.stride[0], conv1.padding[0]
+        Ho, Wo = (H + 2 * pad - r) // stride + 1, (W + 2 * pad - s) // stride + 1
+        tape = [] if need_grad else None
+        dev = img.device
+
+        # ---- stem: im2col + GEMM (+BN1, ReLU), 3x3/2 max pool, aux branch -------------------------
+        col = torch.empty(B * Ho * Wo, 160, device=dev, dtype=torch.float32)
+        L.pe_im2col_stem(P(img), P(col), B, Cimg, H, W, r, s, stride, pad, 160, self.round_tf32, st)
+        y0 = Act(torch.empty(B * Ho * Wo, 64, device=dev, dtype=torch.float32), B, Ho, Wo, 64)
+        if training:
+            self.stats.zero_()
+            L.pe_linear_fwd(P(col), 160, P(self.w_tck[0]), 160, None, None, P(y0.t), 64, y0.P, 64, 160, 0, 0, 0,
+                            P(self._bn_views(0)[4]), st)
+            if tape is not None:
+                tape.append(("stem", col, y0))
+            a1 = self._bn_train(y0, 0, True, None, tape)
+        else:
+            self.prepare_eval()
+            sc, sh = self._bn_views(0)[:2]
+            L.pe_linear_fwd(P(col), 160, P(self.w_tck[0]), 160, P(sh), P(sc), P(y0.t), 64, y0.P, 64, 160, 1, 0,
+                            self.round_tf32, None, st)
+            a1 = y0
+            del col
+        Hp, Wp = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
+        x = Act(torch.empty(B * Hp * Wp, 64, device=dev, dtype=torch.float32), B, Hp, Wp, 64)
+        argmax = torch.empty(B * Hp * Wp * 64, device=dev, dtype=torch.uint8) if need_grad else None
+        L.pe_maxpool3x3s2_fwd(P(a1.t), P(x.t), P(argmax), B, Ho, Wo, 64, st)
+        if tape is not None:
+            tape.append(("maxpool", a1, x, argmax))
+        if self.aux_conv is not None:
+            aux_am = torch.empty(B * (Ho // 2) * (Wo // 2), device=dev, dtype=torch.uint8) if need_grad else None
+            L.pe_aux_fwd(P(a1.t), P(self.aux_conv.weight), P(self.aux_conv.bias), P(aux_out), ld_aux, P(aux_am), B,
+                         Ho, Wo, 64, self.round_tf32, st)
+            if tape is not None:
+                tape.append(("aux", a1, aux_am))
+
+        # ---- bottleneck stages ------------------------------------------------------------------
+        for blk, ids in self.blocks:
+            if training:
+                o = self._bn_train(self._conv_train(x, ids[1], tape), ids[1], True, None, tape)
+                o = self._bn_train(self._conv_train(o, ids[2], tape), ids[2], True, None, tape)
+                y3 = self._conv_train(o, ids[3], tape)
+                if "d" in ids:
+                    idn = self._bn_train(self._conv_train(x, ids["d"], tape), ids["d"], False, None, tape)
+                else:
+                    idn = x
+                x = self._bn_train(y3, ids[3], True, idn, tape)
+            else:
+                o = self._conv_eval(x, ids[1], True, None)
+                o = self._conv_eval(o, ids[2], True, None)
+                idn = self._conv_eval(x, ids["d"], False, None) if "d" in ids else x
+                x = self._conv_eval(o, ids[3], True, idn)
+
+        # ---- global average pool + fc -----------------------------------------------------------
+        fc = self.net.fc
+        pool = torch.empty(B, x.C, device=dev, dtype=torch.float32)
+        L.pe_avgpool_fwd(P(x.t), P(pool), x.C, B, x.H * x.W, x.C, self.round_tf32, st)
+        L.pe_linear_fwd(P(pool), x.C, P(self.fc_w), x.C, P(fc.bias), None, P(feat_out), ld_feat, B, fc.out_features,
+                        x.C, 0, 0, self.round_tf32, None, st)
+        if training:
+            for _, bn in self.convs:
+                L.pe_add_i64(P(bn.num_batches_tracked), 1, 1, st)
+        if tape is None:
+            return None
+        tape.append(("tail", x, pool))
+        return {"tape": tape, "B": B}
+
+    # ------------------------------------------------------------------------------------------
+    def backward(self, ctx, d_feat, ld_dfeat, d_aux, ld_daux, grad_of):
+        """d_feat: gradient w.r.t. the latent features (row stride ld_dfeat); d_aux likewise for the aux
+        vector.  `grad_of(param)` returns the tensor that receives that parameter's gradient."""
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        tape = ctx["tape"]
+        B = ctx["B"]
+        slots = GradSlots()
+        dev = self.scale.device
+        self.sums.zero_()
+        rt = self.round_tf32
+        for rec in reversed(tape):
+            kind = rec[0]
+            if kind == "tail":
+                _, x, pool = rec
+                fc = self.net.fc
+                nin, nout = fc.in_features, fc.out_features
+                # rounded copy of d_feat so that the TF32 truncation of the MMA operand is unbiased
+                dfr = torch.empty(B, nout, device=dev, dtype=torch.float32)
+                L.pe_copy_cols(P(d_feat), ld_dfeat, P(dfr), nout, B, nout, rt, st)
+                L.pe_linear_wgrad(P(pool), nin, P(dfr), nout, P(grad_of(fc.weight)), nin, B, nout, nin, st)
+                L.pe_colsum(P(dfr), nout, P(grad_of(fc.bias)), B, nout, 0, st)
+                dpool = torch.empty(B, nin, device=dev, dtype=torch.float32)
+                L.pe_linear_fwd(P(dfr), nout, P(self.fc_wt), nout, None, None, P(dpool), nin, B, nin, nout, 0, 0, 0,
+                                None, st)
+                dx = torch.empty_like(x.t)
+                L.pe_avgpool_bwd(P(dpool), nin, P(dx), B, x.H * x.W, x.C, st)
+                slots.add(x, dx)
+            elif kind == "bn":
+                _, i, y, out, relu, residual = rec
+                _, bn = self.convs[i]
+                _, _, mean, invstd, _, sums = self._bn_views(i)
+                d1, d2 = slots.pop(out)
+                L.pe_bn_bwd_reduce(P(d1), P(d2), P(out.t), P(y.t), P(mean), P(invstd), P(sums), y.P, y.C, int(relu),
+                                   st)
+                dy = torch.empty_like(y.t)
+                dres = torch.empty_like(y.t) if residual is not None else None
+                L.pe_bn_bwd_apply(P(d1), P(d2), P(out.t), P(y.t), P(mean), P(invstd), P(bn.weight), P(sums), P(dy),
+                                  P(dres), 0, P(grad_of(bn.weight)), P(grad_of(bn.bias)), 0, y.P, y.C, int(relu), rt,
+                                  st)
+                slots.add(y, dy)
+                if residual is not None:
+                    slots.add(residual, dres)
+            elif kind == "conv":
+                _, i, x, y = rec
+                conv, _ = self.convs[i]
+                co, ci, r, s = conv.weight.shape
+                stride, pad = conv.stride[0], conv.padding[0]
+                dy, none = slots.pop(y)
+                assert none is None
+                gw = grad_of(conv.weight)
+                if r == 1 and s == 1:
+                    L.pe_conv2d_wgrad(P(x.t), P(dy), P(gw), x.B, x.H, x.W, ci, co, r, s, stride, pad, st)
+                else:
+                    tmp = torch.empty(r * s, co, ci, device=dev, dtype=torch.float32)
+                    L.pe_conv2d_wgrad(P(x.t), P(dy), P(tmp), x.B, x.H, x.W, ci, co, r, s, stride, pad, st)
+                    L.pe_unpack_conv_wgrad(P(tmp), P(gw), co, ci, r, s, 0, st)
+                dx = torch.empty_like(x.t)
+                L.pe_conv2d_dgrad(P(dy), P(self.w_tkc[i]), P(dx), x.B, x.H, x.W, ci, co, r, s, stride, pad, st)
+                slots.add(x, dx)
+            elif kind == "maxpool":
+                _, a1, x, argmax = rec
+                d1, d2 = slots.pop(x)
+                da1 = torch.empty_like(a1.t)
+                L.pe_maxpool3x3s2_bwd(P(d1), P(d2), P(argmax), P(da1), 0, a1.B, a1.H, a1.W, a1.C, st)
+                slots.add(a1, da1)
+            elif kind == "aux":
+                _, a1, aux_am = rec
+                # runs AFTER the maxpool record in reversed order? no: "aux" was taped after "maxpool",
+                # so it is visited first -> seed the slot with a zero-initialised accumulate target.
+                da1_aux = torch.empty_like(a1.t)
+                gw = gb = None
+                if self.aux_trainable:
+                    gw, gb = grad_of(self.aux_conv.weight), grad_of(self.aux_conv.bias)
+                    gw.zero_()
+                    gb.zero_()
+                L.pe_aux_bwd(P(d_aux), ld_daux, P(aux_am), P(a1.t), P(self.aux_conv.weight), P(da1_aux), 0, P(gw),
+                             P(gb), a1.B, a1.H, a1.W, a1.C, st)
+                slots.add(a1, da1_aux)
+            elif kind == "stem":
+                _, col, y0 = rec
+                dy, none = slots.pop(y0)
+                conv1 = self.net.conv1
+                co, ci, r, s = conv1.weight.shape
+                k = ci * r * s
+                tmp = torch.empty(co, 160, device=dev, dtype=torch.float32)
+                L.pe_linear_wgrad(P(col), 160, P(dy), co, P(tmp), 160, y0.P, co, 160, st)
+                L.pe_copy_cols(P(tmp), 160, P(grad_of(conv1.weight)), k, co, k, 0, st)
+            else:
+                raise native.PeError("internal: unknown tape record %r" % (kind,))
+
+    def parameters_in_backward_order(self):
+        """Parameters grouped in the order their gradients become final (for bucketed all-reduce)."""
+        groups = [[self.net.fc.weight, self.net.fc.bias]]
+        for blk, ids in reversed(self.blocks):
+            g = []
+            for key in (3, "d", 2, 1):
+                if key in ids:
+                    conv, bn = self.convs[ids[key]]
+                    g += [conv.weight, bn.weight, bn.bias]
+            groups.append(g)
+        stem = [self.net.conv1.weight, self.net.bn1.weight, self.net.bn1.bias]
+        if self.aux_conv is not None and self.aux_trainable:
+            stem += [self.aux_conv.weight, self.aux_conv.bias]
+        groups.append(stem)
+        return groups
+
+
+# ================================================================================================
+# heads
+# ================================================================================================
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _pad32(n):
+    return (n + 31) // 32 * 32
+
+
+class LinearOp:
+    """y = act(x W^T + b) through the tap-GEMM; keeps TF32-rounded W (K padded to ld_in) and W^T shadows."""
+
+    def __init__(self, linear, ld_in=None):
+        self.lin = linear
+        self.nin, self.nout = linear.in_features, linear.out_features
+        self.ld_in = ld_in or _pad4(self.nin)
+        self.ld_out = _pad4(self.nout)
+        self._ver = None
+        self.w = self.wt = None
+
+    def pack(self, need_dgrad, round_tf32=1):
+        lin = self.lin
+        _dev_check(lin.weight)
+        ver = (_params_version([lin.weight]), need_dgrad)
+        if ver == self._ver:
+            return
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        dev = lin.weight.device
+        if self.w is None or self.w.device != dev:
+            self.w = torch.zeros(self.nout, self.ld_in, device=dev, dtype=torch.float32)
+            # rows padded so a dgrad GEMM may ask for a few columns past nin (they come out as zeros)
+            self.wt = torch.zeros(_pad32(self.nin), self.ld_out, device=dev, dtype=torch.float32)
+        L.pe_copy_cols(P(lin.weight), self.nin, P(self.w), self.ld_in, self.nout, self.nin, round_tf32, st)
+        if need_dgrad:
+            L.pe_transpose(P(lin.weight), self.nin, P(self.wt), self.ld_out, self.nout, self.nin, round_tf32, st)
+        self._ver = ver
+
+    def forward(self, x, ldx, M, y, ldy, relu=False, accumulate=False, round_out=1, bias=True):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        L.pe_linear_fwd(P(x), ldx, P(self.w), self.ld_in, P(self.lin.bias) if bias else None, None, P(y), ldy, M,
+                        self.nout, self.nin, int(relu), int(accumulate), round_out, None, st)
+
+    def backward(self, x, ldx, M, dy, lddy, grad_of, dx=None, lddx=0, dx_cols=None, bias_grad=True,
+                 accumulate_w=False):
+        """dy must be TF32-rounded, zero in its padding columns (lddy = ld_out).  dx_cols limits how many
+        input columns get a gradient (the rest of the concat buffer does not need one)."""
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        gw = grad_of(self.lin.weight)
+        if accumulate_w:
+            tmp = torch.empty_like(gw)
+            L.pe_linear_wgrad(P(x), ldx, P(dy), lddy, P(tmp), self.nin, M, self.nout, self.nin, st)
+            gw.add_(tmp)
+        else:
+            L.pe_linear_wgrad(P(x), ldx, P(dy), lddy, P(gw), self.nin, M, self.nout, self.nin, st)
+        if bias_grad:
+            L.pe_colsum(P(dy), lddy, P(grad_of(self.lin.bias)), M, self.nout, 0, st)
+        if dx is not None:
+            n = dx_cols if dx_cols is not None else self.nin
+            L.pe_linear_fwd(P(dy), lddy, P(self.wt), self.ld_out, None, None, P(dx), lddx, M, n, self.nout, 0, 0, 0,
+                            None, st)
+
+
+class LSTMOp:
+    """Single-layer seq-major nn.LSTM (gates i,f,g,o): one big input-projection GEMM, then per-step
+    recurrent GEMM + fused cell kernel; BPTT in reverse with the mirrored kernels."""
+
+    def __init__(self, lstm, ld_in):
+        self.lstm = lstm
+        self.nin, self.H = lstm.input_size, lstm.hidden_size
+        self.ld_in = ld_in
+        self._ver = None
+        self.w_ih = self.w_ih_t = self.w_hh = self.w_hh_t = None
+
+    def pack(self, need_dgrad, round_tf32=1):
+        lstm = self.lstm
+        _dev_check(lstm.weight_ih_l0)
+        ver = (_params_version([lstm.weight_ih_l0, lstm.weight_hh_l0]), need_dgrad)
+        if ver == self._ver:
+            return
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        dev = lstm.weight_ih_l0.device
+        G, H = 4 * self.H, self.H
+        if self.w_ih is None or self.w_ih.device != dev:
+            self.w_ih = torch.zeros(G, self.ld_in, device=dev, dtype=torch.float32)
+            self.w_ih_t = torch.zeros(_pad32(self.nin), G, device=dev, dtype=torch.float32)
+            self.w_hh = torch.empty(G, H, device=dev, dtype=torch.float32)
+            self.w_hh_t = torch.empty(H, G, device=dev, dtype=torch.float32)
+        L.pe_copy_cols(P(lstm.weight_ih_l0), self.nin, P(self.w_ih), self.ld_in, G, self.nin, round_tf32, st)
+        L.pe_copy_cols(P(lstm.weight_hh_l0), H, P(self.w_hh), H, G, H, round_tf32, st)
+        if need_dgrad:
+            L.pe_transpose(P(lstm.weight_ih_l0), self.nin, P(self.w_ih_t), G, G, self.nin, round_tf32, st)
+            L.pe_transpose(P(lstm.weight_hh_l0), H, P(self.w_hh_t), G, G, H, round_tf32, st)
+        self._ver = ver
+
+    def forward(self, x, S, N, h0=None, c0=None, need_grad=False):
+        """x: [S*N, ld_in] (TF32-rounded, zero padded).  Returns (h_all [S*N, H], h_last, c_last, ctx)."""
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        lstm = self.lstm
+        dev = x.device
+        G, H = 4 * self.H, self.H
+        gx = torch.empty(S * N, G, device=dev, dtype=torch.float32)
+        L.pe_linear_fwd(P(x), self.ld_in, P(self.w_ih), self.ld_in, None, None, P(gx), G, S * N, G, self.nin, 0, 0, 0,
+                        None, st)
+        h_all = torch.empty(S * N, H, device=dev, dtype=torch.float32)
+        c_all = torch.empty(S * N, H, device=dev, dtype=torch.float32)
+        act = torch.empty(S * N, G, device=dev, dtype=torch.float32) if need_grad else None
+        gh = torch.empty(N, G, device=dev, dtype=torch.float32)
+        h_prev, c_prev = h0, c0
+        for t in range(S):
+            gh_t = None
+            if h_prev is not None:
+                L.pe_linear_fwd(P(h_prev), H, P(self.w_hh), H, None, None, P(gh), G, N, G, H, 0, 0, 0, None, st)
+                gh_t = gh
+            L.pe_lstm_cell_fwd(P(gx[t * N:]), G, P(gh_t), G, P(lstm.bias_ih_l0), P(lstm.bias_hh_l0), P(c_prev),
+                               P(c_all[t * N:]), P(h_all[t * N:]), H, P(act[t * N:]) if act is not None else None, N,
+                               H, 1, st)
+            h_prev, c_prev = h_all[t * N:(t + 1) * N], c_all[t * N:(t + 1) * N]
+        ctx = None
+        if need_grad:
+            ctx = dict(x=x, S=S, N=N, h_all=h_all, c_all=c_all, act=act, h0=h0, c0=c0)
+        return h_all, h_prev, c_prev, ctx
+
+    def backward(self, ctx, dh_all, grad_of, dx=None, lddx=0, dx_cols=None):
+        """dh_all: [S*N, H] gradient w.r.t. every hidden output.  Writes parameter grads; optionally
+        dx[:, :dx_cols] = gradient w.r.t. the LSTM input."""
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        lstm = self.lstm
+        S, N, H = ctx["S"], ctx["N"], self.H
+        G = 4 * H
+        dev = dh_all.device
+        h_all, c_all, act = ctx["h_all"], ctx["c_all"], ctx["act"]
+        dg = torch.empty(S * N, G, device=dev, dtype=torch.float32)
+        dh_rec = None
+        dc = None
+        dhr_buf = torch.empty(N, H, device=dev, dtype=torch.float32)
+        dc_bufs = [torch.empty(N, H, device=dev, dtype=torch.float32) for _ in range(2)]
+        for t in range(S - 1, -1, -1):
+            c_prev = c_all[(t - 1) * N:] if t > 0 else ctx["c0"]
+            dc_new = dc_bufs[t & 1]
+            L.pe_lstm_cell_bwd(P(dh_all[t * N:]), H, P(dh_rec), P(dc), P(act[t * N:]), P(c_prev), P(c_all[t * N:]),
+                               P(dg[t * N:]), G, P(dc_new), N, H, st)
+            dc = dc_new
+            if t > 0 or ctx["h0"] is not None:
+                L.pe_linear_fwd(P(dg[t * N:]), G, P(self.w_hh_t), G, None, None, P(dhr_buf), H, N, H, G, 0, 0, 0,
+                                None, st)
+                dh_rec = dhr_buf
+        # round dg once for the three big GEMMs that consume it as a TF32 operand
+        L.pe_copy_cols(P(dg), G, P(dg), G, S * N, G, 1, st)
+        L.pe_linear_wgrad(P(ctx["x"]), self.ld_in, P(dg), G, P(grad_of(lstm.weight_ih_l0)), self.nin, S * N, G,
+                          self.nin, st)
+        g_hh = grad_of(lstm.weight_hh_l0)
+        if S > 1:
+            L.pe_linear_wgrad(P(h_all), H, P(dg[N:]), G, P(g_hh), H, (S - 1) * N, G, H, st)
+        else:
+            g_hh.zero_()
+        if ctx["h0"] is not None:
+            tmp = torch.empty_like(g_hh)
+            L.pe_linear_wgrad(P(ctx["h0"]), H, P(dg), G, P(tmp), H, N, G, H, st)
+            g_hh.add_(tmp)
+        g_bih = grad_of(lstm.bias_ih_l0)
+        L.pe_colsum(P(dg), G, P(g_bih), S * N, G, 0, st)
+        L.pe_copy_cols(P(g_bih), G, P(grad_of(lstm.bias_hh_l0)), G, 1, G, 0, st)
+        if dx is not None:
+            n = dx_cols if dx_cols is not None else self.nin
+            L.pe_linear_fwd(P(dg), G, P(self.w_ih_t), G, None, None, P(dx), lddx, S * N, n, G, 0, 0, 0, None, st)

@@ -60,7 +60,7 @@ def check_linear(M, N, K, relu=False, bias=True, ldpad=0):
     b = torch.randn(N, device=DEV, generator=g) if bias else None
     ldy = ((N + 3) // 4) * 4
     y = torch.full((M, ldy), float("nan"), device=DEV)
-    L.pe_linear_fwd(P(x), ldx, P(w), ldx, P(b), P(y), ldy, M, N, K, int(relu), 0, 0, S())
+    L.pe_linear_fwd(P(x), ldx, P(w), ldx, P(b), None, P(y), ldy, M, N, K, int(relu), 0, 0, None, S())
     ref = x[:, :K].double() @ w[:, :K].double().t()
     if bias:
         ref = ref + b.double()
@@ -76,7 +76,7 @@ def check_linear_acc(M, N, K):
     w = tf32(torch.randn(N, K, device=DEV, generator=g))
     y0 = torch.randn(M, N, device=DEV, generator=g)
     y = y0.clone()
-    L.pe_linear_fwd(P(x), K, P(w), K, None, P(y), N, M, N, K, 0, 1, 0, S())
+    L.pe_linear_fwd(P(x), K, P(w), K, None, None, P(y), N, M, N, K, 0, 1, 0, None, S())
     ref = y0.double() + x.double() @ w.double().t()
     return [("linear_fwd accumulate M%d N%d K%d" % (M, N, K), relerr(y, ref), 1e-4)]
 
@@ -177,7 +177,7 @@ def check_stem(B):
     wp = torch.zeros(64, ldc, device=DEV)
     wp[:, :147] = w.reshape(64, 147)
     y = torch.full((B * 112 * 112, 64), float("nan"), device=DEV)
-    L.pe_linear_fwd(P(col), ldc, P(wp), ldc, None, P(y), 64, B * 112 * 112, 64, ldc, 0, 0, 0, S())
+    L.pe_linear_fwd(P(col), ldc, P(wp), ldc, None, None, P(y), 64, B * 112 * 112, 64, ldc, 0, 0, 0, None, S())
     ref = nhwc(F.conv2d(img.double(), w.double(), stride=2, padding=3)).reshape(-1, 64)
     out = [("stem conv (im2col+gemm) B%d" % B, relerr(y, ref), 1e-4)]
     unf = F.unfold(img, kernel_size=7, stride=2, padding=3).transpose(1, 2).reshape(-1, 147)
@@ -228,13 +228,15 @@ def check_bn(Pn, C, relu=True, residual=True):
     ins = (yd, gd, bd) + ((rd,) if residual else ())
     grads = torch.autograd.grad(z, ins, dout.double())
     sums = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
-    L.pe_bn_bwd_reduce(P(dout), P(o), P(y), P(mean), P(invstd), P(sums), Pn, C, int(relu), S())
+    dout_a = dout * 0.25
+    dout_b = dout - dout_a
+    L.pe_bn_bwd_reduce(P(dout_a), P(dout_b), P(o), P(y), P(mean), P(invstd), P(sums), Pn, C, int(relu), S())
     dy = torch.empty(Pn, C, device=DEV)
     dres = torch.empty(Pn, C, device=DEV) if residual else None
     dgamma = torch.empty(C, device=DEV)
     dbeta = torch.empty(C, device=DEV)
-    L.pe_bn_bwd_apply(P(dout), P(o), P(y), P(mean), P(invstd), P(gamma), P(sums), P(dy), P(dres), 0, P(dgamma),
-                      P(dbeta), 0, Pn, C, int(relu), S())
+    L.pe_bn_bwd_apply(P(dout_a), P(dout_b), P(o), P(y), P(mean), P(invstd), P(gamma), P(sums), P(dy), P(dres), 0,
+                      P(dgamma), P(dbeta), 0, Pn, C, int(relu), 0, S())
     out.append(("bn_bwd dy " + tag, relerr(dy, grads[0]), 1e-4))
     out.append(("bn_bwd dgamma " + tag, relerr(dgamma, grads[1]), 1e-4))
     out.append(("bn_bwd dbeta " + tag, relerr(dbeta, grads[2]), 1e-4))
@@ -263,7 +265,7 @@ def check_pools(B):
     L.pe_maxpool3x3s2_fwd(P(xn), P(y), P(am), B, 112, 112, 64, S())
     out.append(("maxpool fwd B%d" % B, relerr(y, nhwc(yd.detach())), 0.0))
     dx = torch.full((B, 112, 112, 64), float("nan"), device=DEV)
-    L.pe_maxpool3x3s2_bwd(P(nhwc(dyv.float())), P(am), P(dx), 0, B, 112, 112, 64, S())
+    L.pe_maxpool3x3s2_bwd(P(nhwc(dyv.float())), None, P(am), P(dx), 0, B, 112, 112, 64, S())
     # ties only happen at 0 where the ReLU mask kills the gradient anyway -> compare on x > 0
     mask = (xn > 0).double()
     out.append(("maxpool bwd B%d" % B, relerr(dx.double() * mask, nhwc(gx) * mask), 1e-6))

@@ -1,0 +1,205 @@
+"""End-to-end parity of the CUDA estimators against the CPU oracle (GPU only).
+
+`python tests/model_checks.py [kinds...]` prints per-output / per-parameter errors without stopping;
+tests/test_models_gpu.py asserts on the same numbers.  Tolerances (TF32 operands, fp32 accumulate):
+outputs and loss 1e-3 relative (north_star), gradients ||g-g_ref|| / ||g_ref|| <= 1e-2 per parameter.
+"""
+import contextlib
+import io
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "rgb-proprioceptive-pose-estimator_b200"))
+sys.path.insert(0, ROOT)
+
+from oracle import pose_oracle as po  # noqa: E402
+
+CONFIGS = {
+    # kind: (ctor kwargs, loss kwargs)  -- hyper-parameters from scripts/train_no.sbatch / train_tdo.sbatch
+    "no": dict(latent=512, hidden=[1024, 256, 64], loss=dict(distance_metric="combined", alpha=0.5, mode="pose")),
+    "tdo": dict(latent=512, hidden=512, loss=dict(distance_metric="combined", alpha=0.5, mode="pose")),
+    "td": dict(latent=1024, hidden=512, loss=dict(distance_metric="l2", alpha=0.5, mode="pose")),
+    "n": dict(latent=1024, hidden=[512], loss=dict(distance_metric="l2", alpha=0.5, mode="pose")),
+}
+
+
+def build_model(kind, seed=0):
+    import models.naive as mn
+    import models.time_sensitive as mt
+    import util.model_utils as mu
+    cfg = CONFIGS[kind]
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if kind == "no":
+            return mn.NaiveObjectStateEstimator("cube", list(cfg["hidden"]), 50, cfg["latent"], False, (9,), False,
+                                                False)
+        if kind == "tdo":
+            return mt.TemporallyDependentObjectStateEstimator("robot1_eef", cfg["hidden"], 50, cfg["latent"], 20,
+                                                              feature_extract=False, use_pretrained=False)
+        if kind == "td":
+            return mt.TemporallyDependentStateEstimator(cfg["hidden"], cfg["hidden"], 50, cfg["latent"], 10,
+                                                        feature_extract=False, use_pretrained=False)
+        if kind == "n":
+            orig = mn.import_resnet
+            mn.import_resnet = lambda n, o, fe=True, use_pretrained=True: orig(n, o, fe, use_pretrained=False)
+            try:
+                return mn.NaiveEndEffectorStateEstimator(list(cfg["hidden"]), list(cfg["hidden"]), 50, cfg["latent"],
+                                                         False)
+            finally:
+                mn.import_resnet = orig
+    raise ValueError(kind)
+
+
+def oracle_for(kind, model):
+    extra = None
+    if kind == "td":
+        extra = {"aux_w": model.aux_nets[0][0].weight.detach().cpu(), "aux_b": model.aux_nets[0][0].bias.detach().cpu()}
+    return po.OracleEstimator(kind, {k: v.detach().cpu() for k, v in model.state_dict().items()}, extra)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def relnorm(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def check_train_step(kind, n=2, s=2, seed=1, verbose=False):
+    """forward (train mode) + loss + backward vs oracle.  Returns rows (name, err, tol)."""
+    from models.losses import PoseDistanceLoss
+    cfg = CONFIGS[kind]
+    model = build_model(kind)
+    orc = oracle_for(kind, model)
+    if kind in ("no", "n"):
+        img, x0, tgt = po.synthetic_batch(kind, n, seed=seed)
+    else:
+        img, x0, tgt = po.synthetic_batch(kind, n, s=s, seed=seed)
+    lk = cfg["loss"]
+    t0 = time.time()
+    if kind in ("no", "tdo"):
+        outs_ref, loss_ref, grads_ref = orc.loss_and_grads(img, x0, tgt, lk)
+        outs_ref = (outs_ref,)
+    else:
+        # two-headed models train on loss(pre, x0) + loss(post, x1)  (util/learn_utils.py:166-172)
+        for k in orc.param_names:
+            orc.sd[k].requires_grad_(True)
+            orc.sd[k].grad = None
+        pre, post = orc.forward(img, x0, training=True)
+        loss_ref = po.pose_loss(pre, x0, **lk) + po.pose_loss(post, tgt, **lk)
+        loss_ref.backward()
+        grads_ref = {k: orc.sd[k].grad for k in orc.param_names}
+        for k in orc.param_names:
+            orc.sd[k].requires_grad_(False)
+        outs_ref = (pre.detach(), post.detach())
+        loss_ref = loss_ref.detach()
+    t_cpu = time.time() - t0
+
+    model.cuda().train()
+    crit = PoseDistanceLoss(distance_metric=lk["distance_metric"], alpha=lk["alpha"], mode=lk["mode"])
+    if kind in ("td", "tdo"):
+        model.reset_initial_state(n)
+    out = model(img.cuda(), None, x0.cuda())
+    outs = out if isinstance(out, tuple) else (out,)
+    if kind in ("no", "tdo"):
+        loss = crit(outs[0], tgt.cuda())
+    else:
+        loss = crit(outs[0], x0.cuda()) + crit(outs[1], tgt.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    rows = []
+    tag = "%s n%d" % (kind, n) + ("" if kind in ("no", "n") else " s%d" % s)
+    for i, (a, b) in enumerate(zip(outs, outs_ref)):
+        rows.append(("%s out%d" % (tag, i), rel(a, b), 1e-3))
+    rows.append(("%s loss" % tag, rel(loss.reshape(1), loss_ref.reshape(1)), 1e-3))
+    named = dict(model.named_parameters())
+    worst = []
+    for k in orc.param_names:
+        g_ref = grads_ref[k]
+        g = named[k].grad
+        if g_ref is None:
+            rows.append(("%s grad %s is None" % (tag, k), 0.0 if g is None else 1.0, 0.0))
+            continue
+        if g is None:
+            rows.append(("%s grad %s MISSING" % (tag, k), 1.0, 0.0))
+            continue
+        worst.append((relnorm(g, g_ref), k))
+    worst.sort(reverse=True)
+    for e, k in (worst if verbose else worst[:6]):
+        rows.append(("%s grad %s" % (tag, k), e, 1e-2))
+    # running statistics after one training forward
+    sd = model.state_dict()
+    e_rm = max(rel(sd[k], orc.sd[k]) for k in sd if k.endswith("running_mean"))
+    e_rv = max(rel(sd[k], orc.sd[k]) for k in sd if k.endswith("running_var"))
+    nbt_ok = all(int(sd[k]) == int(orc.sd[k]) for k in sd if k.endswith("num_batches_tracked"))
+    rows.append(("%s running_mean (max over BNs)" % tag, e_rm, 2e-3))
+    rows.append(("%s running_var (max over BNs)" % tag, e_rv, 2e-3))
+    rows.append(("%s num_batches_tracked" % tag, 0.0 if nbt_ok else 1.0, 0.0))
+    rows.append(("%s [oracle cpu seconds]" % tag, t_cpu, float("inf")))
+
+    # eval-mode forward with the same (now updated) running statistics
+    model.eval()
+    with torch.no_grad():
+        if kind in ("td", "tdo"):
+            model.reset_initial_state(n)
+        oe = model(img.cuda(), None, x0.cuda())
+    oe = oe if isinstance(oe, tuple) else (oe,)
+    ref_e = orc.forward(img, x0, training=False)
+    ref_e = ref_e if isinstance(ref_e, tuple) else (ref_e,)
+    for i, (a, b) in enumerate(zip(oe, ref_e)):
+        rows.append(("%s eval out%d" % (tag, i), rel(a, b), 2e-3))
+    return rows
+
+
+def check_rollout(kind="tdo", steps=3):
+    """Batch-1 streaming inference with carried LSTM state vs oracle."""
+    model = build_model(kind)
+    orc = oracle_for(kind, model)
+    model.cuda().eval()
+    model.rollout = True
+    model.reset_initial_state(1)
+    orc.reset_state(1)
+    rows = []
+    for t in range(steps):
+        img, x0, _ = po.synthetic_batch(kind, 1, s=1, seed=10 + t)
+        with torch.no_grad():
+            o = model(img.cuda(), None, x0.cuda())
+        r = orc.forward(img, x0, training=False, rollout=True)
+        o = o if isinstance(o, tuple) else (o,)
+        r = r if isinstance(r, tuple) else (r,)
+        rows.append(("%s rollout step %d" % (kind, t), max(rel(a, b) for a, b in zip(o, r)), 2e-3))
+    return rows
+
+
+def main(argv):
+    kinds = argv or ["no", "tdo", "td", "n"]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    nfail = 0
+    from pe_b200 import native
+    for kind in kinds:
+        try:
+            rows = check_train_step(kind, verbose=("-v" in argv))
+            if kind in ("tdo", "td"):
+                rows += check_rollout(kind)
+        except Exception as e:
+            import traceback
+            traceback.print_exc()
+            rows = [("EXCEPTION %s: %r" % (kind, e), float("inf"), 0.0)]
+        for name, err, tol in rows:
+            ok = err <= tol
+            nfail += (not ok)
+            print("%-4s %-64s err %.3e tol %.1e" % ("ok" if ok else "FAIL", name, err, tol), flush=True)
+    print("device error flag:", native.lib().pe_device_error())
+    print("FAILED: %d" % nfail)
+    return nfail
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main([a for a in sys.argv[1:]]) else 0)
