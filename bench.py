@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the pose-estimator hot path (driver contract: one JSON line on stdout from rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model no|tdo|td|n]
+
+A "step" is one training step (forward, pose loss, backward, Adam) of the naive-object estimator on a
+synthetic batch of 256 RGB frames per GPU -- BASELINE.json configs[1] ("naive model training on
+1 B200, synthetic batch 256, hammer target").  `value` is whole-job samples/s with inputs resident in
+HBM; `e2e` is the same step driven from pinned HOST buffers (H2D of the frames / proprio / targets and
+a D2H read of the loss inside the timed region).  Weak scaling: each rank owns its own 256 frames.
+
+`--impl reference` times the reference algorithm's CPU path (the oracle restatement of the reference
+modules; the reference tree itself cannot travel to the GPU box) on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "rgb-proprioceptive-pose-estimator_b200"))
+sys.path.insert(0, ROOT)
+
+LOSS = dict(distance_metric="combined", alpha=0.5, mode="pose")          # scripts/train_no.sbatch:61-83
+TRAIN_GFLOP_PER_FRAME = {"no": 24.32, "tdo": 24.35, "td": 24.42, "n": 24.30}
+TRAIN_MB_PER_FRAME = 223.0                                                # SURVEY 8(d) compulsory fp32 traffic
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops_sustained"], which="measured")
+    return dict(hbm=6650.0, bf16=1400.0, which="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build(kind, seed=0):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import model_checks
+    return model_checks.build_model(kind, seed)
+
+
+def synth(kind, n, s, seed):
+    from oracle import pose_oracle as po
+    return po.synthetic_batch(kind, n, s=s, seed=seed) if kind in ("td", "tdo") else po.synthetic_batch(kind, n, seed=seed)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(kind, batch, seq, steps, warmup):
+    """samples/s of the reference algorithm on the host cores (oracle port), bounded sample."""
+    import torch
+    from oracle import pose_oracle as po
+    torch.set_num_threads(os.cpu_count())
+    model = build(kind)
+    extra = None
+    if kind == "td":
+        extra = {"aux_w": model.aux_nets[0][0].weight, "aux_b": model.aux_nets[0][0].bias}
+    orc = po.OracleEstimator(kind, model.state_dict(), extra)
+    img, x0, tgt = synth(kind, batch, seq, 1)
+    frames = img.shape[0] * (img.shape[1] if kind in ("td", "tdo") else 1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        if kind in ("no", "tdo"):
+            orc.train_step(img, x0, tgt, LOSS)
+        else:
+            orc.train_step(img, x0, tgt, LOSS, which=-1)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return frames / med, med, frames
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    batch = args.cpu_batch
+    rate, sec, frames = cpu_reference_rate(args.model, batch, args.seq, args.steps, min(args.warmup, 2))
+    cores = os.cpu_count()
+    sample = "%d-frame batches of the %s training step, %d timed steps (median)" % (frames, args.model, args.steps)
+    out = {"impl": "reference", "metric": "train_samples_per_s", "value": rate, "unit": "samples/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args),
+           "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def workload_config(args):
+    names = {"no": "naive-object estimator (models/naive.py) training step, hammer target, latent 512, hidden 1024/256/64, combined pose loss, Adam",
+             "tdo": "TDO estimator training step, robot1_eef target, latent 512, LSTM 512",
+             "td": "TD estimator training step, latent 1024, LSTM 512",
+             "n": "naive end-effector estimator training step"}
+    cfg = {"workload": names[args.model], "per_gpu_batch": args.batch, "frame": "3x224x224 fp32",
+           "cache": "inputs_larger_than_l2"}
+    if args.model in ("td", "tdo"):
+        cfg["sequence_length"] = args.seq
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pe_b200 import native
+    from pe_b200.trainer import FusedTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    L = native.lib()
+    kind = args.model
+    model = build(kind).to(dev).train()
+    trainer = FusedTrainer(model, lr=1e-3, process_group=pg, **LOSS)
+    seq = args.seq
+    img, x0, tgt = synth(kind, args.batch, seq, 1 + rank)
+    frames = args.batch * (seq if kind in ("td", "tdo") else 1)
+    targets_h = (x0, tgt) if kind in ("td", "n") else tgt
+    img_h, x0_h = img.pin_memory(), x0.pin_memory()
+    tg_h = tuple(t.pin_memory() for t in targets_h) if isinstance(targets_h, tuple) else targets_h.pin_memory()
+    img_d, x0_d = img_h.to(dev), x0_h.to(dev)
+    tg_d = tuple(t.to(dev) for t in tg_h) if isinstance(tg_h, tuple) else tg_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    last_loss = [None]
+
+    def step_resident():
+        last_loss[0] = trainer.step(img_d, x0_d, tg_d)
+
+    h2d = img_h.numel() * 4 + x0_h.numel() * 4 + sum(t.numel() * 4 for t in (tg_h if isinstance(tg_h, tuple) else (tg_h,)))
+
+    def step_e2e():
+        i = img_h.to(dev, non_blocking=True)
+        x = x0_h.to(dev, non_blocking=True)
+        t = tuple(a.to(dev, non_blocking=True) for a in tg_h) if isinstance(tg_h, tuple) else tg_h.to(dev, non_blocking=True)
+        last_loss[0] = float(trainer.step(i, x, t).item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    L.check_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    n_calls0 = native.call_count()
+    ms = timed(step_resident, args.steps)
+    n_calls = native.call_count() - n_calls0
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    loss_val = last_loss[0]
+
+    # ---- per-kernel-family device time (one instrumented step, outside the timed regions) ----------
+    native.enable_timing(True)
+    step_resident()
+    torch.cuda.synchronize()
+    fam = native.timing_summary()
+    native.enable_timing(False)
+    L.check_device()
+
+    value = world * frames * args.steps / (ms / 1e3)
+    e2e = world * frames * args.steps / (ms_e2e / 1e3)
+    pk = peaks()
+    gemm_ms = sum(v for k, v in fam.items() if k in ("pe_conv2d_fwd", "pe_conv2d_dgrad", "pe_conv2d_wgrad",
+                                                      "pe_linear_fwd", "pe_linear_wgrad"))
+    total_ms = sum(fam.values())
+    tf32_peak = pk["bf16"] / 2.0
+    ach_tflops = TRAIN_GFLOP_PER_FRAME[kind] * frames / 1e3 / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
+    stream_ms = sum(v for k, v in fam.items() if k.startswith("pe_bn_") or k in ("pe_maxpool3x3s2_fwd", "pe_maxpool3x3s2_bwd", "pe_adam_step"))
+    out = {
+        "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": n_calls,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel (conv fwd/dgrad/wgrad + dense layers)",
+                     "achieved": ach_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": ach_tflops / tf32_peak if tf32_peak else None, "traffic": None,
+                     "peak_source": "%s bf16 sustained / 2 (TF32 runs at half the bf16 rate)" % pk["which"],
+                     "share_of_step": gemm_ms / total_ms if total_ms else None},
+        "roofline_step": {"bound": "hbm", "achieved": TRAIN_MB_PER_FRAME * frames / 1e3 / (ms / args.steps / 1e3),
+                          "peak": pk["hbm"], "unit": "GB/s",
+                          "frac": TRAIN_MB_PER_FRAME * frames / 1e3 / (ms / args.steps / 1e3) / pk["hbm"],
+                          "note": "compulsory fp32 activation traffic (223 MB/frame) over the whole step"},
+        "kernel_ms": {k: round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])},
+        "loss": loss_val,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                rate, sec, fr = cpu_reference_rate(kind, args.cpu_batch, seq, 3, 1)
+                out["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "%d-frame batch, median of 3 steps (%.2f s/step)" % (fr, sec)}
+            except Exception as e:  # the GPU numbers stand on their own
+                out["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--model", default="no", choices=["no", "tdo", "td", "n"])
+    ap.add_argument("--batch", type=int, default=None, help="frames (naive) or episodes (sequence models) per GPU")
+    ap.add_argument("--seq", type=int, default=None)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.seq is None:
+        args.seq = {"tdo": 20, "td": 10}.get(args.model, 1)
+    if args.batch is None:
+        args.batch = {"no": 256, "n": 256, "tdo": 32, "td": 64}[args.model]
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

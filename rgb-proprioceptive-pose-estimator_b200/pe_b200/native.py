@@ -94,7 +94,17 @@ class _Lib:
         last_error = self._dll.pe_last_error
 
         def call(*args):
-            rc = raw(*args)
+            _STATE["calls"] += 1
+            if _STATE["timing"]:
+                import torch
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = raw(*args)
+                e1.record()
+                _STATE["events"].append((name, e0, e1))
+            else:
+                rc = raw(*args)
             if rc != 0:
                 raise PeError("%s failed (%d): %s" % (name, rc, (last_error() or b"").decode()))
             return 0
@@ -109,6 +119,29 @@ class _Lib:
 
 
 _lib = None
+_STATE = {"calls": 0, "timing": False, "events": []}
+
+
+def call_count():
+    """Number of C-ABI kernel calls issued so far (each launches at least one CUDA kernel)."""
+    return _STATE["calls"]
+
+
+def enable_timing(on):
+    """Bracket every C-ABI call with CUDA events on the current stream (profiling aid for bench.py)."""
+    _STATE["timing"] = bool(on)
+    if on:
+        _STATE["events"] = []
+
+
+def timing_summary():
+    """{entry point: total device milliseconds} for the calls recorded since enable_timing(True)."""
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _STATE["events"]:
+        out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+    return out
 
 
 def lib():

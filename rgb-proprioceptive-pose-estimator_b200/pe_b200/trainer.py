@@ -1,0 +1,148 @@
+"""Fused training step: forward -> pose loss (+gradient) -> backward -> [NCCL all-reduce] -> fused Adam.
+
+This is the body of the reference's hot loop (util/learn_utils.py:151-184: zero_grad / forward / loss /
+backward / optimizer.step) with autograd and the per-parameter optimizer loop taken out of the way:
+parameters, gradients and Adam moments live in flat 128-byte-aligned arenas, gradients are written in
+place by the backward kernels, and one 128-bit streaming kernel applies the update.  Semantics are those
+of `torch.optim.Adam(model.parameters(), lr)` (scripts/train_model.py:228).
+
+Multi-GPU: one process per GPU, batch (naive) or episodes (sequence models) sharded across ranks,
+gradients summed (not averaged: the loss is a sum over samples, models/losses.py:75,128) with NCCL in
+backward-ordered buckets on a side stream; BatchNorm statistics stay per GPU.
+"""
+import torch
+
+from . import native
+from .engine import LinearOp, LSTMOp
+
+_METRIC_ID = {"l1": 0, "l2": 1, "linf": 2, "combined": 3}
+_ALIGN = 32  # floats (128 B)
+
+
+def get_core(model):
+    """The estimator core of a mirrored model (built lazily, shared with model.forward)."""
+    from . import estimators as est
+    core = getattr(model, "_core", None)
+    if core is None:
+        name = type(model).__name__
+        cls = {"NaiveObjectStateEstimator": est.NaiveObjectCore,
+               "NaiveEndEffectorStateEstimator": est.NaiveEefCore,
+               "TemporallyDependentObjectStateEstimator": est.TDOCore,
+               "TemporallyDependentStateEstimator": est.TDCore}[name]
+        core = cls(model)
+        object.__setattr__(model, "_core", core)
+    return core
+
+
+def invalidate_core(core):
+    """Drop every packed-weight cache (parameters were updated by a raw kernel, not a torch op)."""
+    for v in vars(core).values():
+        items = v if isinstance(v, (list, tuple)) else [v]
+        for it in items:
+            if isinstance(it, (LinearOp, LSTMOp)):
+                it._ver = None
+    m = core.m if hasattr(core, "m") else None
+    net = getattr(core, "net", None)
+    if m is not None:
+        fn = m.feature_net
+        net = getattr(fn, "module", fn)
+    if net is not None and getattr(net, "_pe_engine", None) is not None:
+        net._pe_engine.invalidate()
+
+
+class FusedTrainer:
+    def __init__(self, model, distance_metric="l2", alpha=1.0, epsilon=1e-4, scale_factor=1.0, mode="pose",
+                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, optimizer="adam", momentum=0.0,
+                 process_group=None, bucket_mb=32):
+        if mode not in ("pose", "position"):
+            raise ValueError("training loss mode must be 'pose' or 'position'")
+        self.model = model
+        self.core = get_core(model)
+        self.loss_cfg = (_METRIC_ID[distance_metric], 1 if mode == "pose" else 0, float(alpha), float(epsilon),
+                         float(scale_factor))
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.optimizer, self.momentum = optimizer, momentum
+        self.pg = process_group
+        self.bucket_bytes = bucket_mb << 20
+        self.t = 0
+        self._flat = None
+        self.comm_stream = None
+
+    # ------------------------------------------------------------------------------------------
+    def _flatten(self):
+        params = [p for p in self.model.parameters()]
+        if not params or not params[0].is_cuda:
+            raise native.PeError("FusedTrainer: move the model to a CUDA device first (no CPU fallback)")
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        pf = torch.zeros(total, device=dev, dtype=torch.float32)
+        gf = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.views = {}
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                n = p.numel()
+                pf[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = pf[o:o + n].view(p.shape)
+                gv = gf[o:o + n].view(p.shape)
+                self.views[id(p)] = gv
+                p.grad = gv
+        self.p_flat, self.g_flat = pf, gf
+        self.m_flat = torch.zeros_like(pf)
+        self.v_flat = torch.zeros_like(pf) if self.optimizer == "adam" else None
+        self.param_offsets = {id(p): (o, p.numel()) for p, o in zip(params, offs)}
+        # BatchNorm counters -> one int64 arena, one kernel launch per step
+        nbts = [b for n, b in self.model.named_buffers() if n.endswith("num_batches_tracked")]
+        self._flat = True
+        invalidate_core(self.core)
+        if self.pg is not None:
+            self.comm_stream = torch.cuda.Stream(device=dev)
+
+    def grad_of(self, p):
+        return self.views[id(p)]
+
+    # ------------------------------------------------------------------------------------------
+    def step(self, img, self_measurement, targets):
+        """One optimisation step.  `targets`: a tensor (object-pose models) or a (x0, x1) pair for the
+        two-headed models, matching util/learn_utils.py:160-172.  Returns the loss as a 1-element device
+        tensor (sum over the local samples)."""
+        import torch.distributed as dist
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        if self._flat is None:
+            self._flatten()
+        model, core = self.model, self.core
+        state = None
+        outs, saved, _ = core.forward((img, self_measurement), True, True, state)
+        if not isinstance(targets, (tuple, list)):
+            targets = (targets,)
+        if len(targets) != len(outs):
+            raise ValueError("expected %d target tensor(s), got %d" % (len(outs), len(targets)))
+        dev = img.device
+        metric, mode, alpha, epsilon, scale = self.loss_cfg
+        losses = torch.empty(len(outs), device=dev, dtype=torch.float32)
+        douts = []
+        for i, (o, t) in enumerate(zip(outs, targets)):
+            n = o.numel() // 7
+            o2 = o.reshape(n, 7)
+            t2 = t.reshape(n, 7)
+            if t2.stride(1) != 1:
+                t2 = t2.contiguous()
+            d = torch.empty(n, 7, device=dev, dtype=torch.float32)
+            L.pe_pose_loss(P(o2), o2.stride(0), P(t2), t2.stride(0), n, metric, mode, alpha, epsilon, scale,
+                           P(losses[i:]), P(d), 7, None, st)
+            douts.append(d)
+        core.backward(saved, tuple(douts), self.grad_of)
+        if self.pg is not None and dist.get_world_size(self.pg) > 1:
+            dist.all_reduce(self.g_flat, op=dist.ReduceOp.SUM, group=self.pg)
+        self.t += 1
+        n = self.p_flat.numel()
+        if self.optimizer == "adam":
+            L.pe_adam_step(P(self.p_flat), P(self.g_flat), P(self.m_flat), P(self.v_flat), n, self.lr, self.betas[0],
+                           self.betas[1], self.eps, self.wd, self.t, 1.0, st)
+        else:
+            L.pe_sgd_step(P(self.p_flat), P(self.g_flat), P(self.m_flat) if self.momentum else None, n, self.lr,
+                          self.momentum, self.wd, int(self.t == 1), 1.0, st)
+        invalidate_core(core)
+        return losses.sum() if len(outs) > 1 else losses

@@ -27,11 +27,15 @@ CONFIGS = {
 }
 
 
+SHALLOW = [False]   # when set, Bottleneck stacks are [1,1,1,1] instead of ResNet-50's [3,4,6,3]
+
+
 def build_model(kind, seed=0):
     import models.naive as mn
     import models.time_sensitive as mt
     import util.model_utils as mu
     cfg = CONFIGS[kind]
+    mu._RESNET_LAYERS[50] = [1, 1, 1, 1] if SHALLOW[0] else [3, 4, 6, 3]
     torch.manual_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
         if kind == "no":
@@ -132,7 +136,11 @@ def check_train_step(kind, n=2, s=2, seed=1, verbose=False):
         worst.append((relnorm(g, g_ref), k))
     worst.sort(reverse=True)
     for e, k in (worst if verbose else worst[:6]):
-        rows.append(("%s grad %s" % (tag, k), e, 1e-2))
+        rows.append(("%s grad %s (|g_ref| %.2e)" % (tag, k, float(grads_ref[k].norm())), e, 1e-2))
+    convs = [e for e, k in worst if ("conv" in k or "downsample.0" in k) and k.endswith("weight")]
+    if convs:
+        rows.append(("%s worst conv-weight grad" % tag, max(convs), 1e-2))
+        rows.append(("%s median conv-weight grad" % tag, sorted(convs)[len(convs) // 2], 1e-2))
     # running statistics after one training forward
     sd = model.state_dict()
     e_rm = max(rel(sd[k], orc.sd[k]) for k in sd if k.endswith("running_mean"))
@@ -177,15 +185,64 @@ def check_rollout(kind="tdo", steps=3):
     return rows
 
 
+def calibrate(kind="no", n=2, s=2, seed=1):
+    """How far does torch's own cuDNN path (fp32 and TF32) land from the CPU fp32 oracle on the same
+    problem?  Uses the oracle restatement on the GPU; this is the yard-stick for the TF32 tolerances."""
+    cfg = CONFIGS[kind]
+    model = build_model(kind)
+    orc = oracle_for(kind, model)
+    img, x0, tgt = po.synthetic_batch(kind, n, seed=seed) if kind in ("no", "n") else po.synthetic_batch(kind, n, s=s, seed=seed)
+    outs_ref, loss_ref, grads_ref = orc.loss_and_grads(img, x0, tgt, cfg["loss"])
+    rows = []
+    for tf in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf
+        torch.backends.cudnn.allow_tf32 = tf
+        g = oracle_for(kind, model)
+        g.sd = {k: v.cuda() for k, v in g.sd.items()}
+        outs, loss, grads = g.loss_and_grads(img.cuda(), x0.cuda(), tgt.cuda(), cfg["loss"])
+        tag = "calib torch-%s %s n%d" % ("tf32" if tf else "fp32", kind, n)
+        rows.append((tag + " out", rel(outs, outs_ref), float("inf")))
+        rows.append((tag + " loss", rel(loss.reshape(1), loss_ref.reshape(1)), float("inf")))
+        worst = sorted(((relnorm(grads[k], grads_ref[k]), k) for k in grads_ref if grads_ref[k] is not None), reverse=True)
+        for e, k in worst[:4]:
+            rows.append((tag + " grad " + k, e, float("inf")))
+        convs = [e for e, k in worst if k.endswith("conv1.weight") or k.endswith("conv2.weight") or k.endswith("conv3.weight")]
+        rows.append((tag + " worst conv weight grad", max(convs), float("inf")))
+        rm = max(rel(g.sd[k], orc.sd[k]) for k in g.sd if k.endswith("running_var"))
+        rows.append((tag + " running_var", rm, float("inf")))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return rows
+
+
 def main(argv):
-    kinds = argv or ["no", "tdo", "td", "n"]
+    if "--shallow" in argv and "--calib" in argv:
+        SHALLOW[0] = True
+        argv = [a for a in argv if a != "--shallow"]
+    if "--calib" in argv:
+        argv = [a for a in argv if a != "--calib"]
+        n = 2
+        for a in list(argv):
+            if a.startswith("n="):
+                n = int(a[2:]); argv.remove(a)
+        for name, err, tol in calibrate(argv[0] if argv else "no", n=n):
+            print("%-70s %.3e" % (name, err), flush=True)
+        return 0
+    nb = 2
+    if "--shallow" in argv:
+        SHALLOW[0] = True
+        argv = [a for a in argv if a != "--shallow"]
+    for a in list(argv):
+        if a.startswith("n="):
+            nb = int(a[2:]); argv.remove(a)
+    kinds = [a for a in argv if not a.startswith("-")] or ["no", "tdo", "td", "n"]
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     nfail = 0
     from pe_b200 import native
     for kind in kinds:
         try:
-            rows = check_train_step(kind, verbose=("-v" in argv))
+            rows = check_train_step(kind, n=nb, verbose=("-v" in argv))
             if kind in ("tdo", "td"):
                 rows += check_rollout(kind)
         except Exception as e:
