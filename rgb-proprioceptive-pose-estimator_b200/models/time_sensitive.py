@@ -138,6 +138,7 @@ class TemporallyDependentObjectStateEstimator(nn.Module):
         self.aux_latent_dim = 0
         self.use_depth = use_depth
         feature_net, _ = import_resnet(num_resnet_layers, latent_dim, feature_extract, use_pretrained=use_pretrained)
+        self.feature_net = feature_net        # registered first, re-wrapped below (keeps the reference's key order)
         if feature_layer_nums is not None:
             self.early_features = []
             aux, depth, self.aux_latent_dim = _probe_feature_layers(self, feature_net, feature_layer_nums,

@@ -292,11 +292,17 @@ class TrunkEngine:
         return {"tape": tape, "B": B}
 
     # ------------------------------------------------------------------------------------------
-    def backward(self, ctx, d_feat, ld_dfeat, d_aux, ld_daux, grad_of):
+    def backward(self, ctx, d_feat, ld_dfeat, d_aux, ld_daux, grad_of, on_ready=None):
         """d_feat: gradient w.r.t. the latent features (row stride ld_dfeat); d_aux likewise for the aux
-        vector.  `grad_of(param)` returns the tensor that receives that parameter's gradient."""
+        vector.  `grad_of(param)` returns the tensor that receives that parameter's gradient;
+        `on_ready(params)` is told whenever a group of parameters has its final gradient (all-reduce
+        buckets can start while the rest of backward is still running)."""
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         tape = ctx["tape"]
+        done_after_conv = {}
+        if on_ready is not None:
+            for blk, ids in self.blocks:
+                done_after_conv[ids[1]] = [p for p in blk.parameters()]
         B = ctx["B"]
         slots = GradSlots()
         dev = self.scale.device
@@ -319,6 +325,8 @@ class TrunkEngine:
                 dx = torch.empty_like(x.t)
                 L.pe_avgpool_bwd(P(dpool), nin, P(dx), B, x.H * x.W, x.C, st)
                 slots.add(x, dx)
+                if on_ready is not None:
+                    on_ready([fc.weight, fc.bias])
             elif kind == "bn":
                 _, i, y, out, relu, residual = rec
                 _, bn = self.convs[i]
@@ -351,6 +359,8 @@ class TrunkEngine:
                 dx = torch.empty_like(x.t)
                 L.pe_conv2d_dgrad(P(dy), P(self.w_tkc[i]), P(dx), x.B, x.H, x.W, ci, co, r, s, stride, pad, st)
                 slots.add(x, dx)
+                if i in done_after_conv:
+                    on_ready(done_after_conv[i])
             elif kind == "maxpool":
                 _, a1, x, argmax = rec
                 d1, d2 = slots.pop(x)
@@ -379,6 +389,11 @@ class TrunkEngine:
                 tmp = torch.empty(co, 160, device=dev, dtype=torch.float32)
                 L.pe_linear_wgrad(P(col), 160, P(dy), co, P(tmp), 160, y0.P, co, 160, st)
                 L.pe_copy_cols(P(tmp), 160, P(grad_of(conv1.weight)), k, co, k, 0, st)
+                if on_ready is not None:
+                    ps = [conv1.weight, self.net.bn1.weight, self.net.bn1.bias]
+                    if self.aux_conv is not None and self.aux_trainable:
+                        ps += [self.aux_conv.weight, self.aux_conv.bias]
+                    on_ready(ps)
             else:
                 raise native.PeError("internal: unknown tape record %r" % (kind,))
 

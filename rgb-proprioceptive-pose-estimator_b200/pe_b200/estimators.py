@@ -56,10 +56,10 @@ class TrunkCore:
         ctx = eng.forward(img, training, need_grad, out, n)
         return (out,), (eng, ctx, B, n), None
 
-    def backward(self, saved, douts, grad_of):
+    def backward(self, saved, douts, grad_of, on_ready=None):
         eng, ctx, B, n = saved
         d = douts[0].contiguous()
-        eng.backward(ctx, d, n, None, 0, grad_of)
+        eng.backward(ctx, d, n, None, 0, grad_of, on_ready)
 
 
 class NaiveObjectCore:
@@ -107,7 +107,7 @@ class NaiveObjectCore:
             x, ldx = y, y.shape[1]
         return (x[:, :7],), (eng, tctx, hs, B), None
 
-    def backward(self, saved, douts, grad_of):
+    def backward(self, saved, douts, grad_of, on_ready=None):
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         eng, tctx, hs, B = saved
         dev = hs[0].device
@@ -127,7 +127,9 @@ class NaiveObjectCore:
                 dx = torch.empty(B, self.ld_cat, device=dev, dtype=torch.float32)
                 op.backward(x, self.ld_cat, B, dz, ldy, grad_of, dx, self.ld_cat, dx_cols=ncols)
             d = dx
-        eng.backward(tctx, d, self.ld_cat, d[:, self.latent:] if self.use_aux else None, self.ld_cat, grad_of)
+        if on_ready is not None:
+            on_ready([p for op in self.fcs for p in op.lin.parameters()])
+        eng.backward(tctx, d, self.ld_cat, d[:, self.latent:] if self.use_aux else None, self.ld_cat, grad_of, on_ready)
 
 
 class NaiveEefCore:
@@ -190,7 +192,7 @@ class NaiveEefCore:
             d = dx
         return d
 
-    def backward(self, saved, douts, grad_of):
+    def backward(self, saved, douts, grad_of, on_ready=None):
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         eng, tctx, hs_pre, hs_post, B = saved
         dev = hs_pre[0].device
@@ -204,7 +206,9 @@ class NaiveEefCore:
         # features feed both MLPs
         L.pe_axpby_cols(P(dcat_pre), self.ld_cat, P(dcat_post), self.ld_cat, P(dcat_pre), self.ld_cat, B,
                         self.latent, 1.0, 1.0, 0, st)
-        eng.backward(tctx, dcat_pre, self.ld_cat, None, 0, grad_of)
+        if on_ready is not None:
+            on_ready([p for op in self.pre + self.post for p in op.lin.parameters()])
+        eng.backward(tctx, dcat_pre, self.ld_cat, None, 0, grad_of, on_ready)
 
 
 class TDOCore:
@@ -256,7 +260,7 @@ class TDOCore:
         saved = (eng, tctx, rctx, cat, h_all, z, S, N)
         return (out[:, :7].reshape(S, N, 7),), saved, (h_last, c_last)
 
-    def backward(self, saved, douts, grad_of):
+    def backward(self, saved, douts, grad_of, on_ready=None):
         eng, tctx, rctx, cat, h_all, z, S, N = saved
         M = S * N
         dev = cat.device
@@ -270,7 +274,10 @@ class TDOCore:
         ncols = self.latent + (AUX_DIM if self.use_aux else 0)
         dcat = torch.empty(M, self.ld_cat, device=dev, dtype=torch.float32)
         self.rnn.backward(rctx, dh, grad_of, dcat, self.ld_cat, dx_cols=ncols)
-        eng.backward(tctx, dcat, self.ld_cat, dcat[:, self.latent:] if self.use_aux else None, self.ld_cat, grad_of)
+        if on_ready is not None:
+            on_ready(list(self.m.rnn.parameters()) + list(self.m.fc.parameters()))
+        eng.backward(tctx, dcat, self.ld_cat, dcat[:, self.latent:] if self.use_aux else None, self.ld_cat, grad_of,
+                     on_ready)
 
 
 class TDCore:
@@ -330,7 +337,7 @@ class TDCore:
         outs = (pre_out[:, :7].reshape(S, N, 7), post_out[:, :7].reshape(S, N, 7))
         return outs, saved, ((h1_last, c1_last), (h2_last, c2_last))
 
-    def backward(self, saved, douts, grad_of):
+    def backward(self, saved, douts, grad_of, on_ready=None):
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         eng, tctx, rctx1, rctx2, cat, h1, h2, S, N = saved
         M = S * N
@@ -350,5 +357,9 @@ class TDCore:
         self.pre_rnn.backward(rctx1, dh1, grad_of, dcat1, self.ld_cat, dx_cols=self.n_feat)
         L.pe_axpby_cols(P(dcat1), self.ld_cat, P(dcat2), self.ld_cat, P(dcat1), self.ld_cat, M, self.n_feat, 1.0,
                         1.0, 0, st)
+        if on_ready is not None:
+            m = self.m
+            on_ready(list(m.pre_measurement_rnn.parameters()) + list(m.pre_measurement_fc.parameters()) +
+                     list(m.post_measurement_rnn.parameters()) + list(m.post_measurement_fc.parameters()))
         eng.backward(tctx, dcat1, self.ld_cat, dcat1[:, self.latent:] if self.use_aux else None, self.ld_cat,
-                     grad_of)
+                     grad_of, on_ready)

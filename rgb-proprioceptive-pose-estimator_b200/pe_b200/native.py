@@ -158,4 +158,6 @@ def ptr(t):
 
 def stream_ptr():
     import torch
+    if not torch.cuda.is_available():
+        raise PeError("no CUDA device visible: the B200 pose-estimator path has no CPU fallback")
     return torch.cuda.current_stream().cuda_stream

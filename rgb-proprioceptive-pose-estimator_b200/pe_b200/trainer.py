@@ -97,11 +97,23 @@ class FusedTrainer:
         nbts = [b for n, b in self.model.named_buffers() if n.endswith("num_batches_tracked")]
         self._flat = True
         invalidate_core(self.core)
+        self.touched = set()
+        self.reducer = None
         if self.pg is not None:
-            self.comm_stream = torch.cuda.Stream(device=dev)
+            import torch.distributed as dist
+            from .ddp import BucketedAllReduce
+            if dist.get_world_size(self.pg) > 1:
+                self.comm_stream = torch.cuda.Stream(device=dev)
+                self.reducer = BucketedAllReduce(gf, self.bucket_bytes // 4, group=self.pg, stream=self.comm_stream)
 
     def grad_of(self, p):
+        self.touched.add(id(p))
         return self.views[id(p)]
+
+    def _on_ready(self, params):
+        for p in params:
+            o, n = self.param_offsets[id(p)]
+            self.reducer.ready(o, o + (n + _ALIGN - 1) // _ALIGN * _ALIGN)
 
     # ------------------------------------------------------------------------------------------
     def step(self, img, self_measurement, targets):
@@ -133,9 +145,18 @@ class FusedTrainer:
             L.pe_pose_loss(P(o2), o2.stride(0), P(t2), t2.stride(0), n, metric, mode, alpha, epsilon, scale,
                            P(losses[i:]), P(d), 7, None, st)
             douts.append(d)
-        core.backward(saved, tuple(douts), self.grad_of)
-        if self.pg is not None and dist.get_world_size(self.pg) > 1:
-            dist.all_reduce(self.g_flat, op=dist.ReduceOp.SUM, group=self.pg)
+        red = self.reducer
+        if red is not None:
+            red.reset()
+            if self.t > 0:
+                # parameters that never receive a gradient (unused depth nets) are final from the start
+                for pid, (o, n) in self.param_offsets.items():
+                    if pid not in self.touched:
+                        red.ready(o, o + (n + _ALIGN - 1) // _ALIGN * _ALIGN)
+            core.backward(saved, tuple(douts), self.grad_of, self._on_ready if self.t > 0 else None)
+            red.wait()
+        else:
+            core.backward(saved, tuple(douts), self.grad_of)
         self.t += 1
         n = self.p_flat.numel()
         if self.optimizer == "adam":

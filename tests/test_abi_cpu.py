@@ -1,0 +1,117 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, and the mirrored modules reproduce the reference's constructor / checkpoint surface."""
+import ctypes
+import io
+import json
+import os
+import re
+import contextlib
+
+import pytest
+import torch
+
+from pe_b200 import native
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    native.build()
+    protos = native.parse_header()
+    assert len(protos) >= 35
+    dll = ctypes.CDLL(native.LIB_PATH)
+    missing = [n for n in protos if not hasattr(dll, n)]
+    assert not missing, missing
+    text = open(native.HEADER).read()
+    declared = set(re.findall(r"\b(pe_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", text, flags=re.S)))
+    assert declared == set(protos), declared ^ set(protos)
+    assert native.lib().pe_version() >= 100
+
+
+def test_header_cites_reference_sites():
+    text = open(native.HEADER).read()
+    for cite in ("models/losses.py:47-128", "models/naive.py", "models/time_sensitive.py", "scripts/train_model.py:228"):
+        assert cite in text
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of routing around the kernels."""
+    import model_checks as mc
+    from models.losses import PoseDistanceLoss
+    mc.SHALLOW[0] = True
+    try:
+        m = mc.build_model("no")
+    finally:
+        mc.SHALLOW[0] = False
+    with pytest.raises(native.PeError):
+        m(torch.zeros(1, 3, 224, 224), None, torch.zeros(1, 7))
+    with pytest.raises(native.PeError):
+        PoseDistanceLoss()(torch.zeros(2, 7), torch.zeros(2, 7))
+
+
+def test_product_never_imports_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(__file__)), "rgb-proprioceptive-pose-estimator_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+@pytest.mark.parametrize("kind", ["no", "n", "td", "tdo"])
+def test_state_dict_layout_matches_reference_manifest(kind):
+    """Keys, order, shapes, dtypes, parameter order and the seed-0 init values equal the reference's
+    (tests/golden/state_dicts.json, generated from the reference constructors)."""
+    import model_checks as mc
+    man = json.load(open(os.path.join(GOLDEN, "state_dicts.json")))[kind]
+    m = mc.build_model(kind)
+    sd = m.state_dict()
+    assert [[k, list(v.shape), str(v.dtype)] for k, v in sd.items()] == man["keys"]
+    assert [n for n, _ in m.named_parameters()] == man["params"]
+    for k, v in sd.items():
+        s, s2 = man["checksum"][k]
+        assert abs(float(v.double().sum()) - s) <= 1e-9 * max(1.0, abs(s)), k
+        assert abs(float((v.double() ** 2).sum()) - s2) <= 1e-9 * max(1.0, abs(s2)), k
+
+
+def test_checkpoint_round_trip_and_deepcopy(tmp_path):
+    import copy
+    import model_checks as mc
+    m = mc.build_model("tdo")
+    path = tmp_path / "ck.pth"
+    torch.save(m.state_dict(), path)
+    m2 = mc.build_model("tdo", seed=123)
+    m2.load_state_dict(torch.load(path, map_location="cpu"))
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    best = copy.deepcopy(m.state_dict())          # util/learn_utils.py:68,217
+    m3 = copy.deepcopy(m)
+    assert list(best) == list(m3.state_dict())
+
+
+def test_constructor_and_loss_error_behaviour():
+    from models.losses import PoseDistanceLoss
+    with pytest.raises(ValueError):
+        PoseDistanceLoss(distance_metric="l3")
+    with pytest.raises(ValueError):
+        PoseDistanceLoss(mode="train")
+    import models.naive as mn
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.raises(AssertionError):
+            mn.import_resnet(51, 8, False, False)
+    m = PoseDistanceLoss(distance_metric="combined", alpha=0.5)
+    assert (m.distance_metric, m.alpha, m.epsilon, m.mode, m.scale_factor) == ("combined", 0.5, 1e-4, "pose", 1.0)
+
+
+def test_state_protocol():
+    import model_checks as mc
+    mc.SHALLOW[0] = True
+    try:
+        tdo, no = mc.build_model("tdo"), mc.build_model("no")
+    finally:
+        mc.SHALLOW[0] = False
+    assert tdo.requires_sequence and not no.requires_sequence
+    assert tdo.rollout is False and hasattr(no, "object_name") and no.use_depth is False
+    tdo.reset_initial_state(3)
+    assert tuple(tdo.rnn_h.shape) == (1, 3, 512) and tdo.rnn_h.requires_grad
+    assert hasattr(no.feature_net.module, "layer1") and hasattr(no.aux_nets[0].module, "register_forward_hook")

@@ -1,0 +1,113 @@
+"""CPU checks of the oracle: against the golden fixtures (always) and against the reference's own
+modules imported from /root/reference (build container only)."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import pose_oracle as po
+from oracle import ref_shim
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden(name):
+    return json.load(open(os.path.join(GOLDEN, name)))
+
+
+def test_loss_known_answers():
+    """Every (metric, mode) of PoseDistanceLoss: value and gradient equal the reference's."""
+    for c in _golden("loss_vectors.json"):
+        pred = torch.tensor(c["pred"], requires_grad=True)
+        truth = torch.tensor(c["truth"])
+        if c["mode"] == "val":
+            pos, ang = po.pose_val_metrics(pred.detach(), truth)
+            assert abs(pos - c["pos"]) <= 1e-5 * max(1, abs(c["pos"]))
+            assert abs(ang - c["angle"]) <= 1e-4 * max(1, abs(c["angle"]))
+            continue
+        loss = po.pose_loss(pred, truth, c["metric"], c["scale_factor"], c["alpha"], 1e-4, c["mode"])
+        loss.backward()
+        assert abs(float(loss) - c["loss"]) <= 1e-6 * max(1, abs(c["loss"])), c
+        assert torch.allclose(pred.grad, torch.tensor(c["grad"]), rtol=1e-5, atol=1e-6), c
+
+
+def test_survey_appendix_c_values():
+    """The survey's hand-recorded numbers for combined / pose."""
+    pred = torch.tensor([[0.1, 0.2, 0.3, 0.5, 0.5, 0.5, 0.5], [-0.4, 0.25, 0.0, 0.1, -0.2, 0.3, -0.4]])
+    truth = torch.tensor([[0., 0., 0., 0., 0., 0., 1.], [0.1, 0.25, -0.3, 0., 0.6, 0., 0.8]])
+    want = {("l1", "position"): 1.40000010, ("l2", "pose"): 1.87496209, ("combined", "pose"): 4.07496214}
+    for (metric, mode), v in want.items():
+        assert abs(float(po.pose_loss(pred, truth, metric, 1.0, 0.5, 1e-4, mode)) - v) < 1e-5
+    pos, ang = po.pose_val_metrics(pred, truth)
+    assert abs(pos - 0.9574803) < 1e-5 and abs(ang - 3.3702678813908973) < 1e-4
+    nan = po.pose_loss(torch.tensor([[0.1, 0, 0, 0., 0., 0., 0.]]), truth[:1], "l2", 1.0, 0.5, 1e-4, "pose")
+    assert torch.isnan(nan)
+
+
+@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n"])
+def test_forward_backward_golden(kind):
+    """Oracle forward / loss / gradients / BN running stats / eval outputs == reference fixtures."""
+    import model_checks as mc
+    fx = _golden("forward_%s.json" % kind)
+    model = mc.build_model(kind)
+    orc = mc.oracle_for(kind, model)
+    img, x0, tgt = po.synthetic_batch(kind, seed=1, **fx["shapes"])
+    lk = fx["loss_cfg"]
+    for k in orc.param_names:
+        orc.sd[k].requires_grad_(True)
+    out = orc.forward(img, x0, training=True)
+    outs = list(out) if isinstance(out, tuple) else [out]
+    loss = po.pose_loss(outs[0], tgt, **lk) if kind in ("no", "tdo") else \
+        po.pose_loss(outs[0], x0, **lk) + po.pose_loss(outs[1], tgt, **lk)
+    loss.backward()
+    for o, g in zip(outs, fx["outputs"]):
+        assert torch.allclose(o.detach(), torch.tensor(g), rtol=1e-4, atol=1e-6)
+    assert abs(float(loss) - fx["loss"]) <= 1e-5 * abs(fx["loss"])
+    for n, gn in fx["grad_norms"].items():
+        g = orc.sd[n].grad
+        if gn is None:
+            assert g is None, n
+        else:
+            assert abs(float(g.norm()) - gn) <= 2e-3 * max(gn, 1e-6), (n, float(g.norm()), gn)
+    for k, v in fx["running_var_sum"].items():
+        assert abs(float(orc.sd[k].double().sum()) - v) <= 1e-5 * abs(v), k
+    for k in orc.param_names:
+        orc.sd[k].requires_grad_(False)
+    oe = orc.forward(img, x0, training=False)
+    oe = list(oe) if isinstance(oe, tuple) else [oe]
+    for o, g in zip(oe, fx["eval_outputs"]):
+        assert torch.allclose(o, torch.tensor(g), rtol=1e-4, atol=1e-6)
+
+
+def test_adam_loss_curve_golden():
+    """First steps of the reference's Adam loss curve (torch.optim.Adam on the reference module)."""
+    import model_checks as mc
+    fx = _golden("curve_no.json")
+    model = mc.build_model("no")
+    orc = mc.oracle_for("no", model)
+    img, x0, tgt = po.synthetic_batch("no", seed=1, **fx["shapes"])
+    for i in range(4):
+        _, loss = orc.train_step(img, x0, tgt, fx["loss_cfg"], lr=fx["lr"])
+        assert abs(float(loss) - fx["losses"][i]) <= 2e-3 * abs(fx["losses"][i]), (i, float(loss), fx["losses"][i])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("kind", ["no", "tdo"])
+def test_oracle_vs_live_reference(kind):
+    """Direct comparison with the unmodified reference modules (build container only)."""
+    ref = ref_shim.load()
+    m = ref_shim.build_reference_model(ref, kind)
+    orc = po.OracleEstimator(kind, m.state_dict())
+    shape = dict(n=2) if kind == "no" else dict(n=2, s=2)
+    img, x0, tgt = po.synthetic_batch(kind, seed=3, **shape)
+    m.train()
+    if kind == "tdo":
+        m.reset_initial_state(2)
+    with ref_shim.quiet():
+        want = m(img, None, x0)
+    got = orc.forward(img, x0, training=True)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    sd = m.state_dict()
+    for k in sd:
+        assert torch.allclose(orc.sd[k].float(), sd[k].float(), rtol=1e-5, atol=1e-6), k
