@@ -89,13 +89,17 @@ int pe_bn_finalize(double* stats, const float* gamma, const float* beta, float* 
 int pe_bn_apply(const float* y, const float* scale, const float* shift, const float* residual, float* out,
                 long long P, int C, int relu, int round_tf32, void* stream);
 /* backward pass 1: g = (dout + dout2)*(out>0 if relu); sums = double[2*C] += (sum g, sum g*xhat).
+ * `out` may be NULL for a BN without residual input: the ReLU mask is then recomputed from
+ * y*mask_scale + mask_shift (the forward's folded scale / shift), saving one full read of the activations.
  * dout2 (optional) is the second gradient branch of a residual join, summed on the fly.              */
 int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
-                     const float* invstd, double* sums, long long P, int C, int relu, void* stream);
+                     const float* invstd, const float* mask_scale, const float* mask_shift, double* sums,
+                     long long P, int C, int relu, void* stream);
 /* backward pass 2: dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P); dres = g (optional);
  * dgamma = sum_gx, dbeta = sum_g (written or accumulated).  The caller zeroes `sums` before pass 1.   */
 int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
-                    const float* invstd, const float* gamma, double* sums, float* dy, float* dres,
+                    const float* invstd, const float* gamma, const float* mask_scale, const float* mask_shift,
+                    double* sums, float* dy, float* dres,
                     int dres_accumulate, float* dgamma, float* dbeta, int param_accumulate, long long P, int C,
                     int relu, int round_tf32, void* stream);
 

@@ -119,7 +119,7 @@ def forward_fixture(ref, kind):
     dump("forward_%s.json" % kind, fx)
 
 
-def curve_fixture(ref, kind, steps):
+def curve_fixture(ref, kind, steps, lr=1e-3, name=None):
     lk = LOSS_CFG[kind]
     shape = dict(n=4) if kind in ("no", "n") else dict(n=2, s=2)
     img, x0, tgt = po.synthetic_batch(kind, seed=1, **shape)
@@ -127,7 +127,7 @@ def curve_fixture(ref, kind, steps):
         m = ref_shim.build_reference_model(ref, kind)
     m.train()
     crit = ref.losses.PoseDistanceLoss(**lk)
-    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    opt = torch.optim.Adam(m.parameters(), lr=lr)
     losses = []
     for i in range(steps):
         opt.zero_grad()
@@ -140,7 +140,7 @@ def curve_fixture(ref, kind, steps):
         losses.append(float(loss))
         if i % 10 == 0:
             print(kind, i, losses[-1], flush=True)
-    dump("curve_%s.json" % kind, dict(kind=kind, shapes=shape, loss_cfg=lk, lr=1e-3, losses=losses))
+    dump(name or "curve_%s.json" % kind, dict(kind=kind, shapes=shape, loss_cfg=lk, lr=lr, losses=losses))
 
 
 def main():
@@ -157,6 +157,11 @@ def main():
     if "curve" in what:
         curve_fixture(ref, "no", 100)
         curve_fixture(ref, "tdo", 30)
+    if "curve_small_lr" in what:
+        # lr = 1e-5: the smooth regime, where a 100-step curve is a meaningful pointwise target (at the
+        # scripts' default 1e-3 the tiny synthetic batch puts training in a chaotic regime after ~4 steps)
+        curve_fixture(ref, "no", 100, lr=1e-5, name="curve_no_lr1e-5.json")
+        curve_fixture(ref, "tdo", 100, lr=1e-5, name="curve_tdo_lr1e-5.json")
 
 
 if __name__ == "__main__":

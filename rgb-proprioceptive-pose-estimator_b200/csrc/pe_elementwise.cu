@@ -38,7 +38,8 @@ template <int KIND>  // 0: (y, y*y)   1: (g, g*xhat) with g = dout * (out > 0 if
 __global__ void __launch_bounds__(EW_THREADS)
 channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ a2, const float* __restrict__ b,
                       const float* __restrict__ c, const float* __restrict__ mean,
-                      const float* __restrict__ invstd, double* __restrict__ sums, long long P, int C, int relu) {
+                      const float* __restrict__ invstd, const float* __restrict__ msc,
+                      const float* __restrict__ msh, double* __restrict__ sums, long long P, int C, int relu) {
     __shared__ float sm0[EW_THREADS * 4];
     __shared__ float sm1[EW_THREADS * 4];
     const int G = C >> 2;
@@ -52,10 +53,14 @@ channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ a2,
     if (row1 > P) row1 = P;
 
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-    float4 mu = s0, is = s0;
+    float4 mu = s0, is = s0, ksc = s0, ksh = s0;
     if (KIND == 1) {
         mu = ld4(mean + 4 * g);
         is = ld4(invstd + 4 * g);
+        if (relu && !b) {   // ReLU mask recomputed from y (no residual): out > 0 <=> y*scale + shift > 0
+            ksc = ld4(msc + 4 * g);
+            ksh = ld4(msh + 4 * g);
+        }
     }
     for (long long row = row0 + r; row < row1; row += TR) {
         const long long off = row * C + 4 * g;
@@ -69,14 +74,20 @@ channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ a2,
                 const float4 e = ld4_stream(a2 + off);
                 d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
             }
+            const float4 y = ld4_stream(c + off);
             if (relu) {
-                const float4 o = ld4_stream(b + off);
+                float4 o;
+                if (b) {
+                    o = ld4_stream(b + off);
+                } else {
+                    o.x = fmaf(y.x, ksc.x, ksh.x); o.y = fmaf(y.y, ksc.y, ksh.y);
+                    o.z = fmaf(y.z, ksc.z, ksh.z); o.w = fmaf(y.w, ksc.w, ksh.w);
+                }
                 d.x = o.x > 0.f ? d.x : 0.f;
                 d.y = o.y > 0.f ? d.y : 0.f;
                 d.z = o.z > 0.f ? d.z : 0.f;
                 d.w = o.w > 0.f ? d.w : 0.f;
             }
-            const float4 y = ld4_stream(c + off);
             s0.x += d.x; s0.y += d.y; s0.z += d.z; s0.w += d.w;
             s1.x += d.x * (y.x - mu.x) * is.x;
             s1.y += d.y * (y.y - mu.y) * is.y;
@@ -176,6 +187,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ dout2,
                     const float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ msc, const float* __restrict__ msh,
                     const double* __restrict__ sums, float* __restrict__ dy, float* __restrict__ dres,
                     int dres_acc, float* __restrict__ dgamma, float* __restrict__ dbeta, int param_acc,
                     long long P, int C, int relu, int round_out) {
@@ -208,8 +220,16 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ do
             const float4 e = ld4_stream(dout2 + 4 * i);
             d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
         }
+        const float4 yv = ld4_stream(y + 4 * i);
         if (relu) {
-            const float4 o = ld4_stream(out + 4 * i);
+            float4 o;
+            if (out) {
+                o = ld4_stream(out + 4 * i);
+            } else {
+                const float4 ksc = ld4(msc + 4 * g), ksh = ld4(msh + 4 * g);
+                o.x = fmaf(yv.x, ksc.x, ksh.x); o.y = fmaf(yv.y, ksc.y, ksh.y);
+                o.z = fmaf(yv.z, ksc.z, ksh.z); o.w = fmaf(yv.w, ksc.w, ksh.w);
+            }
             d.x = o.x > 0.f ? d.x : 0.f;
             d.y = o.y > 0.f ? d.y : 0.f;
             d.z = o.z > 0.f ? d.z : 0.f;
@@ -224,7 +244,6 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ do
                 st4(dres + 4 * i, d);
             }
         }
-        const float4 yv = ld4_stream(y + 4 * i);
         const float4 a = ld4(ca + 4 * g), b = ld4(cb + 4 * g), c = ld4(cc + 4 * g);
         float4 r;
         r.x = fmaf(a.x, d.x, fmaf(b.x, yv.x, c.x));
@@ -274,25 +293,32 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ tck, float* __rest
 __global__ void im2col_stem_kernel(const float* __restrict__ img, float* __restrict__ col, int B, int C, int H,
                                    int W, int R, int S, int stride, int pad, int Ho, int Wo, int ldc,
                                    int round_out) {
-    const long long n = (long long)B * Ho * Wo * ldc;
-    const long long gs = (long long)gridDim.x * blockDim.x;
+    // threads of a block share one (c, r, s) decode per k; rows are walked with 32-bit arithmetic
     const int K = C * R * S;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
-        const int k = (int)(i % ldc);
-        const long long row = i / ldc;
-        float v = 0.f;
-        if (k < K) {
-            const int s = k % S;
-            const int r = (k / S) % R;
-            const int c = k / (S * R);
-            const int wo = (int)(row % Wo);
-            const int ho = (int)((row / Wo) % Ho);
-            const int b = (int)(row / ((long long)Wo * Ho));
-            const int h = ho * stride + r - pad, w = wo * stride + s - pad;
-            if (h >= 0 && h < H && w >= 0 && w < W) v = img[(((long long)b * C + c) * H + h) * W + w];
-            if (round_out) v = round_tf32(v);
+    const int nrows = B * Ho * Wo;
+    const int rows_per_block = blockDim.x / 32;          // one warp per row, lanes over k
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int row = blockIdx.x * rows_per_block + wrp; row < nrows; row += gridDim.x * rows_per_block) {
+        const int wo = row % Wo;
+        const int t = row / Wo;
+        const int ho = t % Ho;
+        const int b = t / Ho;
+        const float* src = img + (size_t)b * C * H * W;
+        float* dst = col + (size_t)row * ldc;
+        const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+        for (int k = lane; k < ldc; k += 32) {
+            float v = 0.f;
+            if (k < K) {
+                const int s = k % S;
+                const int q = k / S;
+                const int r = q % R;
+                const int c = q / R;
+                const int h = h0 + r, w = w0 + s;
+                if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(src + ((size_t)c * H + h) * W + w);
+                if (round_out) v = round_tf32(v);
+            }
+            dst[k] = v;
         }
-        col[i] = v;
     }
 }
 
@@ -612,7 +638,7 @@ int pe_bn_stats(const float* y, long long P, int C, double* stats, void* stream)
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_stats: unsupported channel count %d", C);
     channel_reduce_kernel<0><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        y, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
+        y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -638,23 +664,28 @@ int pe_bn_apply(const float* y, const float* scale, const float* shift, const fl
 }
 
 int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
-                     const float* invstd, double* sums, long long P, int C, int relu, void* stream) {
+                     const float* invstd, const float* mask_scale, const float* mask_shift, double* sums,
+                     long long P, int C, int relu, void* stream) {
+    PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_reduce: ReLU mask needs `out` or scale/shift");
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_bwd_reduce: unsupported channel count %d", C);
     channel_reduce_kernel<1><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dout, dout2, out, y, mean, invstd, sums, P, C, relu);
+        dout, dout2, out, y, mean, invstd, mask_scale, mask_shift, sums, P, C, relu);
     PE_LAUNCH_CHECK();
     return 0;
 }
 
 int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
-                    const float* invstd, const float* gamma, double* sums, float* dy, float* dres,
+                    const float* invstd, const float* gamma, const float* mask_scale, const float* mask_shift,
+                    double* sums, float* dy, float* dres,
                     int dres_accumulate, float* dgamma, float* dbeta, int param_accumulate, long long P, int C,
                     int relu, int round_tf32, void* stream) {
     PE_REQUIRE(C % 4 == 0 && C <= 4096, "bn_bwd_apply: unsupported channel count %d", C);
+    PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_apply: ReLU mask needs `out` or scale/shift");
     const long long n4 = P * (C / 4);
     bn_bwd_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
-        dout, dout2, out, y, mean, invstd, gamma, sums, dy, dres, dres_accumulate, dgamma, dbeta, param_accumulate,
+        dout, dout2, out, y, mean, invstd, gamma, mask_scale, mask_shift, sums, dy, dres, dres_accumulate, dgamma,
+        dbeta, param_accumulate,
         P, C, relu, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
@@ -682,8 +713,8 @@ int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W
                    int ldc, int round_tf32, void* stream) {
     PE_REQUIRE(ldc >= C * R * S && ldc % 4 == 0, "im2col: ldc %d too small / unaligned", ldc);
     const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
-    const long long n = (long long)B * Ho * Wo * ldc;
-    im2col_stem_kernel<<<grid_for(n, EW_THREADS * 4, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    const long long n = (long long)B * Ho * Wo;
+    im2col_stem_kernel<<<grid_for(n, (EW_THREADS / 32) * 4, 32), EW_THREADS, 0, (cudaStream_t)stream>>>(
         img_nchw, col, B, C, H, W, R, S, stride, pad, Ho, Wo, ldc, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;

@@ -330,15 +330,17 @@ class TrunkEngine:
             elif kind == "bn":
                 _, i, y, out, relu, residual = rec
                 _, bn = self.convs[i]
-                _, _, mean, invstd, _, sums = self._bn_views(i)
+                sc, sh, mean, invstd, _, sums = self._bn_views(i)
                 d1, d2 = slots.pop(out)
-                L.pe_bn_bwd_reduce(P(d1), P(d2), P(out.t), P(y.t), P(mean), P(invstd), P(sums), y.P, y.C, int(relu),
-                                   st)
+                # without a residual input the ReLU mask is recomputed from y (one activation read less)
+                mask_src = out.t if (relu and residual is not None) else None
+                L.pe_bn_bwd_reduce(P(d1), P(d2), P(mask_src), P(y.t), P(mean), P(invstd), P(sc), P(sh), P(sums), y.P,
+                                   y.C, int(relu), st)
                 dy = torch.empty_like(y.t)
                 dres = torch.empty_like(y.t) if residual is not None else None
-                L.pe_bn_bwd_apply(P(d1), P(d2), P(out.t), P(y.t), P(mean), P(invstd), P(bn.weight), P(sums), P(dy),
-                                  P(dres), 0, P(grad_of(bn.weight)), P(grad_of(bn.bias)), 0, y.P, y.C, int(relu), rt,
-                                  st)
+                L.pe_bn_bwd_apply(P(d1), P(d2), P(mask_src), P(y.t), P(mean), P(invstd), P(bn.weight), P(sc), P(sh),
+                                  P(sums), P(dy), P(dres), 0, P(grad_of(bn.weight)), P(grad_of(bn.bias)), 0, y.P, y.C,
+                                  int(relu), rt, st)
                 slots.add(y, dy)
                 if residual is not None:
                     slots.add(residual, dres)

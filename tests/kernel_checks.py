@@ -230,12 +230,16 @@ def check_bn(Pn, C, relu=True, residual=True):
     sums = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
     dout_a = dout * 0.25
     dout_b = dout - dout_a
-    L.pe_bn_bwd_reduce(P(dout_a), P(dout_b), P(o), P(y), P(mean), P(invstd), P(sums), Pn, C, int(relu), S())
+    use_mask = relu and not residual
+    o_arg = None if use_mask else o
+    L.pe_bn_bwd_reduce(P(dout_a), P(dout_b), P(o_arg), P(y), P(mean), P(invstd), P(scale), P(shift), P(sums), Pn, C,
+                       int(relu), S())
     dy = torch.empty(Pn, C, device=DEV)
     dres = torch.empty(Pn, C, device=DEV) if residual else None
     dgamma = torch.empty(C, device=DEV)
     dbeta = torch.empty(C, device=DEV)
-    L.pe_bn_bwd_apply(P(dout_a), P(dout_b), P(o), P(y), P(mean), P(invstd), P(gamma), P(sums), P(dy), P(dres), 0,
+    L.pe_bn_bwd_apply(P(dout_a), P(dout_b), P(o_arg), P(y), P(mean), P(invstd), P(gamma), P(scale), P(shift), P(sums),
+                      P(dy), P(dres), 0,
                       P(dgamma), P(dbeta), 0, Pn, C, int(relu), 0, S())
     out.append(("bn_bwd dy " + tag, relerr(dy, grads[0]), 1e-4))
     out.append(("bn_bwd dgamma " + tag, relerr(dgamma, grads[1]), 1e-4))
@@ -457,6 +461,7 @@ ALL = [
     lambda: check_bn(6272, 64),
     lambda: check_bn(1000, 256, relu=False, residual=False),
     lambda: check_bn(98, 2048),
+    lambda: check_bn(3000, 128, relu=True, residual=False),
     lambda: check_pools(2),
     lambda: check_lstm_cell(5, 512),
     lambda: check_loss(37),
