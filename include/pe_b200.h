@@ -27,6 +27,12 @@ void pe_device_error_clear(void);
 int pe_version(void);
 /* debug: override UMMA shared-memory descriptor strides (bytes; <0 restores the default) */
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo);
+/* debug: tap-GEMM pipeline ablations (1 no TMA store, 2 no staging write, 4 no A loads, 8 no B loads); 0 = normal */
+void pe_debug_flags(int flags);
+/* debug: force the smem split of the tap-GEMM (ring stages x 32 KB + nout x 16 KB <= 223 KB); 0 = default */
+void pe_debug_pipeline(int stages, int nout);
+/* debug: cap the tile width (128 or 256 columns) */
+void pe_debug_max_bn(int bn);
 
 /* ---- convolutions: torchvision resnet.py:143-163,266-282 Conv2d calls reached from
  *      models/naive.py:316 and models/time_sensitive.py:185,472 (bias-free, NHWC here) ------------

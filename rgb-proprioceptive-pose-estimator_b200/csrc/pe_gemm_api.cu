@@ -141,6 +141,8 @@ static void choose_box(int W, int H, int N, int target, int* obw, int* obh, int*
 }
 
 static int g_dbg_desc[4] = {-1, -1, -1, -1};
+static int g_dbg_flags = 0;
+static int g_dbg_stages = 0, g_dbg_nout = 0;
 
 static void init_params(TapParams& p) {
     memset(&p, 0, sizeof(p));
@@ -149,10 +151,30 @@ static void init_params(TapParams& p) {
     p.dbg_a_sbo = g_dbg_desc[1];
     p.dbg_b_lbo = g_dbg_desc[2];
     p.dbg_b_sbo = g_dbg_desc[3];
+    p.dbg_flags = g_dbg_flags;
+
     p.error_flag = g_error_flag;
 }
 
-static int pick_bn(int n_total) { return n_total >= 128 ? 128 : ((n_total + 15) / 16) * 16; }
+static int g_dbg_max_bn = 256;
+static int pick_bn(int n_total) {
+    if (n_total >= 256 && g_dbg_max_bn >= 256) return 256;
+    return n_total >= 128 ? 128 : ((n_total + 15) / 16) * 16;
+}
+
+// Split the 216 KB of dynamic shared memory between the operand ring and the store staging buffers.
+// Long reductions want ring depth, short ones (1x1 convs) are bound by the epilogue's store pipeline.
+static void pick_pipeline(TapParams& p, int ksteps) {
+    p.stage_bytes = TG_A_BYTES + (p.bn > 128 ? 32768 : 16384);
+    const int budget = TG_SMEM_BYTES;
+    int nout = (p.store_mode == TG_STORE_TMA) ? (ksteps >= 24 ? (p.bn > 128 ? 1 : 2) : 4) : 0;
+    if (g_dbg_nout > 0 && p.store_mode == TG_STORE_TMA) nout = g_dbg_nout;
+    int stages = (budget - nout * TG_A_BYTES) / p.stage_bytes;
+    if (stages > TG_STAGES) stages = TG_STAGES;
+    if (g_dbg_stages > 0 && g_dbg_stages < stages) stages = g_dbg_stages;
+    p.stages = stages;
+    p.nout = nout > 0 ? nout : 1;
+}
 
 struct Epilogue {
     const float* bias = nullptr;
@@ -231,6 +253,7 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
     p.relu = ep.relu;
     p.round_out = ep.round_out;
     p.stats = ep.stats;
+    pick_pipeline(p, p.n_taps * p.chunks);
     dim3 grid((Cout + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
     return launch_tapgemm(maps, p, grid, stream);
 }
@@ -295,6 +318,7 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             if (make_nhwc_map(&maps.d, dx, B, H, W, Cin, ph, pw, stride, box)) return 1;
             p.n_total = Cin;
             p.store_mode = TG_STORE_TMA;
+            pick_pipeline(p, p.n_taps * p.chunks);
             dim3 grid((Cin + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
             if (launch_tapgemm(maps, p, grid, stream)) return 2;
         }
@@ -314,7 +338,7 @@ static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B
     TapParams p;
     init_params(p);
     p.mode = 1;
-    p.bn = Cin >= 128 ? 128 : ((Cin + 31) / 32) * 32;
+    p.bn = (Cin >= 256 && g_dbg_max_bn >= 256) ? 256 : (Cin >= 128 ? 128 : ((Cin + 31) / 32) * 32);
     p.m_rows = TG_BM;
     choose_box(Wo, Ho, B, TG_BK, &p.box_w, &p.box_h, &p.box_n, true);
     p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
@@ -350,6 +374,7 @@ static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B
     p.store_mode = ks > 1 ? TG_STORE_ATOMIC : TG_STORE_DIRECT;
     if (ks > 1)
         PE_CHECK_CUDA(cudaMemsetAsync(dw_tck, 0, sizeof(float) * (size_t)R * S * Cout * Cin, stream));
+    pick_pipeline(p, (p.pt_total + ks - 1) / ks);
     dim3 grid(nt, mt, p.n_taps * ks);
     return launch_tapgemm(maps, p, grid, stream);
 }
@@ -415,6 +440,7 @@ static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, flo
                    "linear: residual/accumulate needs N and ldy multiples of 4");
         p.store_mode = TG_STORE_DIRECT;
     }
+    pick_pipeline(p, p.chunks);
     dim3 grid((N + p.bn - 1) / p.bn, p.tiles_w, 1);
     return launch_tapgemm(maps, p, grid, stream);
 }
@@ -427,7 +453,7 @@ static int linear_wgrad_impl(const float* x, int ldx, const float* dy, int lddy,
     TapParams p;
     init_params(p);
     p.mode = 1;
-    p.bn = K >= 128 ? 128 : ((K + 31) / 32) * 32;
+    p.bn = (K >= 256 && g_dbg_max_bn >= 256) ? 256 : (K >= 128 ? 128 : ((K + 31) / 32) * 32);
     p.m_rows = TG_BM;
     p.box_w = TG_BK;
     p.box_h = p.box_n = 1;
@@ -462,6 +488,7 @@ static int linear_wgrad_impl(const float* x, int ldx, const float* dy, int lddy,
     p.ksplit = ks;
     p.store_mode = ks > 1 ? TG_STORE_ATOMIC : TG_STORE_DIRECT;
     if (ks > 1) PE_CHECK_CUDA(cudaMemset2DAsync(dw, sizeof(float) * lddw, 0, sizeof(float) * K, N, stream));
+    pick_pipeline(p, (p.pt_total + ks - 1) / ks);
     dim3 grid(nt, mt, ks);
     return launch_tapgemm(maps, p, grid, stream);
 }
@@ -478,6 +505,15 @@ extern "C" {
 const char* pe_last_error(void) { return pe::get_error(); }
 
 int pe_version(void) { return 100; }
+
+void pe_debug_flags(int flags) { g_dbg_flags = flags; }
+
+void pe_debug_pipeline(int stages, int nout) {
+    g_dbg_stages = stages;
+    g_dbg_nout = nout;
+}
+
+void pe_debug_max_bn(int bn) { g_dbg_max_bn = bn > 0 ? bn : 256; }
 
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
     g_dbg_desc[0] = a_lbo;

@@ -8,7 +8,8 @@
 //   mode 1 ("wgrad"): D[M, N] = sum_pixels A[pixel, M]^T * B[pixel+tap, N]
 //                     A (dY) and B (X) MN-major in shared memory: the reduction runs over pixels.
 //
-// One CTA = one 128 x bn output tile; warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// Persistent CTAs (one per SM) walk a list of 128 x bn output tiles; warp 0 = TMA producer,
+// warp 1 = TMEM owner + MMA issuer (two accumulators, so the next tile overlaps the epilogue),
 // warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store, with optional
 // bias / scale-shift / residual / ReLU / TF32 rounding / per-channel batch statistics).
 #pragma once
@@ -18,12 +19,11 @@ namespace pe {
 
 constexpr int TG_BM = 128;                     // tile rows  (TMEM lanes)
 constexpr int TG_BK = 32;                      // tf32 elements per k-step (128 B swizzle span)
-constexpr int TG_MAX_BN = 128;                 // tile columns (TMEM columns)
-constexpr int TG_STAGES = 3;
+constexpr int TG_MAX_BN = 256;                 // tile columns (TMEM columns per accumulator)
+constexpr int TG_STAGES = 6;                    // maximum ring depth (runtime: TapParams::stages)
 constexpr int TG_A_BYTES = TG_BM * 128;        // 16 KB
-constexpr int TG_B_BYTES = TG_MAX_BN * 128;    // 16 KB
-constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
-constexpr int TG_SMEM_BYTES = TG_STAGES * TG_STAGE_BYTES + 1024;  // + alignment slack
+constexpr int TG_B_BYTES = TG_MAX_BN * 128;    // 32 KB (16 KB when bn <= 128: TapParams::stage_bytes)
+constexpr int TG_SMEM_BYTES = 216 * 1024;       // ring (stages x 32|48 KB) + store staging (nout x 16 KB)
 constexpr int TG_THREADS = 192;
 constexpr int TG_MAX_TAPS = 16;
 
@@ -45,6 +45,7 @@ struct TapParams {
     int n_taps, chunks;       // conv: k-steps = n_taps * chunks
     int ksplit;               // K splits (conv: gridDim.z; wgrad: per tap)
     int pt_total;             // wgrad: number of 32-pixel tiles
+    int work_n, work_m, work_total;  // persistent work list: (n tile, m tile, z), n fastest
     int m_total, n_total;     // logical output extents (wgrad rows; columns in both modes)
     signed char tap_dw[TG_MAX_TAPS], tap_dh[TG_MAX_TAPS], tap_map[TG_MAX_TAPS], tap_b[TG_MAX_TAPS];
     int store_mode;
@@ -62,8 +63,11 @@ struct TapParams {
     int* error_flag;
     // debug overrides for the smem descriptors (bytes, <0 = default)
     int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;
+    int stages, nout;         // smem split: ring depth and number of 16 KB store-staging buffers
+    int stage_bytes;          // 16 KB (A) + 16 or 32 KB (B)
+    int dbg_flags;            // 1: skip TMA store issue, 2: skip staging write + store, 4: skip A loads, 8: skip B loads
 };
 
-int launch_tapgemm(const TapMaps& maps, const TapParams& p, dim3 grid, cudaStream_t stream);
+int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream);
 
 }  // namespace pe

@@ -1,0 +1,175 @@
+"""GPU parity tests of the estimators (through the reference-facing nn.Module API and the C ABI) against
+the CPU oracle and the golden fixtures generated from the reference's own modules.
+
+Tolerances (TF32 tensor-core operands, fp32 accumulate; see DESIGN.md "Numerics"):
+  * full ResNet-50 depth, random init: outputs / loss within 1e-2 relative of the fp32 oracle.  The
+    yard-stick is torch's own cuDNN TF32 path, which lands 3e-3..5e-3 from the same oracle.
+  * 4-block trunk (well conditioned): outputs / loss within 2e-3.
+  * gradients: a random-init BN/ReLU stack amplifies rounding noise ~2000x (cuDNN *fp32* already differs
+    from CPU fp32 by 2e-3..3e-2 in relative gradient norm, cuDNN TF32 by 0.1..0.8).  We therefore assert
+    that our per-parameter gradient error is no worse than 1.5x torch-TF32's error (+2e-2) on the same
+    problem, and pin the kernels individually to 1e-4 in test_kernels_gpu.py.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+import model_checks as mc
+from oracle import pose_oracle as po
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    mc.SHALLOW[0] = False
+    yield
+    mc.SHALLOW[0] = False
+
+
+def _split(rows):
+    fwd = [(n, e, t) for n, e, t in rows if " grad " not in n and "conv-weight grad" not in n and "[oracle" not in n]
+    grads = [(n, e) for n, e, t in rows if " grad " in n and "is None" not in n and "MISSING" not in n]
+    struct = [(n, e, t) for n, e, t in rows if "is None" in n or "MISSING" in n]
+    return fwd, grads, struct
+
+
+@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n"])
+def test_shallow_trunk_parity(kind):
+    mc.SHALLOW[0] = True
+    rows = mc.check_train_step(kind, n=4, verbose=True)
+    if kind in ("tdo", "td"):
+        rows += mc.check_rollout(kind)
+    fwd, grads, struct = _split(rows)
+    bad = [(n, e) for n, e, t in fwd if not e <= max(t, 2e-3)] + [(n, e) for n, e, t in struct if e != 0.0]
+    assert not bad, bad
+    # gradient yard-stick: torch's TF32 path on the same problem
+    if kind == "no":
+        cal = dict((n, e) for n, e, _ in mc.calibrate(kind, n=4))
+        yard = cal["calib torch-tf32 no n4 worst conv weight grad"]
+        worst = max(e for n, e in grads)
+        assert worst <= 1.5 * yard + 2e-2, (worst, yard)
+
+
+@pytest.mark.parametrize("kind", ["no", "tdo"])
+def test_full_depth_parity(kind):
+    rows = mc.check_train_step(kind, n=2)
+    if kind == "tdo":
+        rows += mc.check_rollout(kind, steps=2)
+    fwd, _, struct = _split(rows)
+    bad = [(n, e) for n, e, t in fwd if not e <= (3e-2 if "running_" in n else 1e-2)]
+    bad += [(n, e) for n, e, t in struct if e != 0.0]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n"])
+def test_against_reference_fixture(kind):
+    """Outputs / loss / eval outputs of the CUDA path vs numbers produced by the reference's own modules
+    (tests/golden/forward_<kind>.json)."""
+    from models.losses import PoseDistanceLoss
+    fx = json.load(open(os.path.join(GOLDEN, "forward_%s.json" % kind)))
+    model = mc.build_model(kind).cuda().train()
+    img, x0, tgt = po.synthetic_batch(kind, seed=1, **fx["shapes"])
+    img, x0, tgt = img.cuda(), x0.cuda(), tgt.cuda()
+    crit = PoseDistanceLoss(**fx["loss_cfg"])
+    if kind in ("td", "tdo"):
+        model.reset_initial_state(img.shape[1])
+    out = model(img, None, x0)
+    outs = list(out) if isinstance(out, tuple) else [out]
+    loss = crit(outs[0], tgt) if kind in ("no", "tdo") else crit(outs[0], x0) + crit(outs[1], tgt)
+    loss.backward()
+    for o, g in zip(outs, fx["outputs"]):
+        assert mc.rel(o, torch.tensor(g)) <= 1e-2
+    assert abs(float(loss) - fx["loss"]) <= 1e-2 * abs(fx["loss"])
+    named = dict(model.named_parameters())
+    for n, gn in fx["grad_norms"].items():
+        assert (named[n].grad is None) == (gn is None), n
+    model.eval()
+    with torch.no_grad():
+        if kind in ("td", "tdo"):
+            model.reset_initial_state(img.shape[1])
+        oe = model(img, None, x0)
+    oe = list(oe) if isinstance(oe, tuple) else [oe]
+    for o, g in zip(oe, fx["eval_outputs"]):
+        assert mc.rel(o, torch.tensor(g)) <= 1e-2
+
+
+def test_loss_module_known_answers():
+    from models.losses import PoseDistanceLoss
+    for c in json.load(open(os.path.join(GOLDEN, "loss_vectors.json"))):
+        pred = torch.tensor(c["pred"], device="cuda", requires_grad=True)
+        truth = torch.tensor(c["truth"], device="cuda")
+        if c["mode"] == "val":
+            pos, ang = PoseDistanceLoss(mode="val")(pred.detach(), truth)
+            assert abs(float(pos) - c["pos"]) <= 1e-5 * max(1, abs(c["pos"]))
+            assert abs(ang - c["angle"]) <= 1e-3 * max(1, abs(c["angle"]))
+            continue
+        crit = PoseDistanceLoss(distance_metric=c["metric"], scale_factor=c["scale_factor"], alpha=c["alpha"],
+                                mode=c["mode"])
+        loss = crit(pred, truth)
+        loss.backward()
+        assert abs(float(loss) - c["loss"]) <= 1e-5 * max(1, abs(c["loss"])), c
+        assert torch.allclose(pred.grad.cpu(), torch.tensor(c["grad"]), rtol=1e-4, atol=1e-6), c
+
+
+def test_fused_trainer_matches_autograd_path():
+    """FusedTrainer (flat arenas + fused Adam) == model.forward / loss.backward() / torch.optim.Adam on the
+    same kernels: identical parameters after two steps up to fp32 rounding of the update."""
+    from models.losses import PoseDistanceLoss
+    from pe_b200.trainer import FusedTrainer
+    mc.SHALLOW[0] = True
+    lk = mc.CONFIGS["no"]["loss"]
+    img, x0, tgt = po.synthetic_batch("no", 4, seed=1)
+    img, x0, tgt = img.cuda(), x0.cuda(), tgt.cuda()
+    a = mc.build_model("no").cuda().train()
+    b = mc.build_model("no").cuda().train()
+    tr = FusedTrainer(a, lr=1e-4, **lk)
+    opt = torch.optim.Adam(b.parameters(), lr=1e-4)
+    crit = PoseDistanceLoss(**lk)
+    for _ in range(2):
+        la = tr.step(img, x0, tgt)
+        opt.zero_grad()
+        lb = crit(b(img, None, x0), tgt)
+        lb.backward()
+        opt.step()
+        assert abs(float(la) - float(lb)) <= 1e-4 * abs(float(lb))
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert mc.rel(pa, pb) <= 2e-3, n
+    for (n, ba), (_, bb) in zip(a.named_buffers(), b.named_buffers()):
+        assert mc.rel(ba.float(), bb.float()) <= 1e-3, n
+
+
+@pytest.mark.parametrize("kind,name", [("no", "curve_no_lr1e-5.json"), ("tdo", "curve_tdo_lr1e-5.json")])
+def test_loss_curve_vs_reference(kind, name):
+    """100 Adam steps (lr 1e-5, the smooth regime) against the reference's own loss curve."""
+    path = os.path.join(GOLDEN, name)
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    from pe_b200.trainer import FusedTrainer
+    fx = json.load(open(path))
+    model = mc.build_model(kind).cuda().train()
+    img, x0, tgt = po.synthetic_batch(kind, seed=1, **fx["shapes"])
+    img, x0, tgt = img.cuda(), x0.cuda(), tgt.cuda()
+    tr = FusedTrainer(model, lr=fx["lr"], **fx["loss_cfg"])
+    dev = []
+    for ref in fx["losses"]:
+        dev.append(abs(float(tr.step(img, x0, tgt)) - ref) / abs(ref))
+    assert max(dev) <= 5e-2, max(dev)
+    assert sum(dev) / len(dev) <= 2e-2
+
+
+def test_checkpoint_round_trip_through_gpu(tmp_path):
+    """A checkpoint written from the CUDA model loads bit-identically into a fresh CPU copy and back."""
+    m = mc.build_model("tdo").cuda()
+    path = tmp_path / "ck.pth"
+    torch.save(m.state_dict(), path)
+    sd = torch.load(path, map_location="cpu")
+    m2 = mc.build_model("tdo", seed=5)
+    m2.load_state_dict(sd)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a.cpu(), b), k
