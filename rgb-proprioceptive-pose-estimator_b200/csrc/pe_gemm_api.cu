@@ -166,14 +166,16 @@ static int pick_bn(int n_total) {
 // Long reductions want ring depth, short ones (1x1 convs) are bound by the epilogue's store pipeline.
 static void pick_pipeline(TapParams& p, int ksteps) {
     p.stage_bytes = TG_A_BYTES + (p.bn > 128 ? 32768 : 16384);
-    const int budget = TG_SMEM_BYTES;
-    int nout = (p.store_mode == TG_STORE_TMA) ? (ksteps >= 24 ? (p.bn > 128 ? 1 : 2) : 4) : 0;
+    p.stats_cols = p.stats ? (p.n_total + 31) / 32 * 32 : 0;
+    const int budget = TG_SMEM_BYTES - 2 * p.stats_cols * (int)sizeof(float);
+    // (two epilogue groups: the staging buffers are split evenly between them)
+    int nout = (p.store_mode == TG_STORE_TMA) ? (ksteps >= 24 ? 2 : 4) : 0;
     if (g_dbg_nout > 0 && p.store_mode == TG_STORE_TMA) nout = g_dbg_nout;
     int stages = (budget - nout * TG_A_BYTES) / p.stage_bytes;
     if (stages > TG_STAGES) stages = TG_STAGES;
     if (g_dbg_stages > 0 && g_dbg_stages < stages) stages = g_dbg_stages;
     p.stages = stages;
-    p.nout = nout > 0 ? nout : 1;
+    p.nout = nout > 0 ? nout : 2;
 }
 
 struct Epilogue {
@@ -253,6 +255,8 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
     p.relu = ep.relu;
     p.round_out = ep.round_out;
     p.stats = ep.stats;
+    PE_REQUIRE(!ep.stats || !(ep.scale || ep.bias || ep.residual || ep.relu || ep.round_out),
+               "conv_fwd: batch statistics are taken from the raw output (no affine / residual / ReLU / rounding)");
     pick_pipeline(p, p.n_taps * p.chunks);
     dim3 grid((Cout + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
     return launch_tapgemm(maps, p, grid, stream);
@@ -440,6 +444,8 @@ static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, flo
                    "linear: residual/accumulate needs N and ldy multiples of 4");
         p.store_mode = TG_STORE_DIRECT;
     }
+    PE_REQUIRE(!ep.stats || (p.store_mode == TG_STORE_TMA && !(ep.scale || ep.bias || ep.relu || ep.round_out || p.residual)),
+               "linear_fwd: statistics need the TMA store path and a raw (un-activated) output");
     pick_pipeline(p, p.chunks);
     dim3 grid((N + p.bn - 1) / p.bn, p.tiles_w, 1);
     return launch_tapgemm(maps, p, grid, stream);

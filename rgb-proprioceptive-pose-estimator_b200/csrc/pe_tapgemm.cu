@@ -47,8 +47,10 @@ __device__ __forceinline__ Work decode_work(const TapParams& p, int w) {
         k.k_begin = k.z * per;
         k.nk = max(0, min(ktotal, k.k_begin + per) - k.k_begin);
     } else {
-        k.tap = k.z / p.ksplit;
-        const int split = k.z - k.tap * p.ksplit;
+        // taps vary fastest: CTAs running side by side reduce the same pixel range for different taps,
+        // so the dY / X tiles they share are served from L2 instead of being re-read from HBM per tap
+        k.tap = k.z % p.n_taps;
+        const int split = k.z / p.n_taps;
         const int per = (p.pt_total + p.ksplit - 1) / p.ksplit;
         k.k_begin = split * per;
         k.nk = max(0, min(p.pt_total, k.k_begin + per) - k.k_begin);
@@ -64,17 +66,18 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     __shared__ __align__(8) uint64_t s_tmem_full[2];
     __shared__ __align__(8) uint64_t s_tmem_empty[2];
     __shared__ uint32_t s_tmem_base;
-    __shared__ float s_scale[TG_MAX_BN];
-    __shared__ float s_shift[TG_MAX_BN];
-    __shared__ float s_sum[TG_MAX_BN];
-    __shared__ float s_sq[TG_MAX_BN];
+    __shared__ __align__(16) float s_scale[TG_MAX_BN];
+    __shared__ __align__(16) float s_shift[TG_MAX_BN];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     // 1024-byte aligned tile storage (SWIZZLE_128B atoms are 1024 B)
     const uint32_t smem_base = smem_u32(smem_raw);
-    const uint32_t stage_base = smem_base + p.stages * p.stage_bytes;   // TG_NSTAGE_OUT x 16 KB epilogue staging
+    const uint32_t stage_base = smem_base + p.stages * p.stage_bytes;   // nout x 16 KB epilogue staging
+    // CTA-wide per-channel statistics (one global atomic per channel per CTA instead of per tile)
+    float* s_sum = reinterpret_cast<float*>(smem_raw + p.stages * p.stage_bytes + p.nout * TG_A_BYTES);
+    float* s_sq = s_sum + p.stats_cols;
 
     // ---- one-time setup --------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -84,7 +87,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&s_tmem_full[a]), 1);
-            mbar_init(smem_u32(&s_tmem_empty[a]), 128);
+            mbar_init(smem_u32(&s_tmem_empty[a]), 256);
         }
         fence_mbar_init();
     }
@@ -138,8 +141,11 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     }
                 } else {
                     const int m_off = wk.mt * TG_BM;
-                    const int nb = (p.bn + 31) >> 5;
-                    const uint32_t bytes = static_cast<uint32_t>(4 + nb) * 4096u;
+                    // only the 32-wide atoms that hold real channels are fetched; the MMA reads the rest of the
+                    // stage as don't-care rows / columns of the accumulator
+                    const int na = min(4, (p.m_total - m_off + 31) >> 5);
+                    const int nb = min((p.bn + 31) >> 5, (p.n_total - n_off + 31) >> 5);
+                    const uint32_t bytes = static_cast<uint32_t>(na + nb) * 4096u;
                     const int dw = p.tap_dw[wk.tap], dh = p.tap_dh[wk.tap];
                     const CUtensorMap* mb = &maps.b[p.tap_map[wk.tap]];
                     for (int j = 0; j < wk.nk; ++j, ++it) {
@@ -155,8 +161,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         const uint32_t sa = smem_base + s * p.stage_bytes;
                         const uint32_t sb = sa + TG_A_BYTES;
                         mbar_arrive_expect_tx(full, bytes);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
+                        for (int q = 0; q < na; ++q)
                             tma_load_4d(sa + q * 4096, &maps.a[0], full, m_off + 32 * q, o.w0, o.h0, o.n0);
                         for (int q = 0; q < nb; ++q)
                             tma_load_4d(sb + q * 4096, mb, full, n_off + 32 * q, o.w0 + dw, o.h0 + dh, o.n0);
@@ -214,11 +219,24 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         __syncwarp();
     } else {
         // =============================== epilogue ============================================
+        // Two groups of four warps; group g drains the 32-column chunks with (chunk & 1) == g.  Each group
+        // owns its named barrier, its share of the staging buffers and its TMA-store issuing thread.
+        const int ew = warp - 2;           // 0..7
+        const int grp = ew >> 2;           // epilogue group
         const int q = warp & 3;            // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;     // tile row == TMEM lane
-        const int et = threadIdx.x - 64;   // 0..127
+        const int et = (ew & 3) * 32 + lane;      // 0..127 within the group
+        const int eall = ew * 32 + lane;          // 0..255 over both groups
+        const int bar_id = 1 + grp;
+        const int nbuf = p.nout >> 1 > 0 ? p.nout >> 1 : 1;      // staging buffers per group
+        const uint32_t my_stage = stage_base + (p.nout >= 2 ? grp * nbuf : 0) * TG_A_BYTES;
+        const bool affine = (p.scale != nullptr) || (p.bias != nullptr);
         uint32_t tile_i = 0, cc = 0;
         bool ok = true;
+        if (p.stats) {
+            for (int cidx = eall; cidx < 2 * p.stats_cols; cidx += 256) s_sum[cidx] = 0.f;
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+        }
         for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
             const Work wk = decode_work(p, w);
             const int n_off = wk.nt * p.bn;
@@ -226,24 +244,24 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             if (wk.nk > 0) ++tile_i;
 
             // per-tile column constants (everyone is past the previous tile's reads after this barrier)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int cidx = et; cidx < p.bn; cidx += 128) {
-                const int col = n_off + cidx;
-                float sc = 1.f, sh = 0.f;
-                if (col < p.n_total) {
-                    if (p.scale) {
-                        sc = p.scale[col];
-                        sh = p.shift[col];
-                    } else if (p.bias) {
-                        sh = p.bias[col];
+            if (affine) {
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                for (int cidx = eall; cidx < p.bn; cidx += 256) {
+                    const int col = n_off + cidx;
+                    float sc = 1.f, sh = 0.f;
+                    if (col < p.n_total) {
+                        if (p.scale) {
+                            sc = p.scale[col];
+                            sh = p.shift[col];
+                        } else {
+                            sh = p.bias[col];
+                        }
                     }
+                    s_scale[cidx] = sc;
+                    s_shift[cidx] = sh;
                 }
-                s_scale[cidx] = sc;
-                s_shift[cidx] = sh;
-                s_sum[cidx] = 0.f;
-                s_sq[cidx] = 0.f;
+                asm volatile("bar.sync 3, 256;" ::: "memory");
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
 
             if (wk.nk > 0) {
                 ok = mbar_wait(smem_u32(&s_tmem_full[acc]), aph);
@@ -278,11 +296,14 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             const float* res_row = p.residual ? p.residual + row_lin * p.ld_res : nullptr;
 
             const int nchunks = (p.bn + 31) >> 5;
-            for (int c = 0; c < nchunks; ++c) {
+            int last_c = -1;                       // last chunk this group reads from TMEM
+            for (int c = grp; c < nchunks; c += 2) last_c = c;
+            if (last_c < 0 && wk.nk > 0) mbar_arrive(smem_u32(&s_tmem_empty[acc]));
+            for (int c = grp; c < nchunks; c += 2) {
                 float v[32];
                 if (wk.nk > 0) {
                     tmem_ld_32x32(tmem_base + acc * TG_MAX_BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-                    if (c == nchunks - 1) {   // accumulator fully read: hand it back to the MMA warp
+                    if (c == last_c) {   // this thread is done with the accumulator: hand it back
                         tc_fence_before();
                         mbar_arrive(smem_u32(&s_tmem_empty[acc]));
                     }
@@ -295,33 +316,18 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.f;
                 }
-                // ---- per-channel batch statistics of the raw accumulator -----------------------
-                if (p.stats) {
-                    float a[32], b[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        a[i] = v[i];
-                        b[i] = v[i] * v[i];
-                    }
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float sa_ = up ? a[i] : a[i + off];
-                            const float ka_ = up ? a[i + off] : a[i];
-                            a[i] = ka_ + __shfl_xor_sync(0xffffffffu, sa_, off);
-                            const float sb_ = up ? b[i] : b[i + off];
-                            const float kb_ = up ? b[i + off] : b[i];
-                            b[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, off);
-                        }
-                    }
-                    atomicAdd(&s_sum[c * 32 + lane], a[0]);
-                    atomicAdd(&s_sq[c * 32 + lane], b[0]);
-                }
                 // ---- affine / residual / activation --------------------------------------------
+                if (affine) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], s_scale[c * 32 + i], s_shift[c * 32 + i]);
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[c * 32 + i]);
+                        const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[c * 32 + i]);
+                        v[i] = fmaf(v[i], sc4.x, sh4.x);
+                        v[i + 1] = fmaf(v[i + 1], sc4.y, sh4.y);
+                        v[i + 2] = fmaf(v[i + 2], sc4.z, sh4.z);
+                        v[i + 3] = fmaf(v[i + 3], sc4.w, sh4.w);
+                    }
+                }
                 if (res_row && row_valid) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -344,32 +350,70 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                 }
                 // ---- store ---------------------------------------------------------------------
                 if (p.store_mode == TG_STORE_TMA) {
-                    const uint32_t region = stage_base + (cc % p.nout) * TG_A_BYTES;
-                    // the store issued from this buffer TG_NSTAGE_OUT chunks ago must have finished reading it
+                    const uint32_t region = my_stage + (cc % nbuf) * TG_A_BYTES;
+                    // the store issued from this buffer `nbuf` chunks ago must have finished reading it
                     if (et == 0) {
-                        if (p.nout >= 4) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-                        else if (p.nout == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-                        else if (p.nout == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (nbuf >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (!(p.dbg_flags & 2)) {
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     const uint32_t rbase = region + row * 128;
+                    if (!(p.dbg_flags & 2)) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t addr = rbase + ((j ^ (row & 7)) << 4);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]),
-                                     "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                                     : "memory");
-                    }
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t addr = rbase + ((j ^ (row & 7)) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]),
+                                         "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                                         : "memory");
+                        }
                     }
                     fence_proxy_async_smem();
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     if (et == 0 && !(p.dbg_flags & 3)) {
                         tma_store_4d(&maps.d, region, col0, o.w0, o.h0, o.n0);
                         tma_store_commit();
                     }
                     ++cc;
+                    // ---- per-channel batch statistics: column pass over the staged (raw) tile ------
+                    // thread = (4-column group cg, 8-row group rg); conflict-free 128-bit reads
+                    if (p.stats) {
+                        const int cg = et & 7, rg = et >> 3;
+                        float4 sm = make_float4(0.f, 0.f, 0.f, 0.f), sq = sm;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t addr = region + (rg * 8 + i) * 128 + ((cg ^ i) << 4);
+                            float4 t;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                         : "r"(addr));
+                            sm.x += t.x; sm.y += t.y; sm.z += t.z; sm.w += t.w;
+                            sq.x = fmaf(t.x, t.x, sq.x); sq.y = fmaf(t.y, t.y, sq.y);
+                            sq.z = fmaf(t.z, t.z, sq.z); sq.w = fmaf(t.w, t.w, sq.w);
+                        }
+                        // lanes {l, l^8, l^16, l^24} share cg: fold the four row groups of the warp
+#pragma unroll
+                        for (int off = 8; off <= 16; off <<= 1) {
+                            sm.x += __shfl_xor_sync(0xffffffffu, sm.x, off);
+                            sm.y += __shfl_xor_sync(0xffffffffu, sm.y, off);
+                            sm.z += __shfl_xor_sync(0xffffffffu, sm.z, off);
+                            sm.w += __shfl_xor_sync(0xffffffffu, sm.w, off);
+                            sq.x += __shfl_xor_sync(0xffffffffu, sq.x, off);
+                            sq.y += __shfl_xor_sync(0xffffffffu, sq.y, off);
+                            sq.z += __shfl_xor_sync(0xffffffffu, sq.z, off);
+                            sq.w += __shfl_xor_sync(0xffffffffu, sq.w, off);
+                        }
+                        const int colb = col0 + cg * 4;
+                        if (lane < 8 && colb < p.n_total) {
+                            atomicAdd(&s_sum[colb], sm.x);
+                            atomicAdd(&s_sum[colb + 1], sm.y);
+                            atomicAdd(&s_sum[colb + 2], sm.z);
+                            atomicAdd(&s_sum[colb + 3], sm.w);
+                            atomicAdd(&s_sq[colb], sq.x);
+                            atomicAdd(&s_sq[colb + 1], sq.y);
+                            atomicAdd(&s_sq[colb + 2], sq.z);
+                            atomicAdd(&s_sq[colb + 3], sq.w);
+                        }
+                    }
                 } else if (row_valid) {
                     if (p.store_mode == TG_STORE_DIRECT) {
                         if (col0 + 32 <= p.n_total && (p.ldo & 3) == 0) {
@@ -389,15 +433,12 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     }
                 }
             }
-            if (p.stats) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int cidx = et; cidx < p.bn; cidx += 128) {
-                    const int col = n_off + cidx;
-                    if (col < p.n_total) {
-                        atomicAdd(p.stats + col, static_cast<double>(s_sum[cidx]));
-                        atomicAdd(p.stats + p.n_total + col, static_cast<double>(s_sq[cidx]));
-                    }
-                }
+        }
+        if (p.stats) {
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            for (int col = eall; col < p.n_total; col += 256) {
+                atomicAdd(p.stats + col, static_cast<double>(s_sum[col]));
+                atomicAdd(p.stats + p.n_total + col, static_cast<double>(s_sq[col]));
             }
         }
         if (p.store_mode == TG_STORE_TMA && et == 0) tma_store_wait_all();
