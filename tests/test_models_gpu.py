@@ -4,7 +4,7 @@ the CPU oracle and the golden fixtures generated from the reference's own module
 Tolerances (TF32 tensor-core operands, fp32 accumulate; see DESIGN.md "Numerics"):
   * full ResNet-50 depth, random init, 2-4 frames: outputs / loss within 2e-2 relative of the fp32 oracle.
     The yard-stick is torch's own cuDNN TF32 path, which lands 3e-3..5e-3 from the same oracle.
-  * 4-block trunk (well conditioned): outputs / loss within 2e-3.
+  * 4-block trunk (well conditioned): outputs / loss within 5e-3.
   * gradients: a random-init BN/ReLU stack amplifies rounding noise ~2000x (cuDNN *fp32* already differs
     from CPU fp32 by 2e-3..3e-2 in relative gradient norm, cuDNN TF32 by 0.1..0.8).  We therefore assert
     that our per-parameter gradient error is no worse than 1.5x torch-TF32's error (+2e-2) on the same
@@ -46,7 +46,7 @@ def test_shallow_trunk_parity(kind):
     if kind in ("tdo", "td"):
         rows += mc.check_rollout(kind)
     fwd, grads, struct = _split(rows)
-    bad = [(n, e) for n, e, t in fwd if not e <= max(t, 2e-3)] + [(n, e) for n, e, t in struct if e != 0.0]
+    bad = [(n, e) for n, e, t in fwd if not e <= max(t, 5e-3)] + [(n, e) for n, e, t in struct if e != 0.0]
     assert not bad, bad
     # gradient yard-stick: torch's TF32 path on the same problem
     if kind == "no":
