@@ -1,0 +1,110 @@
+"""Streaming rollout inference (the per-step forward of util/learn_utils.py:366-455) under CUDA Graph capture.
+
+The reference runs one batch-1 forward per simulator step on the CPU with autograd enabled and the LSTM
+state carried in python attributes.  Here the eval-mode forward -- folded BatchNorm,
+fused conv epilogues, LSTM cell, head -- is captured ONCE into a CUDA graph over static input / state /
+output buffers; every step is then two small H2D copies, one graph launch and one 28-byte D2H read.
+"""
+import torch
+
+from . import native
+from .trainer import get_core
+
+
+class StreamingEstimator:
+    def __init__(self, model, batch_size=1, use_graph=True, device=None):
+        self.model = model
+        self.core = get_core(model)
+        self.N = batch_size
+        self.dev = device or next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise native.PeError("StreamingEstimator needs the model on a CUDA device (no CPU fallback)")
+        self.seq = bool(getattr(model, "requires_sequence", False))
+        self.use_graph = use_graph
+        lead = (1, batch_size) if self.seq else (batch_size,)
+        self.img = torch.zeros(*lead, 3, 224, 224, device=self.dev)
+        self.x0 = torch.zeros(*lead, 7, device=self.dev)
+        self.state = self._zero_state()
+        self.graph = None
+        self.outs = None
+        model.eval()
+
+    def _zero_state(self):
+        m, N, dev = self.model, self.N, self.dev
+        name = type(m).__name__
+        if name == "TemporallyDependentObjectStateEstimator":
+            return (torch.zeros(N, m.hidden_dim, device=dev), torch.zeros(N, m.hidden_dim, device=dev))
+        if name == "TemporallyDependentStateEstimator":
+            return ((torch.zeros(N, m.pre_measurement_hidden_dim, device=dev),
+                     torch.zeros(N, m.pre_measurement_hidden_dim, device=dev)),
+                    (torch.zeros(N, m.post_measurement_hidden_dim, device=dev),
+                     torch.zeros(N, m.post_measurement_hidden_dim, device=dev)))
+        return None
+
+    def reset(self):
+        """model.reset_initial_state(batch_size) of the rollout loop (util/learn_utils.py:342)."""
+        def z(t):
+            if isinstance(t, tuple):
+                for u in t:
+                    z(u)
+            elif t is not None:
+                t.zero_()
+        z(self.state)
+
+    def _forward(self):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        outs, _, new_state = self.core.forward((self.img, self.x0), False, False, self.state)
+
+        def carry(dst, src):
+            if isinstance(dst, tuple):
+                for d, s in zip(dst, src):
+                    carry(d, s)
+            elif dst is not None:
+                L.pe_copy_cols(P(src), src.stride(0), P(dst), dst.stride(0), dst.shape[0], dst.shape[1], 0, st)
+        carry(self.state, new_state)
+        return outs
+
+    def _capture(self):
+        # warm every lazily initialised piece (packed weights, folded BN, tensor-map entry point) eagerly
+        saved = self._clone_state()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._forward()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore_state(saved)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outs = self._forward()
+        self._restore_state(saved)
+
+    def _clone_state(self):
+        def c(t):
+            return tuple(c(u) for u in t) if isinstance(t, tuple) else (None if t is None else t.clone())
+        return c(self.state)
+
+    def _restore_state(self, saved):
+        def r(dst, src):
+            if isinstance(dst, tuple):
+                for d, s in zip(dst, src):
+                    r(d, s)
+            elif dst is not None:
+                dst.copy_(src)
+        r(self.state, saved)
+
+    @torch.no_grad()
+    def step(self, img, self_measurement):
+        """img (N,3,224,224) [or (1,N,...)], self_measurement (N,7): host or device tensors.  Returns the
+        pose estimate(s) as device tensors that stay valid until the next step."""
+        self.img.copy_(img.reshape(self.img.shape), non_blocking=True)
+        self.x0.copy_(self_measurement.reshape(self.x0.shape), non_blocking=True)
+        if not self.use_graph:
+            outs = self._forward()
+        else:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+            outs = self.outs
+        return outs if len(outs) > 1 else outs[0]
