@@ -15,9 +15,9 @@ import model_checks as mc  # noqa: E402
 from oracle import pose_oracle as po  # noqa: E402
 
 
-def run_curve(kind, steps=None, use_autograd=False):
+def run_curve(kind, steps=None, use_autograd=False, fixture=None):
     from pe_b200.trainer import FusedTrainer
-    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "curve_%s.json" % kind)))
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", fixture or "curve_%s.json" % kind)))
     steps = steps or len(fx["losses"])
     model = mc.build_model(kind).cuda().train()
     img, x0, tgt = po.synthetic_batch(kind, seed=1, **fx["shapes"])
@@ -46,8 +46,9 @@ def run_curve(kind, steps=None, use_autograd=False):
 
 if __name__ == "__main__":
     kind = sys.argv[1] if len(sys.argv) > 1 else "no"
+    fixture = sys.argv[2] if len(sys.argv) > 2 else None
     for mode in (False, True):
-        losses, ref, dev = run_curve(kind, use_autograd=mode)
+        losses, ref, dev = run_curve(kind, use_autograd=mode, fixture=fixture)
         print("== %s %s: max rel dev %.3e, mean %.3e, final ours %.4f ref %.4f" %
               (kind, "autograd+torch.optim.Adam" if mode else "FusedTrainer", max(dev), sum(dev) / len(dev), losses[-1], ref[-1]))
         for i in range(0, len(losses), max(1, len(losses) // 20)):
