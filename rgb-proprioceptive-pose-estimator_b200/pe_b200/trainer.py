@@ -120,7 +120,12 @@ class FusedTrainer:
         """One optimisation step.  `targets`: a tensor (object-pose models) or a (x0, x1) pair for the
         two-headed models, matching util/learn_utils.py:160-172.  Returns the loss as a 1-element device
         tensor (sum over the local samples)."""
-        import torch.distributed as dist
+        loss = self.forward_backward(img, self_measurement, targets)
+        self.apply_update()
+        return loss
+
+    def forward_backward(self, img, self_measurement, targets):
+        """forward + loss + backward (+ gradient all-reduce): leaves the summed gradient in self.g_flat."""
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         if self._flat is None:
             self._flatten()
@@ -157,6 +162,12 @@ class FusedTrainer:
             red.wait()
         else:
             core.backward(saved, tuple(douts), self.grad_of)
+        self._pending_loss = losses.sum() if len(outs) > 1 else losses
+        return self._pending_loss
+
+    def apply_update(self):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        core = self.core
         self.t += 1
         n = self.p_flat.numel()
         if self.optimizer == "adam":
@@ -166,4 +177,3 @@ class FusedTrainer:
             L.pe_sgd_step(P(self.p_flat), P(self.g_flat), P(self.m_flat) if self.momentum else None, n, self.lr,
                           self.momentum, self.wd, int(self.t == 1), 1.0, st)
         invalidate_core(core)
-        return losses.sum() if len(outs) > 1 else losses

@@ -1,0 +1,62 @@
+"""Multi-GPU check (run under torchrun, NCCL): the bucketed, overlapped gradient all-reduce of the
+FusedTrainer equals the plain sum of the ranks' local gradients, and every rank ends the step with
+identical parameters.  Each rank trains on its own shard of a global synthetic batch."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "rgb-proprioceptive-pose-estimator_b200"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import model_checks as mc  # noqa: E402
+from oracle import pose_oracle as po  # noqa: E402
+from pe_b200.ddp import shard_range  # noqa: E402
+from pe_b200.trainer import FusedTrainer  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    kind = sys.argv[1] if len(sys.argv) > 1 else "tdo"
+    n_global = 2 * world
+    img, x0, tgt = po.synthetic_batch(kind, n_global, s=2, seed=1) if kind in ("td", "tdo") else po.synthetic_batch(kind, n_global, seed=1)
+    lo, hi = shard_range(n_global, rank, world)
+    sl = (slice(None), slice(lo, hi)) if kind in ("td", "tdo") else (slice(lo, hi),)
+    img, x0, tgt = img[sl].contiguous().to(dev), x0[sl].contiguous().to(dev), tgt[sl].contiguous().to(dev)
+    lk = mc.CONFIGS[kind]["loss"]
+    a = mc.build_model(kind).to(dev).train()
+    b = mc.build_model(kind).to(dev).train()
+    ta = FusedTrainer(a, lr=1e-4, process_group=dist.group.WORLD, bucket_mb=8, **lk)
+    tb = FusedTrainer(b, lr=1e-4, **lk)
+    ok = True
+    for step in range(3):                       # step 0: single all-reduce; steps 1-2: overlapped buckets
+        ta.forward_backward(img, x0, tgt)
+        tb.forward_backward(img, x0, tgt)
+        want = tb.g_flat.clone()
+        dist.all_reduce(want)
+        err = float((ta.g_flat - want).abs().max() / want.abs().max())
+        buckets = ta.reducer.launched if ta.reducer is not None else 0
+        ta.apply_update()
+        tb.g_flat.copy_(want)
+        tb.apply_update()
+        perr = float((ta.p_flat - tb.p_flat).abs().max())
+        ref = ta.p_flat.clone()
+        dist.broadcast(ref, 0)
+        same = bool(torch.equal(ref, ta.p_flat))
+        if rank == 0:
+            print("step %d: grad err vs plain sum %.2e, buckets %d, param diff %.2e, ranks identical %s"
+                  % (step, err, buckets, perr, same), flush=True)
+        ok = ok and err < 1e-4 and same
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
