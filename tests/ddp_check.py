@@ -30,14 +30,26 @@ def main():
     sl = (slice(None), slice(lo, hi)) if kind in ("td", "tdo") else (slice(lo, hi),)
     img, x0, tgt = img[sl].contiguous().to(dev), x0[sl].contiguous().to(dev), tgt[sl].contiguous().to(dev)
     lk = mc.CONFIGS[kind]["loss"]
+    # 4-block trunk: the full-depth random-init net amplifies summation-order noise of the split-K atomics
+    # by ~1e5, which would drown the comparison; the plumbing under test is depth independent
+    mc.SHALLOW[0] = "--full" not in sys.argv
     a = mc.build_model(kind).to(dev).train()
     b = mc.build_model(kind).to(dev).train()
+    c = mc.build_model(kind).to(dev).train()
+    tc = FusedTrainer(c, lr=1e-4, **lk)
     ta = FusedTrainer(a, lr=1e-4, process_group=dist.group.WORLD, bucket_mb=8, **lk)
     tb = FusedTrainer(b, lr=1e-4, **lk)
     ok = True
+    from pe_b200.trainer import invalidate_core
     for step in range(3):                       # step 0: single all-reduce; steps 1-2: overlapped buckets
+        if step > 0:                            # same parameters everywhere: only the reduction is under test
+            for t in (tb, tc):
+                t.p_flat.copy_(ta.p_flat)
+                invalidate_core(t.core)
         ta.forward_backward(img, x0, tgt)
         tb.forward_backward(img, x0, tgt)
+        tc.forward_backward(img, x0, tgt)
+        noise = float((tb.g_flat - tc.g_flat).abs().max() / tb.g_flat.abs().max())
         want = tb.g_flat.clone()
         dist.all_reduce(want)
         err = float((ta.g_flat - want).abs().max() / want.abs().max())
@@ -45,14 +57,17 @@ def main():
         ta.apply_update()
         tb.g_flat.copy_(want)
         tb.apply_update()
+        tc.g_flat.copy_(want)
+        tc.apply_update()
         perr = float((ta.p_flat - tb.p_flat).abs().max())
         ref = ta.p_flat.clone()
         dist.broadcast(ref, 0)
         same = bool(torch.equal(ref, ta.p_flat))
         if rank == 0:
-            print("step %d: grad err vs plain sum %.2e, buckets %d, param diff %.2e, ranks identical %s"
-                  % (step, err, buckets, perr, same), flush=True)
-        ok = ok and err < 1e-4 and same
+            print("step %d: grad err vs plain sum %.2e (run-to-run noise of two identical local runs %.2e), "
+                  "buckets %d, param diff %.2e, ranks identical %s" % (step, err, noise, buckets, perr, same),
+                  flush=True)
+        ok = ok and err < max(1e-4, 10 * noise) and same
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
