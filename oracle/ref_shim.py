@@ -90,6 +90,7 @@ class _RefModules:
 def load():
     """Import the reference's models / losses under private names so they never collide with the
     product's own top-level `models` / `util` packages."""
+    import importlib
     import importlib.util
 
     install()
@@ -97,7 +98,14 @@ def load():
                                              "models.time_sensitive", "models.losses")}
     for k in saved:
         sys.modules.pop(k, None)
-    sys.path.insert(0, REFERENCE_ROOT)
+    # The reference's `models` / `util` are namespace packages (no __init__.py); a regular package of the
+    # same name anywhere on sys.path would shadow them, so such entries are hidden during the import.
+    saved_path = list(sys.path)
+    sys.path[:] = [REFERENCE_ROOT] + [
+        q for q in saved_path
+        if not (os.path.isfile(os.path.join(q or ".", "models", "__init__.py"))
+                or os.path.isfile(os.path.join(q or ".", "util", "__init__.py")))]
+    importlib.invalidate_caches()
     try:
         import warnings
         with warnings.catch_warnings():
@@ -107,7 +115,8 @@ def load():
             import models.time_sensitive as ref_ts      # noqa
             import util.model_utils as ref_mu           # noqa
     finally:
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path[:] = saved_path
+        importlib.invalidate_caches()
         out = _RefModules()
         out.losses = sys.modules.get("models.losses")
         out.naive = sys.modules.get("models.naive")

@@ -369,7 +369,7 @@ static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B
     p.ldo = Cin;
     const int mt = (Cout + TG_BM - 1) / TG_BM, nt = (Cin + p.bn - 1) / p.bn;
     const int base_ctas = mt * nt * p.n_taps;
-    int ks = (4 * num_sms() + base_ctas - 1) / base_ctas;
+    int ks = (2 * num_sms() + base_ctas - 1) / base_ctas;
     if (ks > p.pt_total) ks = p.pt_total;
     if (ks < 1) ks = 1;
     // every split must own at least one pixel tile
@@ -459,7 +459,7 @@ static int linear_wgrad_impl(const float* x, int ldx, const float* dy, int lddy,
     TapParams p;
     init_params(p);
     p.mode = 1;
-    p.bn = (K >= 256 && g_dbg_max_bn >= 256) ? 256 : (K >= 128 ? 128 : ((K + 31) / 32) * 32);
+    p.bn = (K >= 256 && g_dbg_max_bn >= 256) ? 256 : ((K + 31) / 32) * 32;
     p.m_rows = TG_BM;
     p.box_w = TG_BK;
     p.box_h = p.box_n = 1;

@@ -426,6 +426,13 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                             for (int i = 0; i < 32; ++i)
                                 if (col0 + i < p.n_total) out_row[col0 + i] = v[i];
                         }
+                    } else if (col0 + 32 <= p.n_total && (p.ldo & 3) == 0) {
+                        // split-K partial sums: 128-bit vector reductions (4x fewer RED instructions)
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out_row + col0 + i),
+                                         "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3])
+                                         : "memory");
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)

@@ -63,7 +63,12 @@ def test_forward_backward_golden(kind):
     loss.backward()
     for o, g in zip(outs, fx["outputs"]):
         assert torch.allclose(o.detach(), torch.tensor(g), rtol=1e-4, atol=1e-6)
-    assert abs(float(loss) - fx["loss"]) <= 1e-5 * abs(fx["loss"])
+    if fx["loss"] != fx["loss"]:
+        # reference quirk Q2/Q7: the "n" model's ReLU'd pre-measurement head emits an all-zero quaternion at
+        # init, which PoseDistanceLoss normalises without an epsilon -> NaN in the reference itself
+        assert torch.isnan(loss)
+    else:
+        assert abs(float(loss) - fx["loss"]) <= 1e-5 * abs(fx["loss"])
     for n, gn in fx["grad_norms"].items():
         g = orc.sd[n].grad
         if gn is None:
