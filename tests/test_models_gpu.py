@@ -90,7 +90,11 @@ def test_against_reference_fixture(kind):
 
     for o, g in zip(outs, fx["outputs"]):
         assert close(o, g)
-    assert abs(float(loss) - fx["loss"]) <= 3e-2 * abs(fx["loss"]), (float(loss), fx["loss"])
+    if fx["loss"] != fx["loss"]:
+        # the reference itself yields NaN here (all-zero ReLU'd quaternion, no epsilon: quirks Q2/Q7)
+        assert torch.isnan(loss)
+    else:
+        assert abs(float(loss) - fx["loss"]) <= 3e-2 * abs(fx["loss"]), (float(loss), fx["loss"])
     named = dict(model.named_parameters())
     for n, gn in fx["grad_norms"].items():
         assert (named[n].grad is None) == (gn is None), n
