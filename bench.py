@@ -73,9 +73,22 @@ class ClockSampler(threading.Thread):
 
 
 def build(kind, seed=0):
+    """Reference constructor under torch.manual_seed(seed), random init.  The one-shot models put a ReLU after
+    their LAST layer (reference quirk, models/naive.py:343-345), so a random-init network emits all-zero
+    quaternions and the reference loss (no epsilon in the normalisation, models/losses.py:68-69) is NaN from
+    step 0.  The bench keeps the arithmetic finite by starting the last layer's bias at +0.5; shapes, FLOPs
+    and bytes are unchanged."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import model_checks
-    return model_checks.build_model(kind, seed)
+    import torch
+    model = model_checks.build_model(kind, seed)
+    with torch.no_grad():
+        if kind == "no":
+            getattr(model, "fc%d" % (model.n_fc - 1)).module.bias.fill_(0.5)
+        elif kind == "n":
+            getattr(model, "pre_fc%d" % (model.n_pre_hidden - 1)).bias.fill_(0.5)
+            getattr(model, "post_fc%d" % (model.n_post_hidden - 1)).bias.fill_(0.5)
+    return model
 
 
 def synth(kind, n, s, seed):
@@ -160,7 +173,7 @@ def run_ours(args):
     L = native.lib()
     kind = args.model
     model = build(kind).to(dev).train()
-    trainer = FusedTrainer(model, lr=1e-3, process_group=pg, **LOSS)
+    trainer = FusedTrainer(model, lr=args.lr, process_group=pg, **LOSS)
     seq = args.seq
     img, x0, tgt = synth(kind, args.batch, seq, 1 + rank)
     frames = args.batch * (seq if kind in ("td", "tdo") else 1)
@@ -258,9 +271,11 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                rate, sec, fr = cpu_reference_rate(kind, args.cpu_batch, seq, 3, 1)
+                n_cpu = 40
+                rate, sec, fr = cpu_reference_rate(kind, args.cpu_batch, seq, n_cpu, 2)
                 out["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-                                       "sample": "%d-frame batch, median of 3 steps (%.2f s/step)" % (fr, sec)}
+                                       "sample": "%d-frame batches of the same training step, median of %d steps "
+                                                 "(%.2f s/step, ~%.0f s of CPU work)" % (fr, n_cpu, sec, n_cpu * sec)}
             except Exception as e:  # the GPU numbers stand on their own
                 out["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(out), flush=True)
@@ -279,6 +294,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames (naive) or episodes (sequence models) per GPU")
     ap.add_argument("--seq", type=int, default=None)
     ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--lr", type=float, default=1e-4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.seq is None:

@@ -44,8 +44,11 @@ void pe_debug_max_bn(int bn);
 int pe_conv2d_fwd(const float* x, const float* w_tck, float* y, int B, int H, int W, int Cin, int Cout, int R,
                   int S, int stride, int pad, const float* scale, const float* shift, const float* residual,
                   int relu, int round_out, double* stats, void* stream);
+/* dgrad epilogue (1x1 stride-1 only): dx += residual * (res_maskbits ? mask : 1) -- the identity branch of a
+ * residual join is added (and ReLU-masked from the join's bit mask) while dx is still in registers.   */
 int pe_conv2d_dgrad(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin, int Cout,
-                    int R, int S, int stride, int pad, void* stream);
+                    int R, int S, int stride, int pad, const float* residual, const unsigned* res_maskbits,
+                    void* stream);
 int pe_conv2d_wgrad(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin, int Cout,
                     int R, int S, int stride, int pad, void* stream);
 /* OIHW (checkpoint layout, util/model_utils.py:136-141) <-> packed tap-major layouts */
@@ -94,18 +97,27 @@ int pe_bn_finalize(double* stats, const float* gamma, const float* beta, float* 
 /* out = act(y*scale[c] + shift[c] (+ residual)) */
 int pe_bn_apply(const float* y, const float* scale, const float* shift, const float* residual, float* out,
                 long long P, int C, int relu, int round_tf32, void* stream);
-/* backward pass 1: g = (dout + dout2)*(out>0 if relu); sums = double[2*C] += (sum g, sum g*xhat).
+/* train-mode forward in ONE pass: scale / shift rebuilt from `stats` by every block (published with mean /
+ * invstd for the backward pass), running statistics and num_batches_tracked updated, out = act(y*scale +
+ * shift (+ residual)).  maskbits (optional, ceil(P*C/128)*4 words, 16-byte aligned): the (out > 0) mask,
+ * one bit per element -- float4 index i owns bit (i & 31) of words [(i >> 5)*4 + component].           */
+int pe_bn_train_apply(const float* y, const double* stats, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, long long* num_batches_tracked, float* scale,
+                      float* shift, float* mean, float* invstd, const float* residual, float* out,
+                      unsigned* maskbits, long long P, int C, float momentum, float eps, int relu, int round_tf32,
+                      void* stream);
+/* backward pass 1: g = (dout + dout2)*(out>0 if relu)*(maskbits if given); sums = double[2*C] += (sum g, sum g*xhat).
  * `out` may be NULL for a BN without residual input: the ReLU mask is then recomputed from
  * y*mask_scale + mask_shift (the forward's folded scale / shift), saving one full read of the activations.
  * dout2 (optional) is the second gradient branch of a residual join, summed on the fly.              */
 int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
-                     const float* invstd, const float* mask_scale, const float* mask_shift, double* sums,
-                     long long P, int C, int relu, void* stream);
+                     const float* invstd, const float* mask_scale, const float* mask_shift,
+                     const unsigned* maskbits, double* sums, long long P, int C, int relu, void* stream);
 /* backward pass 2: dy = gamma*invstd*(g - sum_g/P - xhat*sum_gx/P); dres = g (optional);
  * dgamma = sum_gx, dbeta = sum_g (written or accumulated).  The caller zeroes `sums` before pass 1.   */
 int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
                     const float* invstd, const float* gamma, const float* mask_scale, const float* mask_shift,
-                    double* sums, float* dy, float* dres,
+                    const unsigned* maskbits, double* sums, float* dy, float* dres,
                     int dres_accumulate, float* dgamma, float* dbeta, int param_accumulate, long long P, int C,
                     int relu, int round_tf32, void* stream);
 

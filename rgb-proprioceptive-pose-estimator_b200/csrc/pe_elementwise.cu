@@ -31,17 +31,37 @@ __device__ __forceinline__ float4 round4(float4 v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// ReLU / join masks as bits: float4 index i of a dense [P][C/4] tensor owns bit (i & 31) of the four words
+// maskbits[(i >> 5) * 4 + comp] (one word per float4 component), so a warp that handles 32 consecutive
+// float4s writes its mask with four ballots and reads it back with one broadcast 128-bit load.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_maskbits(const unsigned* __restrict__ bits, long long i4) {
+    return __ldg(reinterpret_cast<const uint4*>(bits) + (i4 >> 5));
+}
+__device__ __forceinline__ float4 apply_maskbits(float4 d, uint4 w, long long i4) {
+    const int sh = (int)(i4 & 31);
+    d.x = ((w.x >> sh) & 1u) ? d.x : 0.f;
+    d.y = ((w.y >> sh) & 1u) ? d.y : 0.f;
+    d.z = ((w.z >> sh) & 1u) ? d.z : 0.f;
+    d.w = ((w.w >> sh) & 1u) ? d.w : 0.f;
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-channel reductions over [P][C]:  acc0 += f0(row, c), acc1 += f1(row, c)
 // block = 256 threads = TR row lanes x GW channel groups (4 channels each); grid.y covers C > 1024.
+// Rows are consumed four at a time so every thread keeps 8-16 independent 128-bit loads in flight.
 // ---------------------------------------------------------------------------------------------
-template <int KIND>  // 0: (y, y*y)   1: (g, g*xhat) with g = dout * (out > 0 if relu)
+template <int KIND>  // 0: (y, y*y)   1: (g, g*xhat) with g = (dout [+ dout2]) * mask
 __global__ void __launch_bounds__(EW_THREADS)
 channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ a2, const float* __restrict__ b,
                       const float* __restrict__ c, const float* __restrict__ mean,
                       const float* __restrict__ invstd, const float* __restrict__ msc,
-                      const float* __restrict__ msh, double* __restrict__ sums, long long P, int C, int relu) {
+                      const float* __restrict__ msh, const unsigned* __restrict__ maskbits,
+                      double* __restrict__ sums, long long P, int C, int relu) {
     __shared__ float sm0[EW_THREADS * 4];
     __shared__ float sm1[EW_THREADS * 4];
+    constexpr int U = 4;
     const int G = C >> 2;
     const int GW = G < EW_THREADS ? G : EW_THREADS;
     const int TR = EW_THREADS / GW;
@@ -62,37 +82,60 @@ channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ a2,
             ksh = ld4(msh + 4 * g);
         }
     }
-    for (long long row = row0 + r; row < row1; row += TR) {
-        const long long off = row * C + 4 * g;
-        if (KIND == 0) {
-            const float4 y = ld4_stream(a + off);
-            s0.x += y.x; s0.y += y.y; s0.z += y.z; s0.w += y.w;
-            s1.x += y.x * y.x; s1.y += y.y * y.y; s1.z += y.z * y.z; s1.w += y.w * y.w;
-        } else {
-            float4 d = ld4_stream(a + off);
-            if (a2) {
-                const float4 e = ld4_stream(a2 + off);
-                d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
-            }
-            const float4 y = ld4_stream(c + off);
-            if (relu) {
-                float4 o;
-                if (b) {
-                    o = ld4_stream(b + off);
+    const bool relu_from_out = KIND == 1 && relu && b != nullptr;
+    const bool relu_from_y = KIND == 1 && relu && b == nullptr;
+    for (long long row = row0 + r; row < row1; row += (long long)U * TR) {
+        float4 d[U], e[U], y[U], o[U];
+        uint4 mb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = row + (long long)u * TR;
+            if (rr < row1) {
+                const long long off = rr * C + 4 * g;
+                if (KIND == 0) {
+                    y[u] = ld4_stream(a + off);
                 } else {
-                    o.x = fmaf(y.x, ksc.x, ksh.x); o.y = fmaf(y.y, ksc.y, ksh.y);
-                    o.z = fmaf(y.z, ksc.z, ksh.z); o.w = fmaf(y.w, ksc.w, ksh.w);
+                    d[u] = ld4_stream(a + off);
+                    if (a2) e[u] = ld4_stream(a2 + off);
+                    y[u] = ld4_stream(c + off);
+                    if (relu_from_out) o[u] = ld4_stream(b + off);
+                    if (maskbits) mb[u] = ld_maskbits(maskbits, rr * G + g);
                 }
-                d.x = o.x > 0.f ? d.x : 0.f;
-                d.y = o.y > 0.f ? d.y : 0.f;
-                d.z = o.z > 0.f ? d.z : 0.f;
-                d.w = o.w > 0.f ? d.w : 0.f;
             }
-            s0.x += d.x; s0.y += d.y; s0.z += d.z; s0.w += d.w;
-            s1.x += d.x * (y.x - mu.x) * is.x;
-            s1.y += d.y * (y.y - mu.y) * is.y;
-            s1.z += d.z * (y.z - mu.z) * is.z;
-            s1.w += d.w * (y.w - mu.w) * is.w;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long rr = row + (long long)u * TR;
+            if (rr < row1) {
+                if (KIND == 0) {
+                    const float4 v = y[u];
+                    s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+                    s1.x += v.x * v.x; s1.y += v.y * v.y; s1.z += v.z * v.z; s1.w += v.w * v.w;
+                } else {
+                    float4 dd = d[u];
+                    const float4 yy = y[u];
+                    if (a2) { dd.x += e[u].x; dd.y += e[u].y; dd.z += e[u].z; dd.w += e[u].w; }
+                    if (maskbits) dd = apply_maskbits(dd, mb[u], rr * G + g);
+                    if (relu_from_out || relu_from_y) {
+                        float4 oo;
+                        if (relu_from_out) {
+                            oo = o[u];
+                        } else {
+                            oo.x = fmaf(yy.x, ksc.x, ksh.x); oo.y = fmaf(yy.y, ksc.y, ksh.y);
+                            oo.z = fmaf(yy.z, ksc.z, ksh.z); oo.w = fmaf(yy.w, ksc.w, ksh.w);
+                        }
+                        dd.x = oo.x > 0.f ? dd.x : 0.f;
+                        dd.y = oo.y > 0.f ? dd.y : 0.f;
+                        dd.z = oo.z > 0.f ? dd.z : 0.f;
+                        dd.w = oo.w > 0.f ? dd.w : 0.f;
+                    }
+                    s0.x += dd.x; s0.y += dd.y; s0.z += dd.z; s0.w += dd.w;
+                    s1.x += dd.x * (yy.x - mu.x) * is.x;
+                    s1.y += dd.y * (yy.y - mu.y) * is.y;
+                    s1.z += dd.z * (yy.z - mu.z) * is.z;
+                    s1.w += dd.w * (yy.w - mu.w) * is.w;
+                }
+            }
         }
     }
     st4(sm0 + 4 * threadIdx.x, s0);
@@ -181,6 +224,84 @@ bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, co
     }
 }
 
+// Training-mode BatchNorm forward in one pass over the activations: every block rebuilds the per-channel
+// scale / shift from the fp64 batch sums (cheap: C <= 2048 channels), block 0 also publishes scale / shift /
+// mean / invstd for the backward pass, updates the running statistics and bumps num_batches_tracked.
+// Optionally emits the (out > 0) mask as bits for the residual joins (see ld_maskbits).
+__global__ void __launch_bounds__(EW_THREADS)
+bn_train_apply_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                      long long* __restrict__ num_batches_tracked, float* __restrict__ scale_out,
+                      float* __restrict__ shift_out, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                      const float* __restrict__ residual, float* __restrict__ out, unsigned* __restrict__ maskbits,
+                      long long P, int C, float momentum, float eps, int relu, int round_out) {
+    extern __shared__ float coef[];  // [2][C]
+    float* csc = coef;
+    float* csh = coef + C;
+    const double count = (double)P;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double m = stats[c] / count;
+        double var = stats[C + c] / count - m * m;
+        if (var < 0.0) var = 0.0;
+        const float mean = (float)m;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = gamma[c] * invstd;
+        const float sh = beta[c] - mean * sc;
+        csc[c] = sc;
+        csh[c] = sh;
+        if (blockIdx.x == 0) {
+            scale_out[c] = sc;
+            shift_out[c] = sh;
+            mean_out[c] = mean;
+            invstd_out[c] = invstd;
+            if (running_mean) {
+                const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+            if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+        }
+    }
+    __syncthreads();
+    const int G = C >> 2;
+    const long long n4 = P * G;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    // warp-uniform loop (the ballots below need every lane)
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n4; i0 += stride) {
+        const long long i = i0 + lane;
+        const bool valid = i < n4;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            const int g = (int)(i % G);
+            const float4 v = ld4_stream(y + 4 * i);
+            const float4 sc = ld4(csc + 4 * g);
+            const float4 sh = ld4(csh + 4 * g);
+            o.x = fmaf(v.x, sc.x, sh.x);
+            o.y = fmaf(v.y, sc.y, sh.y);
+            o.z = fmaf(v.z, sc.z, sh.z);
+            o.w = fmaf(v.w, sc.w, sh.w);
+            if (residual) {
+                const float4 r = ld4_stream(residual + 4 * i);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            if (relu) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            if (round_out) o = round4(o);
+            st4(out + 4 * i, o);
+        }
+        if (maskbits) {
+            const unsigned bx = __ballot_sync(0xffffffffu, o.x > 0.f);
+            const unsigned by = __ballot_sync(0xffffffffu, o.y > 0.f);
+            const unsigned bz = __ballot_sync(0xffffffffu, o.z > 0.f);
+            const unsigned bw = __ballot_sync(0xffffffffu, o.w > 0.f);
+            if (lane == 0) *(reinterpret_cast<uint4*>(maskbits) + (i0 >> 5)) = make_uint4(bx, by, bz, bw);
+        }
+    }
+}
+
 // dy = a*g + b*y + c per channel, a = gamma*invstd, b = -a*k2*invstd, c = -a*k1 + a*k2*invstd*mean,
 // k1 = sum_g/P, k2 = sum_gxhat/P.  Coefficients are rebuilt per block into shared memory.
 __global__ void __launch_bounds__(EW_THREADS)
@@ -188,7 +309,8 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ do
                     const float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ msc, const float* __restrict__ msh,
-                    const double* __restrict__ sums, float* __restrict__ dy, float* __restrict__ dres,
+                    const unsigned* __restrict__ maskbits, const double* __restrict__ sums,
+                    float* __restrict__ dy, float* __restrict__ dres,
                     int dres_acc, float* __restrict__ dgamma, float* __restrict__ dbeta, int param_acc,
                     long long P, int C, int relu, int round_out) {
     extern __shared__ float coef[];  // [3][C]
@@ -221,6 +343,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ do
             d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
         }
         const float4 yv = ld4_stream(y + 4 * i);
+        if (maskbits) d = apply_maskbits(d, ld_maskbits(maskbits, i), i);
         if (relu) {
             float4 o;
             if (out) {
@@ -290,35 +413,43 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ tck, float* __rest
     }
 }
 
-__global__ void im2col_stem_kernel(const float* __restrict__ img, float* __restrict__ col, int B, int C, int H,
-                                   int W, int R, int S, int stride, int pad, int Ho, int Wo, int ldc,
-                                   int round_out) {
-    // threads of a block share one (c, r, s) decode per k; rows are walked with 32-bit arithmetic
+// One block per output row (b, ho): the R input rows of every channel it needs are staged (zero padded,
+// TF32-rounded) in shared memory, then written out as Wo im2col rows with 128-bit coalesced stores.
+// blockDim = (ldc/4, rows in flight); thread x owns the same four k columns for every row.
+__global__ void __launch_bounds__(EW_THREADS)
+im2col_stem_kernel(const float* __restrict__ img, float* __restrict__ col, int B, int C, int H, int W, int R, int S,
+                   int stride, int pad, int Ho, int Wo, int ldc, int round_out) {
+    extern __shared__ float rows_sm[];                // [C*R][SW]
+    const int SW = W + 2 * pad;
     const int K = C * R * S;
-    const int nrows = B * Ho * Wo;
-    const int rows_per_block = blockDim.x / 32;          // one warp per row, lanes over k
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (int row = blockIdx.x * rows_per_block + wrp; row < nrows; row += gridDim.x * rows_per_block) {
-        const int wo = row % Wo;
-        const int t = row / Wo;
-        const int ho = t % Ho;
-        const int b = t / Ho;
-        const float* src = img + (size_t)b * C * H * W;
-        float* dst = col + (size_t)row * ldc;
-        const int h0 = ho * stride - pad, w0 = wo * stride - pad;
-        for (int k = lane; k < ldc; k += 32) {
-            float v = 0.f;
-            if (k < K) {
-                const int s = k % S;
-                const int q = k / S;
-                const int r = q % R;
-                const int c = q / R;
-                const int h = h0 + r, w = w0 + s;
-                if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(src + ((size_t)c * H + h) * W + w);
-                if (round_out) v = round_tf32(v);
-            }
-            dst[k] = v;
-        }
+    const int b = blockIdx.x / Ho, ho = blockIdx.x % Ho;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const float* src = img + (size_t)b * C * H * W;
+    const int h0 = ho * stride - pad;
+    for (int i = tid; i < C * R * SW; i += nthr) {
+        const int x = i % SW, cr = i / SW;
+        const int r = cr % R, c = cr / R;
+        const int h = h0 + r, w = x - pad;
+        float v = 0.f;
+        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(src + ((size_t)c * H + h) * W + w);
+        rows_sm[i] = round_out ? round_tf32(v) : v;
+    }
+    int off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = 4 * threadIdx.x + j;
+        off[j] = k < K ? ((k / S) * SW + (k % S)) : -1;       // k = (c*R + r)*S + s
+    }
+    __syncthreads();
+    float* dst = col + ((size_t)blockIdx.x * Wo) * ldc + 4 * threadIdx.x;
+    for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
+        const int x0 = wo * stride;
+        float4 v;
+        v.x = off[0] >= 0 ? rows_sm[off[0] + x0] : 0.f;
+        v.y = off[1] >= 0 ? rows_sm[off[1] + x0] : 0.f;
+        v.z = off[2] >= 0 ? rows_sm[off[2] + x0] : 0.f;
+        v.w = off[3] >= 0 ? rows_sm[off[3] + x0] : 0.f;
+        st4(dst + (size_t)wo * ldc, v);
     }
 }
 
@@ -638,7 +769,7 @@ int pe_bn_stats(const float* y, long long P, int C, double* stats, void* stream)
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_stats: unsupported channel count %d", C);
     channel_reduce_kernel<0><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
+        y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -663,28 +794,50 @@ int pe_bn_apply(const float* y, const float* scale, const float* shift, const fl
     return 0;
 }
 
+int pe_bn_train_apply(const float* y, const double* stats, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, long long* num_batches_tracked, float* scale,
+                      float* shift, float* mean, float* invstd, const float* residual, float* out,
+                      unsigned* maskbits, long long P, int C, float momentum, float eps, int relu, int round_tf32,
+                      void* stream) {
+    PE_REQUIRE(C % 4 == 0 && C <= 8192, "bn_train_apply: unsupported channel count %d", C);
+    PE_REQUIRE(stats && scale && shift && mean && invstd, "bn_train_apply: stats / scale / shift / mean / invstd required");
+    PE_REQUIRE(!maskbits || (reinterpret_cast<uintptr_t>(maskbits) & 15) == 0,
+               "bn_train_apply: mask bits need a 16-byte aligned pointer");
+    const long long n4 = P * (C / 4);
+    bn_train_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+        y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd, residual,
+        out, maskbits, P, C, momentum, eps, relu, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
 int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
-                     const float* invstd, const float* mask_scale, const float* mask_shift, double* sums,
-                     long long P, int C, int relu, void* stream) {
+                     const float* invstd, const float* mask_scale, const float* mask_shift,
+                     const unsigned* maskbits, double* sums, long long P, int C, int relu, void* stream) {
+    PE_REQUIRE(!maskbits || (C % 32 == 0 && (reinterpret_cast<uintptr_t>(maskbits) & 15) == 0),
+               "bn_bwd_reduce: mask bits need C %% 32 == 0 and a 16-byte aligned pointer");
     PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_reduce: ReLU mask needs `out` or scale/shift");
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_bwd_reduce: unsupported channel count %d", C);
     channel_reduce_kernel<1><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dout, dout2, out, y, mean, invstd, mask_scale, mask_shift, sums, P, C, relu);
+        dout, dout2, out, y, mean, invstd, mask_scale, mask_shift, maskbits, sums, P, C, relu);
     PE_LAUNCH_CHECK();
     return 0;
 }
 
 int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, const float* y, const float* mean,
                     const float* invstd, const float* gamma, const float* mask_scale, const float* mask_shift,
-                    double* sums, float* dy, float* dres,
+                    const unsigned* maskbits, double* sums, float* dy, float* dres,
                     int dres_accumulate, float* dgamma, float* dbeta, int param_accumulate, long long P, int C,
                     int relu, int round_tf32, void* stream) {
+    PE_REQUIRE(!maskbits || (reinterpret_cast<uintptr_t>(maskbits) & 15) == 0,
+               "bn_bwd_apply: mask bits need a 16-byte aligned pointer");
     PE_REQUIRE(C % 4 == 0 && C <= 4096, "bn_bwd_apply: unsupported channel count %d", C);
     PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_apply: ReLU mask needs `out` or scale/shift");
     const long long n4 = P * (C / 4);
     bn_bwd_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
-        dout, dout2, out, y, mean, invstd, gamma, mask_scale, mask_shift, sums, dy, dres, dres_accumulate, dgamma,
+        dout, dout2, out, y, mean, invstd, gamma, mask_scale, mask_shift, maskbits, sums, dy, dres, dres_accumulate,
+        dgamma,
         dbeta, param_accumulate,
         P, C, relu, round_tf32);
     PE_LAUNCH_CHECK();
@@ -713,9 +866,18 @@ int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W
                    int ldc, int round_tf32, void* stream) {
     PE_REQUIRE(ldc >= C * R * S && ldc % 4 == 0, "im2col: ldc %d too small / unaligned", ldc);
     const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
-    const long long n = (long long)B * Ho * Wo;
-    im2col_stem_kernel<<<grid_for(n, (EW_THREADS / 32) * 4, 32), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        img_nchw, col, B, C, H, W, R, S, stride, pad, Ho, Wo, ldc, round_tf32);
+    const int bx = ldc / 4;
+    PE_REQUIRE(bx >= 1 && bx <= EW_THREADS, "im2col: ldc %d out of range", ldc);
+    const size_t smem = sizeof(float) * (size_t)C * R * (W + 2 * pad);
+    PE_REQUIRE(smem <= 160 * 1024, "im2col: %d x %d rows of %d floats do not fit in shared memory", C, R, W + 2 * pad);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        PE_CHECK_CUDA(cudaFuncSetAttribute(im2col_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 block(bx, EW_THREADS / bx);
+    im2col_stem_kernel<<<B * Ho, block, smem, (cudaStream_t)stream>>>(img_nchw, col, B, C, H, W, R, S, stride, pad, Ho,
+                                                                     Wo, ldc, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }

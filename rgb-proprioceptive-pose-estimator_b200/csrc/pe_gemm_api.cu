@@ -267,8 +267,13 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
 // `w_tkc` is the transposed pack [tap][Cin][Cout] so both operands stay K-major.
 // ---------------------------------------------------------------------------------------------
 static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin,
-                           int Cout, int R, int S, int stride, int pad, cudaStream_t stream) {
+                           int Cout, int R, int S, int stride, int pad, const float* residual,
+                           const unsigned* res_mask, cudaStream_t stream) {
     if (ensure_error_flag()) return 2;
+    PE_REQUIRE(!residual || (R == 1 && S == 1 && stride == 1 && pad == 0),
+               "conv_dgrad: the residual epilogue is implemented for 1x1 stride-1 convolutions only");
+    PE_REQUIRE(!res_mask || (residual && Cin % 32 == 0 && (reinterpret_cast<uintptr_t>(res_mask) & 15) == 0),
+               "conv_dgrad: residual mask needs a residual, Cin %% 32 == 0 and a 16-byte aligned mask");
     const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
     PE_REQUIRE(stride == 1 || stride == 2, "stride %d unsupported", stride);
     PE_REQUIRE(R * S <= TG_MAX_TAPS, "too many filter taps");
@@ -322,6 +327,9 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             if (make_nhwc_map(&maps.d, dx, B, H, W, Cin, ph, pw, stride, box)) return 1;
             p.n_total = Cin;
             p.store_mode = TG_STORE_TMA;
+            p.residual = residual;
+            p.res_mask = res_mask;
+            p.ld_res = Cin;
             pick_pipeline(p, p.n_taps * p.chunks);
             dim3 grid((Cin + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
             if (launch_tapgemm(maps, p, grid, stream)) return 2;
@@ -553,8 +561,10 @@ int pe_conv2d_fwd(const float* x, const float* w_tck, float* y, int B, int H, in
 }
 
 int pe_conv2d_dgrad(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin, int Cout,
-                    int R, int S, int stride, int pad, void* stream) {
-    return conv_dgrad_impl(dy, w_tkc, dx, B, H, W, Cin, Cout, R, S, stride, pad, (cudaStream_t)stream);
+                    int R, int S, int stride, int pad, const float* residual, const unsigned* res_maskbits,
+                    void* stream) {
+    return conv_dgrad_impl(dy, w_tkc, dx, B, H, W, Cin, Cout, R, S, stride, pad, residual, res_maskbits,
+                           (cudaStream_t)stream);
 }
 
 int pe_conv2d_wgrad(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin, int Cout,

@@ -329,14 +329,31 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     }
                 }
                 if (res_row && row_valid) {
+                    if (p.res_mask) {
+                        // masked residual (identity branch of a residual join in backward): the eight float4s of
+                        // this chunk sit in one 32-group of the bit mask (ld_res % 32 == 0, col0 % 32 == 0)
+                        const long long i4 = (row_lin * p.ld_res + col0) >> 2;
+                        const uint4 mb = __ldg(reinterpret_cast<const uint4*>(p.res_mask) + (i4 >> 5));
+                        const int sh = static_cast<int>(i4 & 31);
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (col0 + i < p.n_total) {
+                        for (int i = 0; i < 32; i += 4) {
                             const float4 r4 = *reinterpret_cast<const float4*>(res_row + col0 + i);
-                            v[i] += r4.x;
-                            v[i + 1] += r4.y;
-                            v[i + 2] += r4.z;
-                            v[i + 3] += r4.w;
+                            const int bit = sh + (i >> 2);
+                            v[i] += ((mb.x >> bit) & 1u) ? r4.x : 0.f;
+                            v[i + 1] += ((mb.y >> bit) & 1u) ? r4.y : 0.f;
+                            v[i + 2] += ((mb.z >> bit) & 1u) ? r4.z : 0.f;
+                            v[i + 3] += ((mb.w >> bit) & 1u) ? r4.w : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            if (col0 + i < p.n_total) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(res_row + col0 + i);
+                                v[i] += r4.x;
+                                v[i + 1] += r4.y;
+                                v[i + 2] += r4.z;
+                                v[i + 3] += r4.w;
+                            }
                         }
                     }
                 }

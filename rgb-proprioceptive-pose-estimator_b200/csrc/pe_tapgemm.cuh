@@ -56,6 +56,7 @@ struct TapParams {
     const float* scale;       // [n_total] or null  (v = acc*scale + shift)
     const float* shift;
     const float* residual;    // same indexing as a dense NHWC output, row stride ld_res
+    const unsigned* res_mask; // optional bit mask applied to `residual` (layout: pe_elementwise.cu ld_maskbits)
     int ld_res;
     int relu;
     int round_out;            // round result to tf32 (rna) so the consumer's truncation is exact

@@ -35,19 +35,31 @@ class Act:
 
 
 class GradSlots:
-    """Up to two gradient contributions per activation (residual joins are summed by the consumer)."""
+    """Pending gradient contributions per activation: (tensor, maskbits) pairs.  `maskbits` marks a lazy
+    ReLU-masked view (the identity branch of a residual join hands its consumer the un-masked join gradient
+    plus the join's bit mask instead of materialising the masked copy)."""
 
     def __init__(self):
         self.d = {}
 
-    def add(self, act, g):
-        self.d.setdefault(id(act), []).append(g)
+    def add(self, act, g, maskbits=None):
+        self.d.setdefault(id(act), []).append((g, maskbits))
+
+    def pending(self, act):
+        return len(self.d.get(id(act), ()))
 
     def pop(self, act):
         gs = self.d.pop(id(act), [])
         if len(gs) > 2:
             raise native.PeError("internal: more than two gradient branches for one activation")
-        return (gs + [None, None])[:2]
+        return gs
+
+    def pop_plain(self, act, n_max=2):
+        """Entries without masks, padded with None to n_max tensors."""
+        gs = self.pop(act)
+        if len(gs) > n_max or any(m is not None for _, m in gs):
+            raise native.PeError("internal: unexpected gradient branches (%d entries) for this consumer" % len(gs))
+        return ([g for g, _ in gs] + [None] * n_max)[:n_max]
 
 
 def _params_version(params):
@@ -181,17 +193,26 @@ class TrunkEngine:
         return y
 
     def _bn_train(self, y, i, relu, residual, tape, update_running=True):
+        """Training-mode BatchNorm (+residual, +ReLU) in one pass: statistics finalisation, running-stat update,
+        num_batches_tracked and the normalisation share a kernel; residual joins also emit their ReLU mask as
+        bits for the backward pass."""
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         _, bn = self.convs[i]
         sc, sh, mean, invstd, stats, _ = self._bn_views(i)
-        L.pe_bn_finalize(P(stats), P(bn.weight), P(bn.bias), P(bn.running_mean) if update_running else None,
-                         P(bn.running_var) if update_running else None, P(sc), P(sh), P(mean), P(invstd), y.P,
-                         bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps, y.C, st)
         out = Act(torch.empty_like(y.t), y.B, y.H, y.W, y.C)
-        L.pe_bn_apply(P(y.t), P(sc), P(sh), P(residual.t) if residual is not None else None, P(out.t), y.P, y.C,
-                      int(relu), self.round_tf32, st)
+        maskbits = None
+        if residual is not None and relu and tape is not None:
+            n4 = y.P * (y.C // 4)
+            maskbits = torch.empty((n4 + 31) // 32 * 4, device=y.t.device, dtype=torch.int32)
+        L.pe_bn_train_apply(P(y.t), P(stats), P(bn.weight), P(bn.bias),
+                            P(bn.running_mean) if update_running else None,
+                            P(bn.running_var) if update_running else None,
+                            P(bn.num_batches_tracked) if update_running else None, P(sc), P(sh), P(mean), P(invstd),
+                            P(residual.t) if residual is not None else None, P(out.t), P(maskbits), y.P, y.C,
+                            bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps, int(relu),
+                            self.round_tf32, st)
         if tape is not None:
-            tape.append(("bn", i, y, out, relu, residual))
+            tape.append(("bn", i, y, out, relu, residual, maskbits))
         return out
 
     def _conv_eval(self, x, i, relu, residual):
@@ -283,9 +304,6 @@ class TrunkEngine:
         L.pe_avgpool_fwd(P(x.t), P(pool), x.C, B, x.H * x.W, x.C, self.round_tf32, st)
         L.pe_linear_fwd(P(pool), x.C, P(self.fc_w), x.C, P(fc.bias), None, P(feat_out), ld_feat, B, fc.out_features,
                         x.C, 0, 0, self.round_tf32, None, st)
-        if training:
-            for _, bn in self.convs:
-                L.pe_add_i64(P(bn.num_batches_tracked), 1, 1, st)
         if tape is None:
             return None
         tape.append(("tail", x, pool))
@@ -328,29 +346,48 @@ class TrunkEngine:
                 if on_ready is not None:
                     on_ready([fc.weight, fc.bias])
             elif kind == "bn":
-                _, i, y, out, relu, residual = rec
+                _, i, y, out, relu, residual, maskbits = rec
                 _, bn = self.convs[i]
                 sc, sh, mean, invstd, _, sums = self._bn_views(i)
-                d1, d2 = slots.pop(out)
-                # without a residual input the ReLU mask is recomputed from y (one activation read less)
-                mask_src = out.t if (relu and residual is not None) else None
-                L.pe_bn_bwd_reduce(P(d1), P(d2), P(mask_src), P(y.t), P(mean), P(invstd), P(sc), P(sh), P(sums), y.P,
-                                   y.C, int(relu), st)
+                entries = slots.pop(out)
                 dy = torch.empty_like(y.t)
-                dres = torch.empty_like(y.t) if residual is not None else None
+                if residual is not None and maskbits is not None:
+                    # residual join: g = D * mask(out > 0) with the mask read as bits; the identity branch gets
+                    # (D, bits) instead of a materialised masked copy
+                    if len(entries) != 1 or entries[0][1] is not None:
+                        raise native.PeError("internal: a residual join expects one complete gradient")
+                    d1, d2, mb, mask_src, relu_k = entries[0][0], None, maskbits, None, 0
+                else:
+                    if len(entries) == 1 and entries[0][1] is not None:
+                        d1, d2, mb = entries[0][0], None, entries[0][1]     # gradient of a join, masked lazily
+                    else:
+                        if any(m is not None for _, m in entries):
+                            raise native.PeError("internal: masked gradient next to a second branch")
+                        d1, d2 = ([g for g, _ in entries] + [None, None])[:2]
+                        mb = None
+                    # without a residual input the ReLU mask is recomputed from y (one activation read less)
+                    mask_src = out.t if (relu and residual is not None) else None
+                    relu_k = int(relu)
+                L.pe_bn_bwd_reduce(P(d1), P(d2), P(mask_src), P(y.t), P(mean), P(invstd), P(sc), P(sh), P(mb),
+                                   P(sums), y.P, y.C, relu_k, st)
+                dres = None
+                if residual is not None and maskbits is None:
+                    dres = torch.empty_like(y.t)
                 L.pe_bn_bwd_apply(P(d1), P(d2), P(mask_src), P(y.t), P(mean), P(invstd), P(bn.weight), P(sc), P(sh),
-                                  P(sums), P(dy), P(dres), 0, P(grad_of(bn.weight)), P(grad_of(bn.bias)), 0, y.P, y.C,
-                                  int(relu), rt, st)
+                                  P(mb), P(sums), P(dy), P(dres), 0, P(grad_of(bn.weight)), P(grad_of(bn.bias)), 0,
+                                  y.P, y.C, relu_k, rt, st)
                 slots.add(y, dy)
                 if residual is not None:
-                    slots.add(residual, dres)
+                    if maskbits is not None:
+                        slots.add(residual, d1, maskbits)
+                    else:
+                        slots.add(residual, dres)
             elif kind == "conv":
                 _, i, x, y = rec
                 conv, _ = self.convs[i]
                 co, ci, r, s = conv.weight.shape
                 stride, pad = conv.stride[0], conv.padding[0]
-                dy, none = slots.pop(y)
-                assert none is None
+                dy, = slots.pop_plain(y, 1)
                 gw = grad_of(conv.weight)
                 if r == 1 and s == 1:
                     L.pe_conv2d_wgrad(P(x.t), P(dy), P(gw), x.B, x.H, x.W, ci, co, r, s, stride, pad, st)
@@ -359,13 +396,18 @@ class TrunkEngine:
                     L.pe_conv2d_wgrad(P(x.t), P(dy), P(tmp), x.B, x.H, x.W, ci, co, r, s, stride, pad, st)
                     L.pe_unpack_conv_wgrad(P(tmp), P(gw), co, ci, r, s, 0, st)
                 dx = torch.empty_like(x.t)
-                L.pe_conv2d_dgrad(P(dy), P(self.w_tkc[i]), P(dx), x.B, x.H, x.W, ci, co, r, s, stride, pad, st)
+                res = res_mask = None
+                if r == 1 and s == 1 and stride == 1 and slots.pending(x) == 1:
+                    # the other gradient branch of x (identity / downsample path) is added in the dgrad epilogue
+                    (res, res_mask), = slots.pop(x)
+                L.pe_conv2d_dgrad(P(dy), P(self.w_tkc[i]), P(dx), x.B, x.H, x.W, ci, co, r, s, stride, pad, P(res),
+                                  P(res_mask), st)
                 slots.add(x, dx)
                 if i in done_after_conv:
                     on_ready(done_after_conv[i])
             elif kind == "maxpool":
                 _, a1, x, argmax = rec
-                d1, d2 = slots.pop(x)
+                d1, d2 = slots.pop_plain(x, 2)
                 da1 = torch.empty_like(a1.t)
                 L.pe_maxpool3x3s2_bwd(P(d1), P(d2), P(argmax), P(da1), 0, a1.B, a1.H, a1.W, a1.C, st)
                 slots.add(a1, da1)
@@ -384,7 +426,7 @@ class TrunkEngine:
                 slots.add(a1, da1_aux)
             elif kind == "stem":
                 _, col, y0 = rec
-                dy, none = slots.pop(y0)
+                dy, = slots.pop_plain(y0, 1)
                 conv1 = self.net.conv1
                 co, ci, r, s = conv1.weight.shape
                 k = ci * r * s

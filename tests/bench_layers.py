@@ -57,7 +57,7 @@ def main():
             else:
                 L.pe_debug_flags(f)
             t1 = timeit(lambda: L.pe_conv2d_fwd(P(x), P(tck), P(y), B, H, H, ci, co, k, k, st, pad, None, None, None, 0, 0, P(stats), S()))
-            t2 = timeit(lambda: L.pe_conv2d_dgrad(P(y), P(tkc), P(dx), B, H, H, ci, co, k, k, st, pad, S()))
+            t2 = timeit(lambda: L.pe_conv2d_dgrad(P(y), P(tkc), P(dx), B, H, H, ci, co, k, k, st, pad, None, None, S()))
             t3 = timeit(lambda: L.pe_conv2d_wgrad(P(x), P(y), P(dw), B, H, H, ci, co, k, k, st, pad, S()))
             cols.append("%6.0f %6.0f %6.0f" % (t1, t2, t3))
             for i, t in enumerate((t1, t2, t3)):

@@ -103,6 +103,20 @@ def pack(w, L=None):
     return tck, tkc
 
 
+def pack_maskbits(keep):
+    """Reference packing of a boolean tensor into the kernels' bit layout: float4 index i -> bit (i & 31) of
+    words [(i >> 5) * 4 + component]."""
+    flat = keep.reshape(-1).to(torch.int64)
+    n4 = flat.numel() // 4
+    n32 = (n4 + 31) // 32
+    padded = torch.zeros(n32 * 32 * 4, device=keep.device, dtype=torch.int64)
+    padded[:flat.numel()] = flat
+    v = padded.reshape(n32, 32, 4)                                   # [group][float4 in group][component]
+    w = (v << torch.arange(32, device=keep.device).reshape(1, 32, 1)).sum(1)     # [group][component]
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
+    return w.reshape(-1).to(torch.int32).contiguous()
+
+
 def check_conv(B, H, W, Cin, Cout, k, stride):
     L = native.lib()
     pad = (k - 1) // 2
@@ -135,8 +149,17 @@ def check_conv(B, H, W, Cin, Cout, k, stride):
 
     dy_n = nhwc(dy)
     dx = torch.full((B, H, W, Cin), float("nan"), device=DEV)
-    L.pe_conv2d_dgrad(P(dy_n), P(tkc), P(dx), B, H, W, Cin, Cout, k, k, stride, pad, S())
+    L.pe_conv2d_dgrad(P(dy_n), P(tkc), P(dx), B, H, W, Cin, Cout, k, k, stride, pad, None, None, S())
     out.append(("conv_dgrad " + tag, relerr(dx, nhwc(gx)), 1e-4))
+    if k == 1 and stride == 1 and Cin % 32 == 0:
+        # residual epilogue: dx = dgrad + res (plain) and dgrad + res * mask (bit mask of a residual join)
+        res = torch.randn(B, H, W, Cin, device=DEV, generator=g)
+        L.pe_conv2d_dgrad(P(dy_n), P(tkc), P(dx), B, H, W, Cin, Cout, k, k, stride, pad, P(res), None, S())
+        out.append(("conv_dgrad +res " + tag, relerr(dx, nhwc(gx) + res.double()), 1e-4))
+        keep = torch.rand(B, H, W, Cin, device=DEV, generator=g) > 0.5
+        bits = pack_maskbits(keep)
+        L.pe_conv2d_dgrad(P(dy_n), P(tkc), P(dx), B, H, W, Cin, Cout, k, k, stride, pad, P(res), P(bits), S())
+        out.append(("conv_dgrad +masked res " + tag, relerr(dx, nhwc(gx) + res.double() * keep), 1e-4))
 
     dw = torch.full((k * k, Cout, Cin), float("nan"), device=DEV)
     L.pe_conv2d_wgrad(P(x_n), P(dy_n), P(dw), B, H, W, Cin, Cout, k, k, stride, pad, S())
@@ -232,20 +255,47 @@ def check_bn(Pn, C, relu=True, residual=True):
     dout_b = dout - dout_a
     use_mask = relu and not residual
     o_arg = None if use_mask else o
-    L.pe_bn_bwd_reduce(P(dout_a), P(dout_b), P(o_arg), P(y), P(mean), P(invstd), P(scale), P(shift), P(sums), Pn, C,
-                       int(relu), S())
+    L.pe_bn_bwd_reduce(P(dout_a), P(dout_b), P(o_arg), P(y), P(mean), P(invstd), P(scale), P(shift), None, P(sums),
+                       Pn, C, int(relu), S())
     dy = torch.empty(Pn, C, device=DEV)
     dres = torch.empty(Pn, C, device=DEV) if residual else None
     dgamma = torch.empty(C, device=DEV)
     dbeta = torch.empty(C, device=DEV)
-    L.pe_bn_bwd_apply(P(dout_a), P(dout_b), P(o_arg), P(y), P(mean), P(invstd), P(gamma), P(scale), P(shift), P(sums),
-                      P(dy), P(dres), 0,
+    L.pe_bn_bwd_apply(P(dout_a), P(dout_b), P(o_arg), P(y), P(mean), P(invstd), P(gamma), P(scale), P(shift), None,
+                      P(sums), P(dy), P(dres), 0,
                       P(dgamma), P(dbeta), 0, Pn, C, int(relu), 0, S())
     out.append(("bn_bwd dy " + tag, relerr(dy, grads[0]), 1e-4))
     out.append(("bn_bwd dgamma " + tag, relerr(dgamma, grads[1]), 1e-4))
     out.append(("bn_bwd dbeta " + tag, relerr(dbeta, grads[2]), 1e-4))
     if residual:
         out.append(("bn_bwd dres " + tag, relerr(dres, grads[3]), 1e-6))
+    # ---- fused train-mode forward (statistics finalise + running stats + counter + apply + mask bits) ----
+    rm2 = torch.zeros(C, device=DEV)
+    rv2 = torch.ones(C, device=DEV)
+    nbt = torch.full((1,), 7, device=DEV, dtype=torch.int64)
+    sc2, sh2, mean2, invstd2 = (torch.full((C,), float("nan"), device=DEV) for _ in range(4))
+    o2 = torch.full((Pn, C), float("nan"), device=DEV)
+    n4 = Pn * (C // 4)
+    bits = torch.zeros((n4 + 31) // 32 * 4, device=DEV, dtype=torch.int32)
+    L.pe_bn_train_apply(P(y), P(stats), P(gamma), P(beta), P(rm2), P(rv2), P(nbt), P(sc2), P(sh2), P(mean2),
+                        P(invstd2), P(res), P(o2), P(bits), Pn, C, 0.1, 1e-5, int(relu), 0, S())
+    out.append(("bn_train_apply out " + tag, relerr(o2, o), 0.0))
+    out.append(("bn_train_apply scale/shift/mean/invstd " + tag,
+                max(relerr(sc2, scale), relerr(sh2, shift), relerr(mean2, mean), relerr(invstd2, invstd)), 0.0))
+    out.append(("bn_train_apply running stats " + tag, max(relerr(rm2, rm), relerr(rv2, rv)), 0.0))
+    out.append(("bn_train_apply counter " + tag, float(abs(int(nbt.item()) - 8)), 0.0))
+    ref_bits = pack_maskbits(o2 > 0)
+    out.append(("bn_train_apply mask bits " + tag, float((bits != ref_bits).sum()), 0.0))
+    if C % 32 == 0 and relu:
+        # backward with the mask taken from the bits (relu flag off, `out` not read): same result as above
+        sums2 = torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+        L.pe_bn_bwd_reduce(P(dout), None, None, P(y), P(mean), P(invstd), P(scale), P(shift), P(bits), P(sums2), Pn, C,
+                           0, S())
+        dy2 = torch.empty(Pn, C, device=DEV)
+        L.pe_bn_bwd_apply(P(dout), None, None, P(y), P(mean), P(invstd), P(gamma), P(scale), P(shift), P(bits),
+                          P(sums2), P(dy2), None, 0, P(dgamma), P(dbeta), 0, Pn, C, 0, 0, S())
+        out.append(("bn_bwd (mask bits) dy " + tag, relerr(dy2, grads[0]), 1e-4))
+        out.append(("bn_bwd (mask bits) dgamma " + tag, relerr(dgamma, grads[1]), 1e-4))
     # eval-mode finalize
     L.pe_bn_finalize(None, P(gamma), P(beta), P(rm), P(rv), P(scale), P(shift), None, None, Pn, 0.1, 1e-5, C, S())
     sc_ref = gamma.double() / torch.sqrt(rv.double() + 1e-5)

@@ -27,7 +27,7 @@ if __name__ == "__main__":
             L.pe_conv2d_fwd(P(x), P(tck), P(y), B, H, H, ci, co, k, k, st, pad, None, None, None, 0, 0,
                             P(stats) if use_stats else None, S())
         elif mode == "dgrad":
-            L.pe_conv2d_dgrad(P(y), P(tkc), P(dx), B, H, H, ci, co, k, k, st, pad, S())
+            L.pe_conv2d_dgrad(P(y), P(tkc), P(dx), B, H, H, ci, co, k, k, st, pad, None, None, S())
         else:
             L.pe_conv2d_wgrad(P(x), P(y), P(dw), B, H, H, ci, co, k, k, st, pad, S())
     torch.cuda.synchronize()
