@@ -33,6 +33,9 @@ void pe_debug_flags(int flags);
 void pe_debug_pipeline(int stages, int nout);
 /* debug: cap the tile width (128 or 256 columns) */
 void pe_debug_max_bn(int bn);
+/* debug: stride-1 multi-tap wgrad path: 0 one tap per work item, 1 haloed tile (default), 2 haloed tile with the
+ * descriptors' base-offset field set */
+void pe_debug_wgrad_halo(int mode);
 
 /* ---- convolutions: torchvision resnet.py:143-163,266-282 Conv2d calls reached from
  *      models/naive.py:316 and models/time_sensitive.py:185,472 (bias-free, NHWC here) ------------

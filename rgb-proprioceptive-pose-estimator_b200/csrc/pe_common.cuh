@@ -91,6 +91,47 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     return true;
 }
 
+// Warp-convergent variant: ALL 32 lanes call it and get the same (vote-derived, hence provably uniform)
+// answer, so the code that follows stays on the uniform datapath -- descriptors, coordinates and loop
+// counters live in uniform registers and the single-lane issue (elect.sync inside the *_elect wrappers
+// below) costs a handful of instructions instead of a vector->uniform waterfall per TMA / MMA.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, int spin = 0) {
+    if (spin) {
+        // non-blocking poll (latency-critical producer <-> MMA hand-offs)
+        if (__all_sync(0xffffffffu, mbar_test_wait(bar, parity))) return true;
+        const long long t0 = clock64();
+        for (;;) {
+            if (__all_sync(0xffffffffu, mbar_test_wait(bar, parity))) return true;
+            if (__any_sync(0xffffffffu, clock64() - t0 > (1ll << 28))) return false;
+        }
+    }
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
+    const long long t0 = clock64();
+    for (;;) {
+        if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
+        if (__any_sync(0xffffffffu, clock64() - t0 > (1ll << 28))) return false;
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+        ::"r"(bar), "r"(bytes)
+        : "memory");
+}
+
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -100,6 +141,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
         "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar,
+                                                  int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
         ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
         "r"(c3)
         : "memory");
@@ -151,6 +203,25 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar)
+        : "memory");
+}
+// Convergent-warp issue: every lane executes the block, one elected lane issues the MMA.
+__device__ __forceinline__ void tc_mma_tf32_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], TF32 operands, fp32 accumulate. Issued by ONE thread.
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,

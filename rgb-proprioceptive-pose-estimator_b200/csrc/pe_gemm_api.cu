@@ -341,10 +341,108 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
 // convolution wgrad: dw[t][co][ci] = sum_pixels dy[n,ho,wo,co] * x[n, ho*s + r - pad, wo*s + q - pad, ci]
 // Reduction over pixels is split across CTAs and combined with fp32 atomics into a zeroed dw.
 // ---------------------------------------------------------------------------------------------
+// Split-K factor for a persistent grid: base_items * ks work items should fill whole waves of SMs (an item count
+// just above a multiple of the SM count costs a full extra wave).  Prefers the fewest waves that reach 85 %
+// occupancy of the last wave, because every extra split adds a tile of atomic reductions.
+static int pick_ksplit(int base_items, int k_tiles, int max_waves) {
+    const int sms = num_sms();
+    int best_ks = 1;
+    double best_eff = 0.0;
+    for (int waves = 1; waves <= max_waves; ++waves) {
+        int ks = (waves * sms) / base_items;
+        if (ks < 1) ks = 1;
+        if (ks > k_tiles) ks = k_tiles;
+        // every split must own at least one k tile
+        while (ks > 1 && (long long)(ks - 1) * ((k_tiles + ks - 1) / ks) >= k_tiles) --ks;
+        const int items = base_items * ks;
+        const int w = (items + sms - 1) / sms;
+        const double eff = (double)items / ((double)w * sms);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best_ks = ks;
+        }
+        if (best_eff >= 0.85) break;
+    }
+    return best_ks;
+}
+
+static int g_dbg_wgrad_halo = 1;      // 0: one tap per work item (mode 1) everywhere; 2: halo + base-offset descriptors
+
+// Stride-1 multi-tap wgrad with a haloed X tile (tap-GEMM mode 2): the dY pixel tile and the X tile (+halo) are
+// fetched ONCE per tap group instead of once per tap; every tap accumulates into its own TMEM columns.
+static int conv_wgrad_halo_impl(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin,
+                                int Cout, int R, int S, int pad, cudaStream_t stream) {
+    const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
+    TapMaps maps;
+    TapParams p;
+    init_params(p);
+    p.mode = 2;
+    p.base_offset_mode = g_dbg_wgrad_halo == 2;
+    p.bn = Cin >= 128 ? 128 : ((Cin + 31) / 32) * 32;
+    p.m_rows = TG_BM;
+    p.box_w = 8;
+    p.box_h = (Ho % 8 == 0) ? 8 : ((Ho % 7 == 0) ? 7 : 8);
+    p.box_n = 1;
+    p.halo_w = p.box_w + S - 1;
+    p.halo_h = p.box_h + R - 1;
+    p.halo_dw = -pad;
+    p.halo_dh = -pad;
+    p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
+    p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
+    p.tiles_n = (B + p.box_n - 1) / p.box_n;
+    p.pt_total = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.out_w = Wo;
+    p.out_h = Ho;
+    p.out_n = B;
+    PE_REQUIRE(R * S <= TG_MAX_TAPS, "too many filter taps (%d)", R * S);
+    p.n_taps = R * S;
+    for (int r = 0; r < R; ++r)
+        for (int q = 0; q < S; ++q) {
+            p.tap_dh[r * S + q] = (signed char)r;      // row / column of the tap inside the halo tile
+            p.tap_dw[r * S + q] = (signed char)q;
+        }
+    int max_tg = 2 * TG_MAX_BN / p.bn;                       // accumulators that fit in 512 TMEM columns
+    if (max_tg > 8) max_tg = 8;                              // the issue loop is unrolled for <= 8 taps per group
+    p.n_groups = (p.n_taps + max_tg - 1) / max_tg;
+    p.tg_taps = (p.n_taps + p.n_groups - 1) / p.n_groups;
+    p.n_groups = (p.n_taps + p.tg_taps - 1) / p.tg_taps;
+    const int pt = p.box_w * p.box_h * p.box_n, hp = p.halo_w * p.halo_h * p.box_n;
+    p.a_atom_bytes = (pt * 128 + 1023) / 1024 * 1024;
+    p.b_atom_bytes = (hp * 128 + 1023) / 1024 * 1024;
+    const int na_max = Cout >= TG_BM ? 4 : (Cout + 31) / 32;
+    p.a_region_bytes = na_max * p.a_atom_bytes;
+    p.stage_bytes = p.a_region_bytes + (p.bn / 32) * p.b_atom_bytes;
+    p.stages = TG_SMEM_BYTES / p.stage_bytes;
+    if (p.stages > TG_STAGES) p.stages = TG_STAGES;
+    PE_REQUIRE(p.stages >= 2, "wgrad halo: stage of %d bytes does not fit twice", p.stage_bytes);
+    PE_REQUIRE(p.box_w == 8 && p.box_n == 1 && p.box_h <= 8 && p.tg_taps <= 8,
+               "wgrad halo: the issue loop is written for 8 x (<=8) x 1 pixel tiles and <= 8 taps per group");
+    p.nout = 2;
+    const int abox[4] = {32, p.box_w, p.box_h, p.box_n};
+    const int bbox[4] = {32, p.halo_w, p.halo_h, p.box_n};
+    if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, abox, true)) return 1;
+    if (make_nhwc_map(&maps.b[0], x, B, H, W, Cin, 0, 0, 1, bbox, true)) return 1;
+    p.m_total = Cout;
+    p.n_total = Cin;
+    p.out = dw_tck;
+    p.out_tap_stride = (long long)Cout * Cin;
+    p.ldo = Cin;
+    const int mt = (Cout + TG_BM - 1) / TG_BM, nt = (Cin + p.bn - 1) / p.bn;
+    const int ks = pick_ksplit(mt * nt * p.n_groups, p.pt_total, 2);
+    p.ksplit = ks;
+    p.store_mode = ks > 1 ? TG_STORE_ATOMIC : TG_STORE_DIRECT;
+    if (ks > 1)
+        PE_CHECK_CUDA(cudaMemsetAsync(dw_tck, 0, sizeof(float) * (size_t)R * S * Cout * Cin, stream));
+    dim3 grid(nt, mt, p.n_groups * ks);
+    return launch_tapgemm(maps, p, grid, stream);
+}
+
 static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin,
                            int Cout, int R, int S, int stride, int pad, cudaStream_t stream) {
     if (ensure_error_flag()) return 2;
     PE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "conv channels must be multiples of 4");
+    if (g_dbg_wgrad_halo && stride == 1 && R * S > 1 && Cin % 32 == 0 && Cout % 32 == 0)
+        return conv_wgrad_halo_impl(x, dy, dw_tck, B, H, W, Cin, Cout, R, S, pad, stream);
     const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
     TapMaps maps;
     TapParams p;
@@ -376,12 +474,7 @@ static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B
     p.out_tap_stride = (long long)Cout * Cin;
     p.ldo = Cin;
     const int mt = (Cout + TG_BM - 1) / TG_BM, nt = (Cin + p.bn - 1) / p.bn;
-    const int base_ctas = mt * nt * p.n_taps;
-    int ks = (2 * num_sms() + base_ctas - 1) / base_ctas;
-    if (ks > p.pt_total) ks = p.pt_total;
-    if (ks < 1) ks = 1;
-    // every split must own at least one pixel tile
-    while (ks > 1 && (long long)(ks - 1) * ((p.pt_total + ks - 1) / ks) >= p.pt_total) --ks;
+    const int ks = pick_ksplit(mt * nt * p.n_taps, p.pt_total, 3);
     p.ksplit = ks;
     p.store_mode = ks > 1 ? TG_STORE_ATOMIC : TG_STORE_DIRECT;
     if (ks > 1)
@@ -495,10 +588,7 @@ static int linear_wgrad_impl(const float* x, int ldx, const float* dy, int lddy,
     p.out_tap_stride = 0;
     p.ldo = lddw;
     const int mt = (N + TG_BM - 1) / TG_BM, nt = (K + p.bn - 1) / p.bn;
-    int ks = (2 * num_sms() + mt * nt - 1) / (mt * nt);
-    if (ks > p.pt_total) ks = p.pt_total;
-    if (ks < 1) ks = 1;
-    while (ks > 1 && (long long)(ks - 1) * ((p.pt_total + ks - 1) / ks) >= p.pt_total) --ks;
+    const int ks = pick_ksplit(mt * nt, p.pt_total, 3);
     p.ksplit = ks;
     p.store_mode = ks > 1 ? TG_STORE_ATOMIC : TG_STORE_DIRECT;
     if (ks > 1) PE_CHECK_CUDA(cudaMemset2DAsync(dw, sizeof(float) * lddw, 0, sizeof(float) * K, N, stream));
@@ -528,6 +618,8 @@ void pe_debug_pipeline(int stages, int nout) {
 }
 
 void pe_debug_max_bn(int bn) { g_dbg_max_bn = bn > 0 ? bn : 256; }
+
+void pe_debug_wgrad_halo(int mode) { g_dbg_wgrad_halo = mode; }
 
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
     g_dbg_desc[0] = a_lbo;

@@ -46,7 +46,7 @@ __device__ __forceinline__ Work decode_work(const TapParams& p, int w) {
         const int per = (ktotal + p.ksplit - 1) / p.ksplit;
         k.k_begin = k.z * per;
         k.nk = max(0, min(ktotal, k.k_begin + per) - k.k_begin);
-    } else {
+    } else if (p.mode == 1) {
         // taps vary fastest: CTAs running side by side reduce the same pixel range for different taps,
         // so the dY / X tiles they share are served from L2 instead of being re-read from HBM per tap
         k.tap = k.z % p.n_taps;
@@ -54,8 +54,39 @@ __device__ __forceinline__ Work decode_work(const TapParams& p, int w) {
         const int per = (p.pt_total + p.ksplit - 1) / p.ksplit;
         k.k_begin = split * per;
         k.nk = max(0, min(p.pt_total, k.k_begin + per) - k.k_begin);
+    } else {
+        // haloed wgrad: z = split * n_groups + tap group; `tap` is the first tap of the group
+        k.tap = (k.z % p.n_groups) * p.tg_taps;
+        const int split = k.z / p.n_groups;
+        const int per = (p.pt_total + p.ksplit - 1) / p.ksplit;
+        k.k_begin = split * per;
+        k.nk = max(0, min(p.pt_total, k.k_begin + per) - k.k_begin);
     }
     return k;
+}
+
+// One stage of the haloed wgrad: BH tile rows x NTG taps, one MMA each (K = 8 pixels of one tile row).  Rows outer,
+// taps inner: consecutive MMAs target different accumulators, and every descriptor is base + constant.
+// ntg / bh are the runtime bounds (equal to NTG / BH in the straight-line specialisations).
+template <int NTG, int BH>
+__device__ __forceinline__ void issue_halo_stage(uint32_t tmem_d, uint32_t bn, uint32_t a_hi, uint32_t a_lo,
+                                                 uint32_t b_hi, uint32_t b_lo, uint32_t row16,
+                                                 const uint32_t (&tap_off)[8], uint32_t idesc, uint32_t first,
+                                                 int ntg, int bh) {
+#pragma unroll
+    for (int hh = 0; hh < BH; ++hh) {
+        if (hh < bh) {
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + hh * 64u);
+            const uint32_t b_row = b_lo + hh * row16;
+#pragma unroll
+            for (int tl = 0; tl < NTG; ++tl) {
+                if (tl < ntg) {
+                    const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_row + tap_off[tl]);
+                    tc_mma_tf32_elect(tmem_d + tl * bn, ad, bd, idesc, (first | (hh > 0 ? 1u : 0u)));
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(TG_THREADS, 1)
@@ -69,7 +100,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     __shared__ __align__(16) float s_scale[TG_MAX_BN];
     __shared__ __align__(16) float s_shift[TG_MAX_BN];
 
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0: lets ptxas prove the role dispatch below is warp-uniform, which is what allows the
+    // producer / MMA warps to keep their addresses and descriptors on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
     // 1024-byte aligned tile storage (SWIZZLE_128B atoms are 1024 B)
@@ -104,117 +137,238 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+    const int spin = (p.dbg_flags & 128) ? 1 : 0;   // probe: non-blocking barrier polls in the producer / MMA warps
 
     if (warp == 0) {
         // =============================== TMA producer ========================================
-        if (lane == 0) {
-            uint32_t it = 0;
-            bool ok = true;
-            for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
-                const Work wk = decode_work(p, w);
-                const int n_off = wk.nt * p.bn;
-                if (p.mode == 0) {
-                    const TileOrigin o = tile_origin(p, wk.mt);
-                    const uint32_t bytes = static_cast<uint32_t>(p.m_rows + p.bn) * 128u;
-                    for (int j = 0; j < wk.nk; ++j, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (it / p.stages) & 1;
-                        if (!mbar_wait(smem_u32(&s_empty[s]), ph ^ 1)) {
-                            atomicOr(p.error_flag, 1);
-                            ok = false;
-                            break;
-                        }
-                        const int k = wk.k_begin + j;
-                        const int tap = k / p.chunks;
-                        const int ch = k - tap * p.chunks;
-                        const uint32_t full = smem_u32(&s_full[s]);
-                        const uint32_t sa = smem_base + s * p.stage_bytes;
-                        const uint32_t sb = sa + TG_A_BYTES;
-                        uint32_t nbytes = bytes;
-                        if (p.dbg_flags & 4) nbytes -= static_cast<uint32_t>(p.m_rows) * 128u;
-                        if (p.dbg_flags & 8) nbytes -= static_cast<uint32_t>(p.bn) * 128u;
-                        mbar_arrive_expect_tx(full, nbytes);
-                        if (!(p.dbg_flags & 4))
-                            tma_load_4d(sa, &maps.a[p.tap_map[tap]], full, ch * TG_BK, o.w0 + p.tap_dw[tap],
-                                        o.h0 + p.tap_dh[tap], o.n0);
-                        if (!(p.dbg_flags & 8)) tma_load_4d(sb, &maps.b[0], full, ch * TG_BK, n_off, p.tap_b[tap], 0);
+        // The whole warp runs this loop convergently; every barrier result is vote-derived, so coordinates,
+        // stage counters and addresses stay in uniform registers and one elected lane issues each TMA.
+        uint32_t s = 0, ph = 0;
+        bool ok = true;
+        for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
+            const Work wk = decode_work(p, w);
+            const int n_off = wk.nt * p.bn;
+            if (p.mode == 0) {
+                const TileOrigin o = tile_origin(p, wk.mt);
+                uint32_t nbytes = static_cast<uint32_t>(p.m_rows + p.bn) * 128u;
+                if (p.dbg_flags & 4) nbytes -= static_cast<uint32_t>(p.m_rows) * 128u;
+                if (p.dbg_flags & 8) nbytes -= static_cast<uint32_t>(p.bn) * 128u;
+                int tap = wk.k_begin / p.chunks;
+                int ch = wk.k_begin - tap * p.chunks;
+                for (int j = 0; j < wk.nk; ++j) {
+                    if (!mbar_wait_warp(smem_u32(&s_empty[s]), ph ^ 1, spin)) {
+                        atomicOr(p.error_flag, 1);
+                        ok = false;
+                        break;
                     }
-                } else {
-                    const int m_off = wk.mt * TG_BM;
-                    // only the 32-wide atoms that hold real channels are fetched; the MMA reads the rest of the
-                    // stage as don't-care rows / columns of the accumulator
-                    const int na = min(4, (p.m_total - m_off + 31) >> 5);
-                    const int nb = min((p.bn + 31) >> 5, (p.n_total - n_off + 31) >> 5);
-                    const uint32_t bytes = static_cast<uint32_t>(na + nb) * 4096u;
-                    const int dw = p.tap_dw[wk.tap], dh = p.tap_dh[wk.tap];
-                    const CUtensorMap* mb = &maps.b[p.tap_map[wk.tap]];
-                    for (int j = 0; j < wk.nk; ++j, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (it / p.stages) & 1;
-                        if (!mbar_wait(smem_u32(&s_empty[s]), ph ^ 1)) {
-                            atomicOr(p.error_flag, 2);
-                            ok = false;
-                            break;
-                        }
-                        const TileOrigin o = tile_origin(p, wk.k_begin + j);
-                        const uint32_t full = smem_u32(&s_full[s]);
-                        const uint32_t sa = smem_base + s * p.stage_bytes;
-                        const uint32_t sb = sa + TG_A_BYTES;
-                        mbar_arrive_expect_tx(full, bytes);
+                    const uint32_t full = smem_u32(&s_full[s]);
+                    const uint32_t sa = smem_base + s * p.stage_bytes;
+                    const uint32_t sb = sa + TG_A_BYTES;
+                    mbar_arrive_expect_tx_elect(full, nbytes);
+                    if (!(p.dbg_flags & 4))
+                        tma_load_4d_elect(sa, &maps.a[p.tap_map[tap]], full, ch * TG_BK, o.w0 + p.tap_dw[tap],
+                                          o.h0 + p.tap_dh[tap], o.n0);
+                    if (!(p.dbg_flags & 8))
+                        tma_load_4d_elect(sb, &maps.b[0], full, ch * TG_BK, n_off, p.tap_b[tap], 0);
+                    if (++ch == p.chunks) {
+                        ch = 0;
+                        ++tap;
+                    }
+                    if (++s == static_cast<uint32_t>(p.stages)) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            } else if (p.mode == 2) {
+                // haloed wgrad: one dY pixel tile + one X tile with an (R-1, S-1) halo per stage; every tap of
+                // the group reads its shifted window of the SAME X tile through its own UMMA descriptor
+                const int m_off = wk.mt * TG_BM;
+                const int na = min(4, (p.m_total - m_off + 31) >> 5);
+                const int nb = min((p.bn + 31) >> 5, (p.n_total - n_off + 31) >> 5);
+                const uint32_t a_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * 128u;
+                const uint32_t b_bytes = static_cast<uint32_t>(p.halo_w * p.halo_h * p.box_n) * 128u;
+                const uint32_t bytes = na * a_bytes + nb * b_bytes;
+                // running pixel-tile coordinates (w fastest)
+                int tw = wk.k_begin % p.tiles_w;
+                const int r0 = wk.k_begin / p.tiles_w;
+                int th = r0 % p.tiles_h;
+                int tn = r0 / p.tiles_h;
+                for (int j = 0; j < wk.nk; ++j) {
+                    if (!mbar_wait_warp(smem_u32(&s_empty[s]), ph ^ 1, spin)) {
+                        atomicOr(p.error_flag, 2);
+                        ok = false;
+                        break;
+                    }
+                    const int w0 = tw * p.box_w, h0 = th * p.box_h, n0 = tn * p.box_n;
+                    const uint32_t full = smem_u32(&s_full[s]);
+                    const uint32_t sa = smem_base + s * p.stage_bytes;
+                    const uint32_t sb = sa + p.a_region_bytes;
+                    uint32_t nbytes = bytes;
+                    if (p.dbg_flags & 4) nbytes -= na * a_bytes;
+                    if (p.dbg_flags & 8) nbytes -= nb * b_bytes;
+                    mbar_arrive_expect_tx_elect(full, nbytes);
+                    if (!(p.dbg_flags & 4))
                         for (int q = 0; q < na; ++q)
-                            tma_load_4d(sa + q * 4096, &maps.a[0], full, m_off + 32 * q, o.w0, o.h0, o.n0);
+                            tma_load_4d_elect(sa + q * p.a_atom_bytes, &maps.a[0], full, m_off + 32 * q, w0, h0, n0);
+                    if (!(p.dbg_flags & 8))
                         for (int q = 0; q < nb; ++q)
-                            tma_load_4d(sb + q * 4096, mb, full, n_off + 32 * q, o.w0 + dw, o.h0 + dh, o.n0);
+                            tma_load_4d_elect(sb + q * p.b_atom_bytes, &maps.b[0], full, n_off + 32 * q,
+                                              w0 + p.halo_dw, h0 + p.halo_dh, n0);
+                    if (++tw == p.tiles_w) {
+                        tw = 0;
+                        if (++th == p.tiles_h) {
+                            th = 0;
+                            ++tn;
+                        }
+                    }
+                    if (++s == static_cast<uint32_t>(p.stages)) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            } else {
+                const int m_off = wk.mt * TG_BM;
+                // only the 32-wide atoms that hold real channels are fetched; the MMA reads the rest of the
+                // stage as don't-care rows / columns of the accumulator
+                const int na = min(4, (p.m_total - m_off + 31) >> 5);
+                const int nb = min((p.bn + 31) >> 5, (p.n_total - n_off + 31) >> 5);
+                const uint32_t bytes = static_cast<uint32_t>(na + nb) * 4096u;
+                const int dw = p.tap_dw[wk.tap], dh = p.tap_dh[wk.tap];
+                const CUtensorMap* mb = &maps.b[p.tap_map[wk.tap]];
+                int tw = wk.k_begin % p.tiles_w;
+                const int r0 = wk.k_begin / p.tiles_w;
+                int th = r0 % p.tiles_h;
+                int tn = r0 / p.tiles_h;
+                for (int j = 0; j < wk.nk; ++j) {
+                    if (!mbar_wait_warp(smem_u32(&s_empty[s]), ph ^ 1, spin)) {
+                        atomicOr(p.error_flag, 2);
+                        ok = false;
+                        break;
+                    }
+                    const int w0 = tw * p.box_w, h0 = th * p.box_h, n0 = tn * p.box_n;
+                    const uint32_t full = smem_u32(&s_full[s]);
+                    const uint32_t sa = smem_base + s * p.stage_bytes;
+                    const uint32_t sb = sa + TG_A_BYTES;
+                    mbar_arrive_expect_tx_elect(full, bytes);
+                    for (int q = 0; q < na; ++q)
+                        tma_load_4d_elect(sa + q * 4096, &maps.a[0], full, m_off + 32 * q, w0, h0, n0);
+                    for (int q = 0; q < nb; ++q)
+                        tma_load_4d_elect(sb + q * 4096, mb, full, n_off + 32 * q, w0 + dw, h0 + dh, n0);
+                    if (++tw == p.tiles_w) {
+                        tw = 0;
+                        if (++th == p.tiles_h) {
+                            th = 0;
+                            ++tn;
+                        }
+                    }
+                    if (++s == static_cast<uint32_t>(p.stages)) {
+                        s = 0;
+                        ph ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ==========================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TG_BM, p.bn, p.mode, p.mode);
-            // K-major: LBO unused (16 B), SBO = 8 rows * 128 B.  MN-major: LBO = one 32-wide
-            // atom column (32 k-rows * 128 B), SBO = 4 k-rows * 128 B (128B_BASE32B atoms).
-            const uint32_t a_lbo = p.dbg_a_lbo >= 0 ? p.dbg_a_lbo : (p.mode ? 4096 : 16);
-            const uint32_t a_sbo = p.dbg_a_sbo >= 0 ? p.dbg_a_sbo : (p.mode ? 512 : 1024);
-            const uint32_t b_lbo = p.dbg_b_lbo >= 0 ? p.dbg_b_lbo : (p.mode ? 4096 : 16);
-            const uint32_t b_sbo = p.dbg_b_sbo >= 0 ? p.dbg_b_sbo : (p.mode ? 512 : 1024);
-            const uint32_t ltype = p.mode ? 1u : 2u;
-            const uint32_t kstep_bytes = p.mode ? 1024u : 32u;  // 8 tf32 along K
-            uint32_t it = 0, tile_i = 0;   // tile_i counts tiles that really use an accumulator
-            bool ok = true;
-            for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
-                const Work wk = decode_work(p, w);
-                if (wk.nk == 0) continue;
-                const uint32_t acc = tile_i & 1, aph = (tile_i >> 1) & 1;
-                ++tile_i;
-                if (!mbar_wait(smem_u32(&s_tmem_empty[acc]), aph ^ 1)) {
-                    atomicOr(p.error_flag, 16);
-                    break;
+        // Convergent warp, uniform descriptors, one elected lane per tcgen05.mma / tcgen05.commit.
+        const uint32_t idesc = make_idesc_tf32(TG_BM, p.bn, p.mode != 0, p.mode != 0);
+        // K-major: LBO unused (16 B), SBO = 8 rows * 128 B.  MN-major: LBO = one 32-wide
+        // atom column (32 k-rows * 128 B), SBO = 4 k-rows * 128 B (128B_BASE32B atoms).
+        const uint32_t a_lbo = p.dbg_a_lbo >= 0 ? p.dbg_a_lbo : (p.mode ? 4096 : 16);
+        const uint32_t a_sbo = p.dbg_a_sbo >= 0 ? p.dbg_a_sbo : (p.mode ? 512 : 1024);
+        const uint32_t b_lbo = p.dbg_b_lbo >= 0 ? p.dbg_b_lbo : (p.mode ? 4096 : 16);
+        const uint32_t b_sbo = p.dbg_b_sbo >= 0 ? p.dbg_b_sbo : (p.mode ? 512 : 1024);
+        const uint32_t ltype = p.mode ? 1u : 2u;
+        // descriptors are built once for smem address 0 and advanced by (bytes >> 4): the 14-bit address field
+        // cannot carry because shared memory ends below 256 KB
+        const uint64_t a_desc0 = p.mode == 2 ? make_smem_desc(0, p.a_atom_bytes, 512, 1u)
+                                             : make_smem_desc(0, a_lbo, a_sbo, ltype);
+        const uint64_t b_desc0 = p.mode == 2 ? make_smem_desc(0, p.b_atom_bytes, 512, 1u)
+                                             : make_smem_desc(0, b_lbo, b_sbo, ltype);
+        const uint32_t kstep16 = (p.mode ? 1024u : 32u) >> 4;  // 8 tf32 along K, in 16-byte units
+        uint32_t s = 0, ph = 0, tile_i = 0;   // tile_i counts tiles that really use an accumulator
+        bool ok = true;
+        for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
+            const Work wk = decode_work(p, w);
+            if (wk.nk == 0) continue;
+            // mode 2 owns all 512 TMEM columns as ONE set of per-tap accumulators
+            const uint32_t acc = p.mode == 2 ? 0u : (tile_i & 1);
+            const uint32_t aph = p.mode == 2 ? (tile_i & 1) : ((tile_i >> 1) & 1);
+            ++tile_i;
+            if (!mbar_wait_warp(smem_u32(&s_tmem_empty[acc]), aph ^ 1)) {
+                atomicOr(p.error_flag, 16);
+                break;
+            }
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * TG_MAX_BN;
+            if (p.mode == 2) {
+                const int ntg = min(p.tg_taps, p.n_taps - wk.tap);
+                // Issue loop kept free of loop-carried address arithmetic: every descriptor is base + table entry,
+                // rows outer / taps inner so consecutive MMAs hit different accumulators.  (box_w == 8, box_n == 1:
+                // one 8-pixel K segment per tile row.)
+                uint32_t tap_off[8];
+#pragma unroll
+                for (int tl = 0; tl < 8; ++tl) {
+                    const int tap = min(wk.tap + tl, p.n_taps - 1);
+                    tap_off[tl] = static_cast<uint32_t>(p.tap_dh[tap] * p.halo_w + p.tap_dw[tap]) * 8u;
                 }
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * TG_MAX_BN;
-                for (int j = 0; j < wk.nk; ++j, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1;
-                    if (!mbar_wait(smem_u32(&s_full[s]), ph)) {
+                const uint32_t row16 = static_cast<uint32_t>(p.halo_w) * 8u;      // one halo row, 16-byte units
+                const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
+                const uint32_t a_lo0 = static_cast<uint32_t>(a_desc0), b_lo0 = static_cast<uint32_t>(b_desc0);
+                for (int j = 0; j < wk.nk; ++j) {
+                    if (!mbar_wait_warp(smem_u32(&s_full[s]), ph, spin)) {
                         atomicOr(p.error_flag, 4);
                         ok = false;
                         break;
                     }
                     tc_fence_after();
                     const uint32_t sa = smem_base + s * p.stage_bytes;
-                    const uint32_t sb = sa + TG_A_BYTES;
-#pragma unroll
-                    for (int kk = 0; kk < TG_BK / 8; ++kk) {
-                        const uint64_t ad = make_smem_desc(sa + kk * kstep_bytes, a_lbo, a_sbo, ltype);
-                        const uint64_t bd = make_smem_desc(sb + kk * kstep_bytes, b_lbo, b_sbo, ltype);
-                        tc_mma_tf32(tmem_d, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                    const uint32_t a_lo = a_lo0 + (sa >> 4);
+                    const uint32_t b_lo = b_lo0 + ((sa + p.a_region_bytes) >> 4);
+                    if (!(p.dbg_flags & 16)) {
+                        const uint32_t first = j > 0 ? 1u : 0u;
+                        const int key = ntg * 16 + p.box_h;
+                        // straight-line specialisations for the shapes ResNet-50 produces (3x3: groups of 5 / 4 / 3
+                        // taps; 8- or 7-row tiles); anything else takes the predicated generic loop
+                        switch (key) {
+                            case 5 * 16 + 8: issue_halo_stage<5, 8>(tmem_d, p.bn, a_hi, a_lo, b_hi, b_lo, row16, tap_off, idesc, first, 5, 8); break;
+                            case 4 * 16 + 8: issue_halo_stage<4, 8>(tmem_d, p.bn, a_hi, a_lo, b_hi, b_lo, row16, tap_off, idesc, first, 4, 8); break;
+                            case 3 * 16 + 8: issue_halo_stage<3, 8>(tmem_d, p.bn, a_hi, a_lo, b_hi, b_lo, row16, tap_off, idesc, first, 3, 8); break;
+                            case 5 * 16 + 7: issue_halo_stage<5, 7>(tmem_d, p.bn, a_hi, a_lo, b_hi, b_lo, row16, tap_off, idesc, first, 5, 7); break;
+                            case 4 * 16 + 7: issue_halo_stage<4, 7>(tmem_d, p.bn, a_hi, a_lo, b_hi, b_lo, row16, tap_off, idesc, first, 4, 7); break;
+                            case 3 * 16 + 7: issue_halo_stage<3, 7>(tmem_d, p.bn, a_hi, a_lo, b_hi, b_lo, row16, tap_off, idesc, first, 3, 7); break;
+                            default: issue_halo_stage<8, 8>(tmem_d, p.bn, a_hi, a_lo, b_hi, b_lo, row16, tap_off, idesc, first, ntg, p.box_h); break;
+                        }
                     }
-                    tc_commit(smem_u32(&s_empty[s]));  // frees the stage when these MMAs retire
+                    tc_commit_elect(smem_u32(&s_empty[s]));
+                    if (++s == static_cast<uint32_t>(p.stages)) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
-                if (ok) tc_commit(smem_u32(&s_tmem_full[acc]));
+                if (ok) tc_commit_elect(smem_u32(&s_tmem_full[acc]));
+                continue;
             }
+            for (int j = 0; j < wk.nk; ++j) {
+                if (!mbar_wait_warp(smem_u32(&s_full[s]), ph, spin)) {
+                    atomicOr(p.error_flag, 4);
+                    ok = false;
+                    break;
+                }
+                tc_fence_after();
+                const uint32_t sa = smem_base + s * p.stage_bytes;
+                const uint64_t ad = a_desc0 + (sa >> 4);
+                const uint64_t bd = b_desc0 + ((sa + TG_A_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < TG_BK / 8; ++kk)
+                    tc_mma_tf32_elect(tmem_d, ad + kk * kstep16, bd + kk * kstep16, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                tc_commit_elect(smem_u32(&s_empty[s]));  // frees the stage when these MMAs retire
+                if (++s == static_cast<uint32_t>(p.stages)) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+            if (ok) tc_commit_elect(smem_u32(&s_tmem_full[acc]));
         }
         __syncwarp();
     } else {
@@ -240,7 +394,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
             const Work wk = decode_work(p, w);
             const int n_off = wk.nt * p.bn;
-            const uint32_t acc = tile_i & 1, aph = (tile_i >> 1) & 1;
+            const uint32_t acc = p.mode == 2 ? 0u : (tile_i & 1);
+            const uint32_t aph = p.mode == 2 ? (tile_i & 1) : ((tile_i >> 1) & 1);
             if (wk.nk > 0) ++tile_i;
 
             // per-tile column constants (everyone is past the previous tile's reads after this barrier)
@@ -295,7 +450,10 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                 out_row = p.out + (p.mode ? wk.tap * p.out_tap_stride : 0ll) + row_lin * p.ldo;
             const float* res_row = p.residual ? p.residual + row_lin * p.ld_res : nullptr;
 
-            const int nchunks = (p.bn + 31) >> 5;
+            // mode 2: the accumulators of the group's taps sit side by side, bn columns each
+            const int chunks_per_tap = (p.bn + 31) >> 5;
+            const int nchunks = p.mode == 2 ? chunks_per_tap * min(p.tg_taps, p.n_taps - wk.tap) : chunks_per_tap;
+            float* const out_row0 = out_row;
             int last_c = -1;                       // last chunk this group reads from TMEM
             for (int c = grp; c < nchunks; c += 2) last_c = c;
             if (last_c < 0 && wk.nk > 0) mbar_arrive(smem_u32(&s_tmem_empty[acc]));
@@ -311,7 +469,12 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.f;
                 }
-                const int col0 = n_off + c * 32;
+                int col0 = n_off + c * 32;
+                if (p.mode == 2) {
+                    const int tl = c / chunks_per_tap;
+                    col0 = n_off + (c - tl * chunks_per_tap) * 32;
+                    out_row = out_row0 + tl * p.out_tap_stride;
+                }
                 if (!row_valid) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -431,7 +594,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                             atomicAdd(&s_sq[colb + 3], sq.w);
                         }
                     }
-                } else if (row_valid) {
+                } else if (row_valid && !(p.dbg_flags & 64)) {
                     if (p.store_mode == TG_STORE_DIRECT) {
                         if (col0 + 32 <= p.n_total && (p.ldo & 3) == 0) {
 #pragma unroll

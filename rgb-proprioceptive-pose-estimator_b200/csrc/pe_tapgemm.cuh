@@ -36,7 +36,8 @@ struct alignas(64) TapMaps {
 };
 
 struct TapParams {
-    int mode;                 // 0 conv / gemm, 1 wgrad
+    int mode;                 // 0 conv / gemm, 1 wgrad (one tap per work item), 2 wgrad with a haloed X tile
+                              //   (several taps per work item, each tap in its own TMEM accumulator)
     int bn;                   // MMA N (multiple of 16; multiple of 32 in wgrad mode)
     int m_rows;               // rows the A box really fills (<= 128)
     int box_w, box_h, box_n;  // pixel box (conv: product = m_rows; wgrad: product = 32)
@@ -68,6 +69,13 @@ struct TapParams {
     int stage_bytes;          // 16 KB (A) + 16 or 32 KB (B)
     int stats_cols;           // columns of the CTA-wide statistics scratch (n_total rounded up to 32; 0 = none)
     int dbg_flags;            // 1: skip TMA store issue, 2: skip staging write + store, 4: skip A loads, 8: skip B loads
+    // mode 2 (haloed wgrad): pixel tile box_w x box_h x box_n (box_w % 8 == 0), halo tile halo_w x halo_h x box_n
+    int tg_taps, n_groups;    // taps per work item (tg_taps * bn <= 512 TMEM columns), number of tap groups
+    int halo_w, halo_h;       // box_w + S - 1, box_h + R - 1
+    int halo_dw, halo_dh;     // halo origin relative to the pixel tile origin (-pad)
+    int a_atom_bytes, b_atom_bytes;   // bytes between 32-channel atoms of the dY / X tiles in a stage
+    int a_region_bytes;       // offset of the B (X) region inside a stage
+    int base_offset_mode;     // debug: 1 = put (start >> 7) & 7 into the descriptors' base-offset field
 };
 
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream);

@@ -50,7 +50,9 @@ def main():
         flop = 2.0 * B * Ho * Ho * co * ci * k * k / TF32 * 1e6
         cols = []
         for f in flags:
-            if f == 1128:
+            if f == 2000:
+                L.pe_debug_wgrad_halo(0)
+            elif f == 1128:
                 L.pe_debug_max_bn(128)
             elif f >= 100:
                 L.pe_debug_pipeline(f // 100, f % 100)
@@ -65,6 +67,7 @@ def main():
             L.pe_debug_max_bn(256)
             L.pe_debug_pipeline(0, 0)
             L.pe_debug_flags(0)
+            L.pe_debug_wgrad_halo(1)
         L.pe_debug_flags(0)
         L.pe_debug_pipeline(0, 0)
         L.pe_debug_max_bn(256)

@@ -1,5 +1,5 @@
 """A few launches of one tap-GEMM configuration for `ncu --set full` (profiles/ recipes).
-usage: profile_conv.py B H Cin Cout k stride [mode: fwd|dgrad|wgrad] [stats 0|1]"""
+usage: profile_conv.py B H Cin Cout k stride [mode: fwd|dgrad|wgrad] [stats 0|1] [wgrad halo mode 0|1]"""
 import sys
 
 import torch
@@ -13,6 +13,8 @@ if __name__ == "__main__":
     mode = a[6] if len(a) > 6 else "fwd"
     use_stats = int(a[7]) if len(a) > 7 else 1
     L, P, S = native.lib(), kc.P, kc.S
+    if len(a) > 8:
+        L.pe_debug_wgrad_halo(int(a[8]))
     pad = (k - 1) // 2
     Ho = (H + 2 * pad - k) // st + 1
     x = torch.randn(B, H, H, ci, device="cuda")
