@@ -36,6 +36,8 @@ void pe_debug_max_bn(int bn);
 /* debug: stride-1 multi-tap wgrad path: 0 one tap per work item, 1 haloed tile (default), 2 haloed tile with the
  * descriptors' base-offset field set */
 void pe_debug_wgrad_halo(int mode);
+/* debug: 0 = epilogue reads residual rows with plain global loads instead of TMA-prefetched tiles */
+void pe_debug_residual_tma(int on);
 
 /* ---- convolutions: torchvision resnet.py:143-163,266-282 Conv2d calls reached from
  *      models/naive.py:316 and models/time_sensitive.py:185,472 (bias-free, NHWC here) ------------

@@ -157,6 +157,7 @@ static void init_params(TapParams& p) {
 }
 
 static int g_dbg_max_bn = 256;
+static int g_dbg_res_tma = 1;
 static int pick_bn(int n_total) {
     if (n_total >= 256 && g_dbg_max_bn >= 256) return 256;
     return n_total >= 128 ? 128 : ((n_total + 15) / 16) * 16;
@@ -167,9 +168,12 @@ static int pick_bn(int n_total) {
 static void pick_pipeline(TapParams& p, int ksteps) {
     p.stage_bytes = TG_A_BYTES + (p.bn > 128 ? 32768 : 16384);
     p.stats_cols = p.stats ? (p.n_total + 31) / 32 * 32 : 0;
-    const int budget = TG_SMEM_BYTES - 2 * p.stats_cols * (int)sizeof(float);
+    // residual tiles are prefetched by TMA (two 16 KB buffers per epilogue group) when the output goes out by TMA
+    p.nres = (p.residual && p.store_mode == TG_STORE_TMA && g_dbg_res_tma) ? 4 : 0;
+    const int budget = TG_SMEM_BYTES - (p.stats ? 2 * p.stats_cols * (int)sizeof(float) + 8192 : 0) - p.nres * TG_A_BYTES;
     // (two epilogue groups: the staging buffers are split evenly between them)
     int nout = (p.store_mode == TG_STORE_TMA) ? (ksteps >= 24 ? 2 : 4) : 0;
+    if (p.nres && p.bn > 128) nout = 2;
     if (g_dbg_nout > 0 && p.store_mode == TG_STORE_TMA) nout = g_dbg_nout;
     int stages = (budget - nout * TG_A_BYTES) / p.stage_bytes;
     if (stages > TG_STAGES) stages = TG_STAGES;
@@ -245,6 +249,7 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
         if (make_map(&maps.b[0], w_tck, dims, strides, bbox)) return 1;
     }
     if (make_nhwc_map(&maps.d, y, B, Ho, Wo, Cout, 0, 0, 1, box)) return 1;
+    if (ep.residual && make_nhwc_map(&maps.r, ep.residual, B, Ho, Wo, Cout, 0, 0, 1, box)) return 1;
     p.n_total = Cout;
     p.store_mode = TG_STORE_TMA;
     p.bias = ep.bias;
@@ -325,6 +330,7 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             const int bbox[4] = {TG_BK, p.bn, 1, 1};
             if (make_map(&maps.b[0], w_tkc, dims, strides, bbox)) return 1;
             if (make_nhwc_map(&maps.d, dx, B, H, W, Cin, ph, pw, stride, box)) return 1;
+            if (residual && make_nhwc_map(&maps.r, residual, B, H, W, Cin, ph, pw, stride, box)) return 1;
             p.n_total = Cin;
             p.store_mode = TG_STORE_TMA;
             p.residual = residual;
@@ -539,6 +545,7 @@ static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, flo
         const long long strides[3] = {ldy, (long long)ldy * M, (long long)ldy * M};
         const int box[4] = {32, TG_BM, 1, 1};
         if (make_map(&maps.d, y, dims, strides, box)) return 1;
+        if (p.residual && make_map(&maps.r, p.residual, dims, strides, box)) return 1;
         p.store_mode = TG_STORE_TMA;
     } else {
         PE_REQUIRE(!p.residual || (ldy % 4 == 0 && N % 4 == 0),
@@ -620,6 +627,8 @@ void pe_debug_pipeline(int stages, int nout) {
 void pe_debug_max_bn(int bn) { g_dbg_max_bn = bn > 0 ? bn : 256; }
 
 void pe_debug_wgrad_halo(int mode) { g_dbg_wgrad_halo = mode; }
+
+void pe_debug_residual_tma(int on) { g_dbg_res_tma = on; }
 
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
     g_dbg_desc[0] = a_lbo;

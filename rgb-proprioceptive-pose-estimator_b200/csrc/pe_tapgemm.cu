@@ -96,6 +96,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     __shared__ __align__(8) uint64_t s_empty[TG_STAGES];
     __shared__ __align__(8) uint64_t s_tmem_full[2];
     __shared__ __align__(8) uint64_t s_tmem_empty[2];
+    __shared__ __align__(8) uint64_t s_res_full[4];
     __shared__ uint32_t s_tmem_base;
     __shared__ __align__(16) float s_scale[TG_MAX_BN];
     __shared__ __align__(16) float s_shift[TG_MAX_BN];
@@ -109,8 +110,11 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     const uint32_t smem_base = smem_u32(smem_raw);
     const uint32_t stage_base = smem_base + p.stages * p.stage_bytes;   // nout x 16 KB epilogue staging
     // CTA-wide per-channel statistics (one global atomic per channel per CTA instead of per tile)
-    float* s_sum = reinterpret_cast<float*>(smem_raw + p.stages * p.stage_bytes + p.nout * TG_A_BYTES);
+    const uint32_t res_base = stage_base + p.nout * TG_A_BYTES;          // nres x 16 KB residual tiles
+    float* s_sum = reinterpret_cast<float*>(smem_raw + p.stages * p.stage_bytes + (p.nout + p.nres) * TG_A_BYTES);
     float* s_sq = s_sum + p.stats_cols;
+    // per-tile scratch of the statistics: [group 2][chunk 4][warp 4][sum 32 | sq 32] (8 KB, only with stats)
+    float* s_part = s_sum + 2 * p.stats_cols;
 
     // ---- one-time setup --------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -118,6 +122,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             mbar_init(smem_u32(&s_full[s]), 1);
             mbar_init(smem_u32(&s_empty[s]), 1);
         }
+        for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&s_res_full[a]), 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&s_tmem_full[a]), 1);
             mbar_init(smem_u32(&s_tmem_empty[a]), 256);
@@ -128,6 +133,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b[0]);
         if (p.store_mode == TG_STORE_TMA) tma_prefetch_desc(&maps.d);
+        if (p.nres) tma_prefetch_desc(&maps.r);
     }
     if (warp == 1) {
         tmem_alloc(smem_u32(&s_tmem_base), 2 * TG_MAX_BN);
@@ -387,6 +393,30 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         const bool affine = (p.scale != nullptr) || (p.bias != nullptr);
         uint32_t tile_i = 0, cc = 0;
         bool ok = true;
+        // ---- residual tiles by TMA: this group's chunk sequence is prefetched two chunks ahead into its two
+        //      16 KB buffers (swizzled like the staging tile, so each thread reads back its own row conflict-free)
+        const bool res_tma = p.nres > 0;
+        const int res_chunks = (p.bn + 31) >> 5;
+        const uint32_t my_res = res_base + grp * 2 * TG_A_BYTES;
+        uint32_t rq = 0;                      // residual chunks consumed by this group
+        int pw = blockIdx.x, pc = grp;        // next chunk to prefetch (work item, chunk)
+        auto res_issue = [&](uint32_t buf) {  // called by one thread
+            if (pw >= p.work_total || pc >= res_chunks) return;
+            const Work w2 = decode_work(p, pw);
+            const TileOrigin o2 = tile_origin(p, w2.mt);
+            const uint32_t bar = smem_u32(&s_res_full[grp * 2 + buf]);
+            mbar_arrive_expect_tx(bar, static_cast<uint32_t>(p.m_rows) * 128u);
+            tma_load_4d(my_res + buf * TG_A_BYTES, &maps.r, bar, w2.nt * p.bn + pc * 32, o2.w0, o2.h0, o2.n0);
+            pc += 2;
+            if (pc >= res_chunks) {
+                pc = grp;
+                pw += gridDim.x;
+            }
+        };
+        if (res_tma && et == 0) {
+            res_issue(0);
+            res_issue(1);
+        }
         if (p.stats) {
             for (int cidx = eall; cidx < 2 * p.stats_cols; cidx += 256) s_sum[cidx] = 0.f;
             asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -491,7 +521,37 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         v[i + 3] = fmaf(v[i + 3], sc4.w, sh4.w);
                     }
                 }
-                if (res_row && row_valid) {
+                if (res_tma) {
+                    const uint32_t buf = rq & 1;
+                    if (!mbar_wait(smem_u32(&s_res_full[grp * 2 + buf]), (rq >> 1) & 1)) {
+                        atomicOr(p.error_flag, 32);
+                        ok = false;
+                        break;
+                    }
+                    if (row_valid) {
+                        uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
+                        int sh = 0;
+                        if (p.res_mask) {
+                            // the eight float4s of this chunk sit in one 32-group of the bit mask
+                            const long long i4 = (row_lin * p.ld_res + col0) >> 2;
+                            mb = __ldg(reinterpret_cast<const uint4*>(p.res_mask) + (i4 >> 5));
+                            sh = static_cast<int>(i4 & 31);
+                        }
+                        const uint32_t rrow = my_res + buf * TG_A_BYTES + row * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 r4;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(r4.x), "=f"(r4.y), "=f"(r4.z), "=f"(r4.w)
+                                         : "r"(rrow + ((j ^ (row & 7)) << 4)));
+                            const int bit = sh + j;
+                            v[4 * j] += ((mb.x >> bit) & 1u) ? r4.x : 0.f;
+                            v[4 * j + 1] += ((mb.y >> bit) & 1u) ? r4.y : 0.f;
+                            v[4 * j + 2] += ((mb.z >> bit) & 1u) ? r4.z : 0.f;
+                            v[4 * j + 3] += ((mb.w >> bit) & 1u) ? r4.w : 0.f;
+                        }
+                    }
+                } else if (res_row && row_valid) {
                     if (p.res_mask) {
                         // masked residual (identity branch of a residual join in backward): the eight float4s of
                         // this chunk sit in one 32-group of the bit mask (ld_res % 32 == 0, col0 % 32 == 0)
@@ -537,6 +597,11 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    if (res_tma) {
+                        // every thread of the group has read residual buffer (rq & 1): refill it two chunks ahead
+                        if (et == 0) res_issue(rq & 1);
+                        ++rq;
+                    }
                     const uint32_t rbase = region + row * 128;
                     if (!(p.dbg_flags & 2)) {
 #pragma unroll
@@ -582,16 +647,12 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                             sq.z += __shfl_xor_sync(0xffffffffu, sq.z, off);
                             sq.w += __shfl_xor_sync(0xffffffffu, sq.w, off);
                         }
-                        const int colb = col0 + cg * 4;
-                        if (lane < 8 && colb < p.n_total) {
-                            atomicAdd(&s_sum[colb], sm.x);
-                            atomicAdd(&s_sum[colb + 1], sm.y);
-                            atomicAdd(&s_sum[colb + 2], sm.z);
-                            atomicAdd(&s_sum[colb + 3], sm.w);
-                            atomicAdd(&s_sq[colb], sq.x);
-                            atomicAdd(&s_sq[colb + 1], sq.y);
-                            atomicAdd(&s_sq[colb + 2], sq.z);
-                            atomicAdd(&s_sq[colb + 3], sq.w);
+                        // per-warp partials go to the tile scratch; they are folded once per tile (below) by threads
+                        // that own their columns exclusively -- no shared-memory atomics on the per-chunk path
+                        if (lane < 8) {
+                            float* dst = s_part + (((grp * 4 + (c >> 1)) * 4 + (ew & 3)) << 6) + cg * 4;
+                            *reinterpret_cast<float4*>(dst) = sm;
+                            *reinterpret_cast<float4*>(dst + 32) = sq;
                         }
                     }
                 } else if (row_valid && !(p.dbg_flags & 64)) {
@@ -617,6 +678,23 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
                             if (col0 + i < p.n_total) atomicAdd(out_row + col0 + i, v[i]);
+                    }
+                }
+            }
+            if (p.stats && p.store_mode == TG_STORE_TMA) {
+                // fold this tile's per-warp partials into the CTA-wide sums: (group, chunk, column) -> unique owner
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int idx = et + h * 128;
+                    const int ci = idx >> 6, k = idx & 63;
+                    const int c = 2 * ci + grp;
+                    const int col = n_off + c * 32 + (k & 31);
+                    if (c < nchunks && col < p.n_total) {
+                        const float* src = s_part + ((grp * 4 + ci) << 8) + k;
+                        const float t = (src[0] + src[64]) + (src[128] + src[192]);
+                        float* dst = (k < 32 ? s_sum : s_sq) + col;
+                        *dst += t;
                     }
                 }
             }

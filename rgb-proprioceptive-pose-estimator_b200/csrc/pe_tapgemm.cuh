@@ -23,7 +23,7 @@ constexpr int TG_MAX_BN = 256;                 // tile columns (TMEM columns per
 constexpr int TG_STAGES = 6;                    // maximum ring depth (runtime: TapParams::stages)
 constexpr int TG_A_BYTES = TG_BM * 128;        // 16 KB
 constexpr int TG_B_BYTES = TG_MAX_BN * 128;    // 32 KB (16 KB when bn <= 128: TapParams::stage_bytes)
-constexpr int TG_SMEM_BYTES = 216 * 1024;       // ring (stages x 32|48 KB) + store staging (nout x 16 KB)
+constexpr int TG_SMEM_BYTES = 223 * 1024;       // ring (stages x 32|48 KB) + store staging (nout x 16 KB)
 constexpr int TG_THREADS = 320;                // TMA warp + MMA warp + 2 epilogue groups of 4 warps
 constexpr int TG_MAX_TAPS = 16;
 
@@ -33,6 +33,7 @@ struct alignas(64) TapMaps {
     CUtensorMap a[4];
     CUtensorMap b[4];
     CUtensorMap d;
+    CUtensorMap r;            // residual tensor, same geometry as d (only when TapParams::nres > 0)
 };
 
 struct TapParams {
@@ -66,6 +67,7 @@ struct TapParams {
     // debug overrides for the smem descriptors (bytes, <0 = default)
     int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;
     int stages, nout;         // smem split: ring depth and number of 16 KB store-staging buffers
+    int nres;                 // 16 KB residual tiles prefetched by TMA for the epilogue (0 or 4: two per group)
     int stage_bytes;          // 16 KB (A) + 16 or 32 KB (B)
     int stats_cols;           // columns of the CTA-wide statistics scratch (n_total rounded up to 32; 0 = none)
     int dbg_flags;            // 1: skip TMA store issue, 2: skip staging write + store, 4: skip A loads, 8: skip B loads

@@ -61,7 +61,16 @@ def main():
             t1 = timeit(lambda: L.pe_conv2d_fwd(P(x), P(tck), P(y), B, H, H, ci, co, k, k, st, pad, None, None, None, 0, 0, P(stats), S()))
             t2 = timeit(lambda: L.pe_conv2d_dgrad(P(y), P(tkc), P(dx), B, H, H, ci, co, k, k, st, pad, None, None, S()))
             t3 = timeit(lambda: L.pe_conv2d_wgrad(P(x), P(y), P(dw), B, H, H, ci, co, k, k, st, pad, S()))
-            cols.append("%6.0f %6.0f %6.0f" % (t1, t2, t3))
+            extra = ""
+            if k == 1 and st == 1 and ci % 32 == 0:
+                # dgrad with the masked residual epilogue (identity branch of a residual join)
+                bits = torch.randint(-2 ** 31, 2 ** 31 - 1, ((x.numel() // 4 + 31) // 32 * 4,), device="cuda",
+                                     dtype=torch.int32)
+                res = torch.randn_like(x)
+                t4 = timeit(lambda: L.pe_conv2d_dgrad(P(y), P(tkc), P(dx), B, H, H, ci, co, k, k, st, pad, P(res),
+                                                      P(bits), S()))
+                extra = " (+res %4.0f)" % t4
+            cols.append("%6.0f %6.0f %6.0f%s" % (t1, t2, t3, extra))
             for i, t in enumerate((t1, t2, t3)):
                 tot[f][i] += t
             L.pe_debug_max_bn(256)
