@@ -150,6 +150,47 @@ int pe_lstm_cell_bwd(const float* dh, int lddh, const float* dh_rec, const float
                      const float* c_prev, const float* c_out, float* dgates, int lddg, float* dc_prev, int N,
                      int Hd, void* stream);
 
+/* ---- fused fusion-head step for rollout inference (<= 8 frames): replaces, in ONE launch, the torch.cat of
+ *      image / aux features with the proprioceptive vector, the first dense layer or LSTM gate projection, the
+ *      LSTM cell and the remaining small layers (models/naive.py:333-345, :92-104; models/time_sensitive.py:
+ *      213-246, :491-513).  Phase A runs on every SM (each warp streams rows of the first weight matrix once);
+ *      the last CTA to finish runs the tail.  Weights are read in their checkpoint (nn.Linear / nn.LSTM) layout. */
+typedef struct pe_head_desc {
+    /* phase A: out_a[n][j] = act(w_x[j][:] . x[n][:] + w_h[j][:] . h_prev[n][:] + b1[j] + b2[j]),  j < j_a */
+    const float* x;          /* [n_rows][ldx] fusion rows (latent | aux | 7 slots), first k_x columns are used */
+    int ldx, n_rows;
+    const float* inj;        /* optional [n_rows][ld_inj]: 7 values injected at columns inj_col.. (proprio vector) */
+    int ld_inj, inj_col;
+    int k_x;
+    const float* w_x;        /* [j_a][k_x] */
+    int k_h;                 /* 0 = no recurrent term */
+    const float* w_h;        /* [j_a][k_h] */
+    const float* h_prev;     /* [n_rows][k_h] or NULL (zero state) */
+    const float* b1;
+    const float* b2;         /* biases, either may be NULL */
+    int j_a, relu_a;
+    float* out_a;            /* [n_rows][j_a] scratch (gates / first-layer activations) */
+    unsigned int* counter;   /* zero-initialised ticket, reset by the kernel */
+    /* tail */
+    int lstm_hidden;         /* > 0: out_a holds LSTM gates (i,f,g,o) and the cell runs first */
+    const float* c_prev;     /* [n_rows][lstm_hidden] or NULL */
+    float* c_out;
+    float* h_out;            /* may alias c_prev / h_prev (in-place state update) */
+    int n_tail;              /* 0..3 further dense layers */
+    const float* tail_w[3];  /* [tail_j[t]][previous width] */
+    const float* tail_b[3];
+    int tail_j[3], tail_relu[3];
+    float* out;              /* [n_rows][ld_out] output of the last layer */
+    int ld_out;
+    const float* meas;       /* optional: diff[n][diff_col + j] = out[n][j] - meas[n][j] (pre_out - x0bar) */
+    int ld_meas;
+    float* diff;
+    int ld_diff, diff_col;
+} pe_head_desc;
+/* `desc` is a HOST pointer (copied into the launch); every pointer inside it is a device pointer */
+int pe_fused_head(const pe_head_desc* desc, void* stream);
+int pe_head_desc_size(void);   /* sizeof(pe_head_desc), for language bindings that mirror the struct */
+
 /* ---- pose loss (models/losses.py:47-128) ------------------------------------------------------------
  * metric: 0 l1, 1 l2, 2 linf, 3 combined.  mode: 0 position, 1 pose.  loss[0] = scale*(pos+alpha*ori)
  * summed over the n rows; dpred = d loss / d pred (pass NULL to skip).  val-mode metrics:

@@ -18,6 +18,23 @@ AUX_DIM = 3136
 OUT_LD = 8          # 7-D poses live in 8-float rows so every row stays 16-byte aligned for TMA
 
 
+FUSED_HEAD = [True]       # rollout-sized inference (<= 8 frames, no gradients) goes through pe_fused_head
+FUSED_HEAD_MAX_ROWS = 8
+
+
+def _fused_ok(need_grad, rows):
+    return FUSED_HEAD[0] and not need_grad and rows <= FUSED_HEAD_MAX_ROWS
+
+
+def _ticket(core, dev):
+    """Persistent zeroed arrival counter of the fused head kernel (it resets itself after every launch)."""
+    t = getattr(core, "_fh_ticket", None)
+    if t is None or t.device != dev:
+        t = torch.zeros(1, device=dev, dtype=torch.int32)
+        core._fh_ticket = t
+    return t
+
+
 def _f32(x, name):
     if x.dtype != torch.float32:
         raise native.PeError("%s must be float32 (got %s)" % (name, x.dtype))
@@ -93,6 +110,17 @@ class NaiveObjectCore:
         aux_view = cat[:, self.latent:] if self.use_aux else None
         tctx = eng.forward(img, training, need_grad, cat, self.ld_cat, aux_view, self.ld_cat)
         col = self.latent + (AUX_DIM if self.use_aux else 0)
+        if _fused_ok(need_grad, B):
+            # one launch: proprio injection + fc0 over the whole grid, remaining layers by the last CTA
+            x0 = _f32(inputs[1], "self_measurement").reshape(B, 7) if self.m.use_proprioception else None
+            lin0 = self.fcs[0].lin
+            scratch = torch.empty(B, lin0.out_features, device=dev, dtype=torch.float32)
+            out = torch.zeros(B, OUT_LD, device=dev, dtype=torch.float32)
+            tail = [(op.lin.weight, op.lin.bias, op.nout, True) for op in self.fcs[1:]]
+            native.fused_head(cat, self.ld_cat, B, self.n_in, lin0.weight, lin0.out_features, scratch,
+                              _ticket(self, dev), out, OUT_LD, inj=x0, ld_inj=7, inj_col=col, b1=lin0.bias,
+                              relu_a=True, tail=tail)
+            return (out[:, :7],), None, None
         if self.m.use_proprioception:
             x0 = _f32(inputs[1], "self_measurement").reshape(B, 7)
             L.pe_copy_cols(P(x0), 7, P(cat[:, col:]), self.ld_cat, B, 7, 1, st)
@@ -166,6 +194,20 @@ class NaiveEefCore:
         eng = self.m.feature_net.pe_engine()
         cat = torch.zeros(B, self.ld_cat, device=dev, dtype=torch.float32)
         tctx = eng.forward(img, training, need_grad, cat, self.ld_cat)
+        if _fused_ok(need_grad, B):
+            # two launches: pre-measurement MLP (+ measurement difference into the fusion rows), post MLP
+            outs = []
+            for ops, k_x, with_diff in ((self.pre, self.latent, True), (self.post, self.latent + 7, False)):
+                lin0 = ops[0].lin
+                scratch = torch.empty(B, lin0.out_features, device=dev, dtype=torch.float32)
+                out = torch.zeros(B, OUT_LD, device=dev, dtype=torch.float32)
+                tail = [(op.lin.weight, op.lin.bias, op.nout, True) for op in ops[1:]]
+                native.fused_head(cat, self.ld_cat, B, k_x, lin0.weight, lin0.out_features, scratch,
+                                  _ticket(self, dev), out, OUT_LD, b1=lin0.bias, relu_a=True, tail=tail,
+                                  meas=x0 if with_diff else None, ld_meas=7, diff=cat if with_diff else None,
+                                  ld_diff=self.ld_cat, diff_col=self.latent)
+                outs.append(out)
+            return (outs[0][:, :7], outs[1][:, :7]), None, None
         hs_pre = self._mlp(self.pre, cat, self.ld_cat, B, need_grad, dev)
         pre_out = hs_pre[-1]
         # measurement_diff = pre_out - x0bar  -> columns [latent, latent+7) of the fusion buffer
@@ -245,6 +287,24 @@ class TDOCore:
         tctx = eng.forward(img.reshape(M, *img.shape[2:]), training, need_grad, cat, self.ld_cat, aux_view,
                            self.ld_cat)
         col = self.latent + (AUX_DIM if self.use_aux else 0)
+        if S == 1 and _fused_ok(need_grad, N):
+            # streaming step: proprio injection + LSTM gate projections over the whole grid, cell + both dense
+            # layers by the last CTA; the carried state is updated in place
+            x0 = _f32(inputs[1], "self_measurement").reshape(M, 7) if self.m.use_proprioception else None
+            lstm = self.m.rnn.module
+            Hd = self.rnn.H
+            h0, c0 = state if state is not None else (None, None)
+            h_out = h0 if h0 is not None else torch.empty(N, Hd, device=dev, dtype=torch.float32)
+            c_out = c0 if c0 is not None else torch.empty(N, Hd, device=dev, dtype=torch.float32)
+            gates = torch.empty(N, 4 * Hd, device=dev, dtype=torch.float32)
+            out = torch.zeros(N, OUT_LD, device=dev, dtype=torch.float32)
+            fc0, fc1 = self.fc0.lin, self.fc1.lin
+            native.fused_head(cat, self.ld_cat, N, self.n_in, lstm.weight_ih_l0, 4 * Hd, gates, _ticket(self, dev),
+                              out, OUT_LD, inj=x0, ld_inj=7, inj_col=col, k_h=Hd, w_h=lstm.weight_hh_l0, h_prev=h0,
+                              b1=lstm.bias_ih_l0, b2=lstm.bias_hh_l0, lstm_hidden=Hd, c_prev=c0, c_out=c_out,
+                              h_out=h_out, tail=[(fc0.weight, fc0.bias, fc0.out_features, False),
+                                                 (fc1.weight, fc1.bias, fc1.out_features, False)])
+            return (out[:, :7].reshape(S, N, 7),), None, (h_out, c_out)
         if self.m.use_proprioception:
             x0 = _f32(inputs[1], "self_measurement").reshape(M, 7)
             L.pe_copy_cols(P(x0), 7, P(cat[:, col:]), self.ld_cat, M, 7, 1, st)
@@ -323,9 +383,31 @@ class TDCore:
         aux_view = cat[:, self.latent:] if self.use_aux else None
         tctx = eng.forward(img.reshape(M, *img.shape[2:]), training, need_grad, cat, self.ld_cat, aux_view,
                            self.ld_cat)
+        s_pre, s_post = state if state is not None else ((None, None), (None, None))
+        if S == 1 and _fused_ok(need_grad, N):
+            # streaming step in two launches: pre-measurement LSTM + fc (+ measurement difference written into the
+            # fusion rows), then the post-measurement LSTM + fc
+            outs, new_state = [], []
+            m = self.m
+            for lstm, fc, k_x, (h0, c0), with_diff in (
+                    (m.pre_measurement_rnn, m.pre_measurement_fc, self.n_feat, s_pre, True),
+                    (m.post_measurement_rnn, m.post_measurement_fc, self.n_feat + 7, s_post, False)):
+                Hd = lstm.hidden_size
+                h_out = h0 if h0 is not None else torch.empty(N, Hd, device=dev, dtype=torch.float32)
+                c_out = c0 if c0 is not None else torch.empty(N, Hd, device=dev, dtype=torch.float32)
+                gates = torch.empty(N, 4 * Hd, device=dev, dtype=torch.float32)
+                out = torch.zeros(N, OUT_LD, device=dev, dtype=torch.float32)
+                native.fused_head(cat, self.ld_cat, N, k_x, lstm.weight_ih_l0, 4 * Hd, gates, _ticket(self, dev), out,
+                                  OUT_LD, k_h=Hd, w_h=lstm.weight_hh_l0, h_prev=h0, b1=lstm.bias_ih_l0,
+                                  b2=lstm.bias_hh_l0, lstm_hidden=Hd, c_prev=c0, c_out=c_out, h_out=h_out,
+                                  tail=[(fc.weight, fc.bias, fc.out_features, False)],
+                                  meas=x0 if with_diff else None, ld_meas=7, diff=cat if with_diff else None,
+                                  ld_diff=self.ld_cat, diff_col=self.n_feat)
+                outs.append(out[:, :7].reshape(S, N, 7))
+                new_state.append((h_out, c_out))
+            return tuple(outs), None, tuple(new_state)
         for op in (self.pre_rnn, self.post_rnn, self.pre_fc, self.post_fc):
             op.pack(need_grad)
-        s_pre, s_post = state if state is not None else ((None, None), (None, None))
         h1, h1_last, c1_last, rctx1 = self.pre_rnn.forward(cat, S, N, s_pre[0], s_pre[1], need_grad)
         pre_out = torch.zeros(M, OUT_LD, device=dev, dtype=torch.float32)
         self.pre_fc.forward(h1, self.pre_rnn.H, M, pre_out, OUT_LD, relu=False, round_out=0)

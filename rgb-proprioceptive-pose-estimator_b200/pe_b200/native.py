@@ -16,7 +16,7 @@ _REPO_ROOT = os.path.dirname(_PKG_ROOT)
 HEADER = os.path.join(_REPO_ROOT, "include", "pe_b200.h")
 CSRC = os.path.join(_PKG_ROOT, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpe_b200.so")
-SOURCES = ["pe_tapgemm.cu", "pe_gemm_api.cu", "pe_elementwise.cu", "pe_head.cu"]
+SOURCES = ["pe_tapgemm.cu", "pe_gemm_api.cu", "pe_elementwise.cu", "pe_head.cu", "pe_fused_head.cu"]
 
 _CTYPE = {
     "int": ctypes.c_int,
@@ -149,6 +149,49 @@ def lib():
     if _lib is None:
         _lib = _Lib()
     return _lib
+
+
+class HeadDesc(ctypes.Structure):
+    """Mirror of `pe_head_desc` (include/pe_b200.h); tests/test_abi_cpu.py checks the size against the C side."""
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("ldx", ctypes.c_int), ("n_rows", ctypes.c_int),
+        ("inj", ctypes.c_void_p), ("ld_inj", ctypes.c_int), ("inj_col", ctypes.c_int),
+        ("k_x", ctypes.c_int), ("w_x", ctypes.c_void_p),
+        ("k_h", ctypes.c_int), ("w_h", ctypes.c_void_p), ("h_prev", ctypes.c_void_p),
+        ("b1", ctypes.c_void_p), ("b2", ctypes.c_void_p),
+        ("j_a", ctypes.c_int), ("relu_a", ctypes.c_int),
+        ("out_a", ctypes.c_void_p), ("counter", ctypes.c_void_p),
+        ("lstm_hidden", ctypes.c_int), ("c_prev", ctypes.c_void_p), ("c_out", ctypes.c_void_p),
+        ("h_out", ctypes.c_void_p),
+        ("n_tail", ctypes.c_int), ("tail_w", ctypes.c_void_p * 3), ("tail_b", ctypes.c_void_p * 3),
+        ("tail_j", ctypes.c_int * 3), ("tail_relu", ctypes.c_int * 3),
+        ("out", ctypes.c_void_p), ("ld_out", ctypes.c_int),
+        ("meas", ctypes.c_void_p), ("ld_meas", ctypes.c_int),
+        ("diff", ctypes.c_void_p), ("ld_diff", ctypes.c_int), ("diff_col", ctypes.c_int),
+    ]
+
+
+def fused_head(x, ldx, n_rows, k_x, w_x, j_a, out_a, counter, out, ld_out, inj=None, ld_inj=0, inj_col=0, k_h=0,
+               w_h=None, h_prev=None, b1=None, b2=None, relu_a=False, lstm_hidden=0, c_prev=None, c_out=None,
+               h_out=None, tail=(), meas=None, ld_meas=0, diff=None, ld_diff=0, diff_col=0):
+    """Launch pe_fused_head.  Tensor arguments are torch CUDA tensors (or None); `tail` is a sequence of
+    (weight, bias, out_features, relu) for the small layers that follow phase A."""
+    d = HeadDesc()
+    d.x, d.ldx, d.n_rows = ptr(x), ldx, n_rows
+    d.inj, d.ld_inj, d.inj_col = ptr(inj), ld_inj, inj_col
+    d.k_x, d.w_x = k_x, ptr(w_x)
+    d.k_h, d.w_h, d.h_prev = k_h, ptr(w_h), ptr(h_prev)
+    d.b1, d.b2 = ptr(b1), ptr(b2)
+    d.j_a, d.relu_a = j_a, int(bool(relu_a))
+    d.out_a, d.counter = ptr(out_a), ptr(counter)
+    d.lstm_hidden, d.c_prev, d.c_out, d.h_out = lstm_hidden, ptr(c_prev), ptr(c_out), ptr(h_out)
+    d.n_tail = len(tail)
+    for i, (w, b, j, relu) in enumerate(tail):
+        d.tail_w[i], d.tail_b[i], d.tail_j[i], d.tail_relu[i] = ptr(w), ptr(b), j, int(bool(relu))
+    d.out, d.ld_out = ptr(out), ld_out
+    d.meas, d.ld_meas = ptr(meas), ld_meas
+    d.diff, d.ld_diff, d.diff_col = ptr(diff), ld_diff, diff_col
+    return lib().pe_fused_head(ctypes.byref(d), stream_ptr())
 
 
 def ptr(t):

@@ -59,7 +59,7 @@ class StreamingEstimator:
             if isinstance(dst, tuple):
                 for d, s in zip(dst, src):
                     carry(d, s)
-            elif dst is not None:
+            elif dst is not None and src.data_ptr() != dst.data_ptr():   # the fused head updates the state in place
                 L.pe_copy_cols(P(src), src.stride(0), P(dst), dst.stride(0), dst.shape[0], dst.shape[1], 0, st)
         carry(self.state, new_state)
         return outs

@@ -483,6 +483,73 @@ def check_misc():
     return out
 
 
+def check_fused_head(n_rows, mode):
+    """pe_fused_head against fp64 torch: 'mlp' (no-model head: 3 ReLU'd layers after the first), 'lstm' (tdo step:
+    proprio injection, recurrent term, cell, two linear layers), 'lstm_diff' (td pre-measurement step: zero state,
+    one linear layer, measurement difference written back into the fusion rows)."""
+    g = torch.Generator(device=DEV).manual_seed(n_rows * 7 + len(mode))
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    k_x, ld = 3655, 3680
+    x = rnd(n_rows, ld)
+    inj = rnd(n_rows, 7)
+    counter = torch.zeros(1, device=DEV, dtype=torch.int32)
+    out = torch.full((n_rows, 8), float("nan"), device=DEV)
+    rows = []
+    tag = "fused_head %s n%d" % (mode, n_rows)
+    xr = x[:, :k_x].double().clone()
+    if mode == "mlp":
+        dims = [k_x, 1024, 256, 64, 7]
+        ws = [rnd(dims[i + 1], dims[i]) / dims[i] ** 0.5 for i in range(4)]
+        bs = [rnd(dims[i + 1]) * 0.1 for i in range(4)]
+        scratch = torch.empty(n_rows, 1024, device=DEV)
+        native.fused_head(x, ld, n_rows, k_x, ws[0], 1024, scratch, counter, out, 8, inj=inj, ld_inj=7, inj_col=3648,
+                          b1=bs[0], relu_a=True, tail=[(ws[i], bs[i], dims[i + 1], True) for i in (1, 2, 3)])
+        xr[:, 3648:3655] = inj.double()
+        y = xr
+        for w, b in zip(ws, bs):
+            y = (y @ w.double().t() + b.double()).clamp_min(0)
+        rows.append((tag + " out", relerr(out[:, :7], y), 1e-5))
+    else:
+        Hd = 512
+        w_ih, w_hh = rnd(4 * Hd, k_x) / k_x ** 0.5, rnd(4 * Hd, Hd) / Hd ** 0.5
+        b_ih, b_hh = rnd(4 * Hd) * 0.1, rnd(4 * Hd) * 0.1
+        zero_state = mode == "lstm_diff"
+        h0 = None if zero_state else rnd(n_rows, Hd)
+        c0 = None if zero_state else rnd(n_rows, Hd)
+        h_ref0 = torch.zeros(n_rows, Hd, device=DEV).double() if zero_state else h0.double().clone()
+        c_ref0 = torch.zeros(n_rows, Hd, device=DEV).double() if zero_state else c0.double().clone()
+        gates = torch.empty(n_rows, 4 * Hd, device=DEV)
+        if mode == "lstm":
+            fw0, fb0, fw1, fb1 = rnd(128, Hd) / Hd ** 0.5, rnd(128) * 0.1, rnd(7, 128) / 128 ** 0.5, rnd(7) * 0.1
+            tail = [(fw0, fb0, 128, False), (fw1, fb1, 7, False)]
+            h_out, c_out = h0, c0          # in-place state update
+            native.fused_head(x, ld, n_rows, k_x, w_ih, 4 * Hd, gates, counter, out, 8, inj=inj, ld_inj=7,
+                              inj_col=3648, k_h=Hd, w_h=w_hh, h_prev=h0, b1=b_ih, b2=b_hh, lstm_hidden=Hd, c_prev=c0,
+                              c_out=c_out, h_out=h_out, tail=tail)
+            xr[:, 3648:3655] = inj.double()
+        else:
+            fw0, fb0 = rnd(7, Hd) / Hd ** 0.5, rnd(7) * 0.1
+            tail = [(fw0, fb0, 7, False)]
+            h_out, c_out = torch.empty(n_rows, Hd, device=DEV), torch.empty(n_rows, Hd, device=DEV)
+            native.fused_head(x, ld, n_rows, k_x, w_ih, 4 * Hd, gates, counter, out, 8, k_h=Hd, w_h=w_hh, h_prev=None,
+                              b1=b_ih, b2=b_hh, lstm_hidden=Hd, c_prev=None, c_out=c_out, h_out=h_out, tail=tail,
+                              meas=inj, ld_meas=7, diff=x, ld_diff=ld, diff_col=3660)
+        gt = xr @ w_ih.double().t() + h_ref0 @ w_hh.double().t() + b_ih.double() + b_hh.double()
+        i, f, gg, o = gt[:, :Hd].sigmoid(), gt[:, Hd:2 * Hd].sigmoid(), gt[:, 2 * Hd:3 * Hd].tanh(), gt[:, 3 * Hd:].sigmoid()
+        c_ref = f * c_ref0 + i * gg
+        h_ref = o * c_ref.tanh()
+        y = h_ref
+        for w, b, _, _ in tail:
+            y = y @ w.double().t() + b.double()
+        rows.append((tag + " out", relerr(out[:, :7], y), 1e-5))
+        rows.append((tag + " h", relerr(h_out, h_ref), 1e-5))
+        rows.append((tag + " c", relerr(c_out, c_ref), 1e-5))
+        if mode == "lstm_diff":
+            rows.append((tag + " diff", relerr(x[:, 3660:3667], y - inj.double()), 1e-5))
+    rows.append((tag + " ticket reset", float(counter.item()), 0.0))
+    return rows
+
+
 ALL = [
     lambda: check_linear(128, 128, 32, bias=False),
     lambda: check_linear(128, 128, 256),
@@ -516,6 +583,11 @@ ALL = [
     lambda: check_lstm_cell(5, 512),
     lambda: check_loss(37),
     lambda: check_adam(100003),
+    lambda: check_fused_head(1, "mlp"),
+    lambda: check_fused_head(8, "mlp"),
+    lambda: check_fused_head(1, "lstm"),
+    lambda: check_fused_head(5, "lstm"),
+    lambda: check_fused_head(2, "lstm_diff"),
     check_misc,
 ]
 

@@ -115,3 +115,10 @@ def test_state_protocol():
     tdo.reset_initial_state(3)
     assert tuple(tdo.rnn_h.shape) == (1, 3, 512) and tdo.rnn_h.requires_grad
     assert hasattr(no.feature_net.module, "layer1") and hasattr(no.aux_nets[0].module, "register_forward_hook")
+
+
+def test_head_descriptor_layout_matches_c():
+    """The ctypes mirror of pe_head_desc has the C struct's size (field order / padding drift shows up here)."""
+    import ctypes
+    from pe_b200 import native
+    assert native.lib()._dll.pe_head_desc_size() == ctypes.sizeof(native.HeadDesc)

@@ -219,3 +219,50 @@ def test_cuda_graph_rollout_matches_eager_and_oracle(kind):
         ref = orc.forward(img, x0, training=False, rollout=True)
         assert torch.equal(og.reshape(-1), oe.reshape(-1)), t
         assert mc.rel(og.reshape(-1), ref.reshape(-1)) <= 5e-3, t
+
+
+@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n"])
+def test_fused_head_matches_gemm_head(kind):
+    """Rollout-sized inference: the one-launch fused head (pe_fused_head, fp32 FMA) and the tap-GEMM head (TF32
+    tensor cores) agree on outputs and carried LSTM state."""
+    from pe_b200 import estimators as est
+    mc.SHALLOW[0] = True
+    model = mc.build_model(kind).cuda().eval()
+    seq = kind in ("td", "tdo")
+    n = 3
+    res = {}
+    for fused in (True, False):
+        est.FUSED_HEAD[0] = fused
+        try:
+            if seq:
+                model.rollout = True
+                model.reset_initial_state(n)
+            outs = []
+            with torch.no_grad():
+                for t in range(2):
+                    img, x0, _ = po.synthetic_batch(kind, n, s=1, seed=20 + t) if seq else po.synthetic_batch(kind, n, seed=20 + t)
+                    o = model(img.cuda(), None, x0.cuda())
+                    outs += [v.clone() for v in (o if isinstance(o, tuple) else (o,))]
+            res[fused] = outs
+        finally:
+            est.FUSED_HEAD[0] = True
+    for a, b in zip(res[True], res[False]):
+        assert mc.rel(a, b) <= 5e-3, (kind, mc.rel(a, b))
+
+
+def test_streaming_estimator_graph_with_fused_head():
+    """CUDA-graph replay of the TDO streaming step == eager steps (state carried in place by the fused head)."""
+    from pe_b200.rollout import StreamingEstimator
+    mc.SHALLOW[0] = True
+    model = mc.build_model("tdo").cuda().eval()
+    outs = {}
+    for use_graph in (True, False):
+        est_ = StreamingEstimator(model, batch_size=2, use_graph=use_graph)
+        est_.reset()
+        seq = []
+        for t in range(3):
+            img, x0, _ = po.synthetic_batch("tdo", 2, s=1, seed=30 + t)
+            seq.append(est_.step(img.cuda(), x0.cuda()).clone())
+        outs[use_graph] = seq
+    for a, b in zip(outs[True], outs[False]):
+        assert mc.rel(a, b) <= 1e-5, mc.rel(a, b)
