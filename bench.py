@@ -246,7 +246,28 @@ def run_ours(args):
     total_ms = sum(fam.values())
     tf32_peak = pk["bf16"] / 2.0
     ach_tflops = TRAIN_GFLOP_PER_FRAME[kind] * frames / 1e3 / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
-    stream_ms = sum(v for k, v in fam.items() if k.startswith("pe_bn_") or k in ("pe_maxpool3x3s2_fwd", "pe_maxpool3x3s2_bwd", "pe_adam_step"))
+    # DRAM bytes per kernel family from the committed ncu launch list of this same step (profiles/): live CUDA-event
+    # times divided into ncu-measured bytes give the achieved HBM rate of the streaming kernels
+    prof = {}
+    try:
+        pj = json.load(open(os.path.join(ROOT, "profiles", "launches_r01b_train_step_no_b256_summary.json")))
+        prof = {k["kernel"]: k for k in pj["kernels"]}
+    except Exception:
+        pass
+    fam_of = {"bn_train_apply_kernel": "pe_bn_train_apply", "channel_reduce_kernel<1>": "pe_bn_bwd_reduce",
+              "bn_bwd_apply_kernel": "pe_bn_bwd_apply", "adam_kernel": "pe_adam_step"}
+    hbm_kernels = {}
+    if kind == "no" and args.batch == 256:
+        for kname, fname in fam_of.items():
+            if kname in prof and fam.get(fname):
+                gb = prof[kname]["dram_read_GB"] + prof[kname]["dram_write_GB"]
+                rate = gb / (fam[fname] / 1e3)
+                hbm_kernels[fname] = {"ms": round(fam[fname], 3), "dram_GB": round(gb, 3), "GB_per_s": round(rate, 1),
+                                      "frac_of_peak": round(rate / pk["hbm"], 3)}
+    gemm_launches = prof.get("tapgemm_kernel", {}).get("launches")
+    gemm_traffic = None
+    if kind == "no" and args.batch == 256 and gemm_launches:
+        gemm_traffic = (prof["tapgemm_kernel"]["dram_read_GB"] + prof["tapgemm_kernel"]["dram_write_GB"]) * 1e9 / gemm_launches
     out = {
         "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -258,13 +279,18 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel (conv fwd/dgrad/wgrad + dense layers)",
                      "achieved": ach_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": ach_tflops / tf32_peak if tf32_peak else None, "traffic": None,
+                     "frac": ach_tflops / tf32_peak if tf32_peak else None, "traffic": gemm_traffic,
+                     "traffic_note": "ncu dram bytes read+written, average per tapgemm launch over one step "
+                                     "(profiles/launches_r01b_train_step_no_b256_summary.json)",
+                     "algorithmic_flop_per_step": TRAIN_GFLOP_PER_FRAME[kind] * frames * 1e9,
+                     "launches_per_step": gemm_launches,
                      "peak_source": "%s bf16 sustained / 2 (TF32 runs at half the bf16 rate)" % pk["which"],
                      "share_of_step": gemm_ms / total_ms if total_ms else None},
         "roofline_step": {"bound": "hbm", "achieved": TRAIN_MB_PER_FRAME * frames / 1e3 / (ms / args.steps / 1e3),
                           "peak": pk["hbm"], "unit": "GB/s",
                           "frac": TRAIN_MB_PER_FRAME * frames / 1e3 / (ms / args.steps / 1e3) / pk["hbm"],
                           "note": "compulsory fp32 activation traffic (223 MB/frame) over the whole step"},
+        "hbm_kernels": hbm_kernels,
         "kernel_ms": {k: round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])},
         "loss": loss_val,
     }
