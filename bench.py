@@ -26,7 +26,8 @@ sys.path.insert(0, os.path.join(ROOT, "rgb-proprioceptive-pose-estimator_b200"))
 sys.path.insert(0, ROOT)
 
 LOSS = dict(distance_metric="combined", alpha=0.5, mode="pose")          # scripts/train_no.sbatch:61-83
-TRAIN_GFLOP_PER_FRAME = {"no": 24.32, "tdo": 24.35, "td": 24.42, "n": 24.30}
+TRAIN_GFLOP_PER_FRAME = {"no": 24.32, "tdo": 24.35, "td": 24.42, "n": 24.30, "tdo_v2": 24.35}
+SEQ_KINDS = ("td", "tdo", "tdo_v2")
 TRAIN_MB_PER_FRAME = 223.0                                                # SURVEY 8(d) compulsory fp32 traffic
 
 
@@ -93,7 +94,7 @@ def build(kind, seed=0):
 
 def synth(kind, n, s, seed):
     from oracle import pose_oracle as po
-    return po.synthetic_batch(kind, n, s=s, seed=seed) if kind in ("td", "tdo") else po.synthetic_batch(kind, n, seed=seed)
+    return po.synthetic_batch(kind, n, s=s, seed=seed) if kind in SEQ_KINDS else po.synthetic_batch(kind, n, seed=seed)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -108,11 +109,11 @@ def cpu_reference_rate(kind, batch, seq, steps, warmup):
         extra = {"aux_w": model.aux_nets[0][0].weight, "aux_b": model.aux_nets[0][0].bias}
     orc = po.OracleEstimator(kind, model.state_dict(), extra)
     img, x0, tgt = synth(kind, batch, seq, 1)
-    frames = img.shape[0] * (img.shape[1] if kind in ("td", "tdo") else 1)
+    frames = img.shape[0] * (img.shape[1] if kind in SEQ_KINDS else 1)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        if kind in ("no", "tdo"):
+        if kind in ("no", "tdo", "tdo_v2"):
             orc.train_step(img, x0, tgt, LOSS)
         else:
             orc.train_step(img, x0, tgt, LOSS, which=-1)
@@ -146,10 +147,11 @@ def workload_config(args):
     names = {"no": "naive-object estimator (models/naive.py) training step, hammer target, latent 512, hidden 1024/256/64, combined pose loss, Adam",
              "tdo": "TDO estimator training step, robot1_eef target, latent 512, LSTM 512",
              "td": "TD estimator training step, latent 1024, LSTM 512",
+             "tdo_v2": "TDO-v2 estimator training step (image LSTM 512 + proprio LSTM 64), robot1_eef target",
              "n": "naive end-effector estimator training step"}
     cfg = {"workload": names[args.model], "per_gpu_batch": args.batch, "frame": "3x224x224 fp32",
            "cache": "inputs_larger_than_l2"}
-    if args.model in ("td", "tdo"):
+    if args.model in SEQ_KINDS:
         cfg["sequence_length"] = args.seq
     return cfg
 
@@ -176,7 +178,7 @@ def run_ours(args):
     trainer = FusedTrainer(model, lr=args.lr, process_group=pg, **LOSS)
     seq = args.seq
     img, x0, tgt = synth(kind, args.batch, seq, 1 + rank)
-    frames = args.batch * (seq if kind in ("td", "tdo") else 1)
+    frames = args.batch * (seq if kind in SEQ_KINDS else 1)
     targets_h = (x0, tgt) if kind in ("td", "n") else tgt
     img_h, x0_h = img.pin_memory(), x0.pin_memory()
     tg_h = tuple(t.pin_memory() for t in targets_h) if isinstance(targets_h, tuple) else targets_h.pin_memory()
@@ -316,7 +318,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--model", default="no", choices=["no", "tdo", "td", "n"])
+    ap.add_argument("--model", default="no", choices=["no", "tdo", "td", "n", "tdo_v2"])
     ap.add_argument("--batch", type=int, default=None, help="frames (naive) or episodes (sequence models) per GPU")
     ap.add_argument("--seq", type=int, default=None)
     ap.add_argument("--cpu-batch", type=int, default=8)
@@ -324,9 +326,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.seq is None:
-        args.seq = {"tdo": 20, "td": 10}.get(args.model, 1)
+        args.seq = {"tdo": 20, "td": 10, "tdo_v2": 20}.get(args.model, 1)
     if args.batch is None:
-        args.batch = {"no": 256, "n": 256, "tdo": 32, "td": 64}[args.model]
+        args.batch = {"no": 256, "n": 256, "tdo": 32, "td": 64, "tdo_v2": 32}[args.model]
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -26,9 +26,10 @@ from oracle import ref_shim  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 LOSS_CFG = {"no": dict(distance_metric="combined", alpha=0.5, mode="pose"),
             "tdo": dict(distance_metric="combined", alpha=0.5, mode="pose"),
+            "tdo_v2": dict(distance_metric="combined", alpha=0.5, mode="pose"),
             "td": dict(distance_metric="l2", alpha=0.5, mode="pose"),
             "n": dict(distance_metric="l2", alpha=0.5, mode="pose")}
-SHAPES = {"no": dict(n=2), "n": dict(n=2), "tdo": dict(n=2, s=2), "td": dict(n=2, s=2)}
+SHAPES = {"no": dict(n=2), "n": dict(n=2), "tdo": dict(n=2, s=2), "td": dict(n=2, s=2), "tdo_v2": dict(n=2, s=2)}
 
 
 def dump(name, obj):
@@ -68,7 +69,7 @@ def loss_vectors(ref):
 
 def manifest(ref):
     out = {}
-    for kind in ("no", "n", "td", "tdo"):
+    for kind in ("no", "n", "td", "tdo", "tdo_v2"):
         m = ref_shim.build_reference_model(ref, kind)
         sd = m.state_dict()
         out[kind] = dict(
@@ -82,11 +83,11 @@ def manifest(ref):
 def run_reference(ref, kind, img, x0, tgt, lk):
     m = ref_shim.build_reference_model(ref, kind)
     m.train()
-    if kind in ("td", "tdo"):
+    if kind in ("td", "tdo", "tdo_v2"):
         m.reset_initial_state(img.shape[1])
     crit = ref.losses.PoseDistanceLoss(**lk)
     out = m(img, None, x0)
-    if kind in ("no", "tdo"):
+    if kind in ("no", "tdo", "tdo_v2"):
         loss = crit(out, tgt)
         outs = [out]
     else:
@@ -111,7 +112,7 @@ def forward_fixture(ref, kind):
               running_var_sum={k: float(v.double().sum()) for k, v in sd.items() if k.endswith("running_var")})
     m.eval()
     with torch.no_grad(), ref_shim.quiet():
-        if kind in ("td", "tdo"):
+        if kind in ("td", "tdo", "tdo_v2"):
             m.reset_initial_state(img.shape[1])
         oe = m(img, None, x0)
     oe = list(oe) if isinstance(oe, tuple) else [oe]
@@ -152,8 +153,10 @@ def main():
     if "manifest" in what:
         manifest(ref)
     if "forward" in what:
-        for kind in ("no", "tdo", "td", "n"):
+        for kind in ("no", "tdo", "td", "n", "tdo_v2"):
             forward_fixture(ref, kind)
+    if "forward_v2" in what:
+        forward_fixture(ref, "tdo_v2")
     if "curve" in what:
         curve_fixture(ref, "no", 100)
         curve_fixture(ref, "tdo", 30)

@@ -143,6 +143,23 @@ def tdo_forward(sd, img, x0bar, training, state=None, use_proprio=True):
     return out, new_state
 
 
+def tdo_v2_forward(sd, img, x0bar, training, state=None):
+    """TemporallyDependentObjectStateEstimatorV2.forward (models/time_sensitive.py:714-786): one LSTM per sensor
+    modality -- image features (latent + aux) and the 7-D proprioceptive measurement -- whose hidden states are
+    concatenated (:776) and fed to Linear(H, H//4) -> Linear(H//4, 7) (:683-686, no nonlinearity).
+    `state` = ((h_img, c_img), (h_pro, c_pro)) for rollout mode; returns (out, new_state)."""
+    S, N = img.shape[0], img.shape[1]
+    feats, early = resnet50_forward(sd, "feature_net.module.", img.reshape(S * N, *img.shape[2:]), training)
+    aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"])
+    f = torch.cat((feats, aux), dim=-1).view(S, N, -1)
+    h_img, st_img = lstm_forward(f, sd, "img_rnn.module.", None if state is None else state[0])
+    h_pro, st_pro = lstm_forward(x0bar, sd, "proprio_rnn.module.", None if state is None else state[1])
+    h = torch.cat((h_img, h_pro), dim=-1)
+    out = F.linear(F.linear(h, sd["fc.module.0.weight"], sd["fc.module.0.bias"]),
+                   sd["fc.module.1.weight"], sd["fc.module.1.bias"])
+    return out, (st_img, st_pro)
+
+
 def td_forward(sd, img, x0bar, training, aux_w, aux_b, state=None):
     """TemporallyDependentStateEstimator.forward (models/time_sensitive.py:165-254).  The aux conv is
     NOT part of the state_dict (plain python list, quirk Q4, :77-78,102-115) so it is passed in.
@@ -232,7 +249,7 @@ class OracleEstimator:
     """Holds a reference-layout state_dict and runs forward / loss / backward / Adam on CPU."""
 
     def __init__(self, kind, state_dict, extra=None):
-        assert kind in ("no", "n", "td", "tdo")
+        assert kind in ("no", "n", "td", "tdo", "tdo_v2")
         self.kind = kind
         self.sd = {k: v.detach().clone() for k, v in state_dict.items()}
         self.extra = {k: v.detach().clone() for k, v in (extra or {}).items()}  # td: aux conv (frozen)
@@ -257,6 +274,11 @@ class OracleEstimator:
             if rollout:
                 self.state = st
             return out
+        if self.kind == "tdo_v2":
+            out, st = tdo_v2_forward(sd, img, x0bar, training, self.state if rollout else None)
+            if rollout:
+                self.state = st
+            return out
         pre, post, st = td_forward(sd, img, x0bar, training, self.extra["aux_w"], self.extra["aux_b"],
                                    self.state if rollout else None)
         if rollout:
@@ -267,6 +289,10 @@ class OracleEstimator:
         h = self.sd["rnn.module.weight_hh_l0"].shape[1] if self.kind == "tdo" else None
         if self.kind == "tdo":
             self.state = (torch.zeros(1, n, h), torch.zeros(1, n, h))
+        elif self.kind == "tdo_v2":
+            hi = self.sd["img_rnn.module.weight_hh_l0"].shape[1]
+            hp = self.sd["proprio_rnn.module.weight_hh_l0"].shape[1]
+            self.state = ((torch.zeros(1, n, hi), torch.zeros(1, n, hi)), (torch.zeros(1, n, hp), torch.zeros(1, n, hp)))
         elif self.kind == "td":
             hp = self.sd["pre_measurement_rnn.weight_hh_l0"].shape[1]
             hq = self.sd["post_measurement_rnn.weight_hh_l0"].shape[1]

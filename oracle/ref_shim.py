@@ -154,6 +154,12 @@ def build_reference_model(ref, kind, seed=0, **kw):
                 num_resnet_layers=50, latent_dim=kw.get("latent_dim", 512),
                 sequence_length=kw.get("sequence_length", 20), feature_extract=False, feature_layer_nums=(9,),
                 use_depth=False, use_pretrained=False)
+        if kind == "tdo_v2":
+            return ref.time_sensitive.TemporallyDependentObjectStateEstimatorV2(
+                object_name=kw.get("object_name", "robot1_eef"), img_hidden_dim=kw.get("hidden_dim", 512),
+                proprio_hidden_dim=kw.get("proprio_hidden_dim", 64), num_resnet_layers=50,
+                latent_dim=kw.get("latent_dim", 512), sequence_length=kw.get("sequence_length", 20),
+                feature_extract=False, feature_layer_nums=(9,), use_depth=False, use_pretrained=False)
         if kind == "td":
             return ref.time_sensitive.TemporallyDependentStateEstimator(
                 hidden_dim_pre_measurement=kw.get("hidden_dim", 512),

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from models.naive import _check_supported, _probe_feature_layers
-from pe_b200.estimators import TDCore, TDOCore
+from pe_b200.estimators import TDCore, TDOCore, TDOV2Core
 from pe_b200.functions import run_core
 from util.model_utils import PassThroughParallel, import_resnet
 
@@ -179,6 +179,93 @@ class TemporallyDependentObjectStateEstimator(nn.Module):
     def reset_initial_state(self, batch_size):
         self.rnn_h = torch.zeros((1, batch_size, self.hidden_dim), requires_grad=True)
         self.rnn_c = torch.zeros((1, batch_size, self.hidden_dim), requires_grad=True)
+        self.out_vec = []
+
+    @property
+    def requires_sequence(self):
+        return True
+
+
+class TemporallyDependentObjectStateEstimatorV2(nn.Module):
+    """
+    TDO variant with one LSTM per sensor modality: image features (trunk + aux) and the proprioceptive
+    measurement each run through their own LSTM; the hidden states are concatenated and fed to
+    Linear(H, H//4) -> Linear(H//4, 7).  Mirror of reference models/time_sensitive.py:536-804
+    (trained by scripts/train_model.py:205-218 as model "tdo_v2").
+    """
+
+    def __init__(
+            self,
+            object_name,
+            img_hidden_dim,
+            proprio_hidden_dim=64,
+            num_resnet_layers=50,
+            latent_dim=50,
+            sequence_length=10,
+            dropout_prob=0.10,
+            feature_extract=True,
+            feature_layer_nums=(9,),
+            use_depth=False,
+            use_pretrained=True,
+            device='cpu'
+    ):
+        super(TemporallyDependentObjectStateEstimatorV2, self).__init__()
+        _check_supported(feature_layer_nums, use_depth)
+        self.object_name = object_name
+        self.early_features = None
+        self.aux_nets = None
+        self.depth_nets = None
+        self.aux_latent_dim = 0
+        self.use_depth = use_depth
+        feature_net, _ = import_resnet(num_resnet_layers, latent_dim, feature_extract, use_pretrained=use_pretrained)
+        self.feature_net = feature_net        # registered first, re-wrapped below (keeps the reference's key order)
+        if feature_layer_nums is not None:
+            self.early_features = []
+            aux, depth, self.aux_latent_dim = _probe_feature_layers(self, feature_net, feature_layer_nums,
+                                                                    PassThroughParallel)
+            self.aux_nets = nn.ModuleList(aux)
+            self.depth_nets = nn.ModuleList(depth)
+        self.feature_net = PassThroughParallel(feature_net)
+        print("Latent Dim + Aux Dim = {}".format(latent_dim + self.aux_latent_dim))
+        input_dim = latent_dim + self.aux_latent_dim
+        self.img_rnn = PassThroughParallel(nn.LSTM(input_size=input_dim, hidden_size=img_hidden_dim))
+        self.proprio_rnn = PassThroughParallel(nn.LSTM(input_size=7, hidden_size=proprio_hidden_dim))
+        fc_input_dim = img_hidden_dim + proprio_hidden_dim
+        self.fc = PassThroughParallel(nn.Sequential(
+            nn.Linear(fc_input_dim, int(fc_input_dim // 4)),
+            nn.Linear(int(fc_input_dim // 4), 7)
+        ))
+        self.sequence_length = sequence_length
+        self.img_rnn_h = None
+        self.img_rnn_c = None
+        self.proprio_rnn_h = None
+        self.proprio_rnn_c = None
+        self.img_hidden_dim = img_hidden_dim
+        self.proprio_hidden_dim = proprio_hidden_dim
+        self.out_vec = None
+        self.rollout = False
+        self._core = None
+
+    def forward(self, img, depth, self_measurement):
+        """img (S,N,C,H,W), self_measurement (S,N,7) -> pose (S,N,7)"""
+        if self._core is None:
+            object.__setattr__(self, "_core", TDOV2Core(self))
+        state = None
+        if self.rollout:
+            state = ((_state_2d(self.img_rnn_h, img), _state_2d(self.img_rnn_c, img)),
+                     (_state_2d(self.proprio_rnn_h, img), _state_2d(self.proprio_rnn_c, img)))
+        out = run_core(self._core, (img, self_measurement), self.training, state)[0]
+        if self.rollout:
+            (h1, c1), (h2, c2) = self._core.last_state
+            self.img_rnn_h, self.img_rnn_c = h1.unsqueeze(0), c1.unsqueeze(0)
+            self.proprio_rnn_h, self.proprio_rnn_c = h2.unsqueeze(0), c2.unsqueeze(0)
+        return out
+
+    def reset_initial_state(self, batch_size):
+        self.img_rnn_h = torch.zeros((1, batch_size, self.img_hidden_dim), requires_grad=True)
+        self.img_rnn_c = torch.zeros((1, batch_size, self.img_hidden_dim), requires_grad=True)
+        self.proprio_rnn_h = torch.zeros((1, batch_size, self.proprio_hidden_dim), requires_grad=True)
+        self.proprio_rnn_c = torch.zeros((1, batch_size, self.proprio_hidden_dim), requires_grad=True)
         self.out_vec = []
 
     @property

@@ -340,6 +340,87 @@ class TDOCore:
                      on_ready)
 
 
+class TDOV2Core:
+    """TemporallyDependentObjectStateEstimatorV2 (reference models/time_sensitive.py:536-804): one LSTM over the
+    image features (latent + aux), one over the 7-D proprioceptive measurement, hidden states concatenated into
+    Linear(H, H//4) -> Linear(H//4, 7)."""
+
+    def __init__(self, m):
+        self.m = m
+        self.latent = m.feature_net.module.fc.out_features
+        self.use_aux = m.early_features is not None
+        self.n_in = self.latent + (AUX_DIM if self.use_aux else 0)
+        self.ld_cat = _pad32(self.n_in)
+        self.img_rnn = LSTMOp(m.img_rnn.module, self.ld_cat)
+        self.pro_rnn = LSTMOp(m.proprio_rnn.module, OUT_LD)
+        self.fc0 = LinearOp(m.fc.module[0])
+        self.fc1 = LinearOp(m.fc.module[1])
+        self.H1, self.H2 = self.img_rnn.H, self.pro_rnn.H
+
+    def _engine(self):
+        aux = self.m.aux_nets[0].module[0] if self.use_aux else None
+        return self.m.feature_net.module.pe_engine(aux, True)
+
+    def params(self):
+        return list(self.m.parameters())
+
+    def forward(self, inputs, training, need_grad, state=None):
+        """inputs: img (S,N,3,H,W), x0bar (S,N,7); state: ((h_img, c_img), (h_pro, c_pro)), each (N, H)."""
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        img = _f32(inputs[0], "img")
+        S, N = img.shape[0], img.shape[1]
+        M = S * N
+        dev = img.device
+        eng = self._engine()
+        cat = torch.zeros(M, self.ld_cat, device=dev, dtype=torch.float32)
+        aux_view = cat[:, self.latent:] if self.use_aux else None
+        tctx = eng.forward(img.reshape(M, *img.shape[2:]), training, need_grad, cat, self.ld_cat, aux_view,
+                           self.ld_cat)
+        x0 = _f32(inputs[1], "self_measurement").reshape(M, 7)
+        x0p = torch.zeros(M, OUT_LD, device=dev, dtype=torch.float32)      # TF32-rounded, zero padded to 8
+        L.pe_copy_cols(P(x0), 7, P(x0p), OUT_LD, M, 7, 1, st)
+        for op in (self.img_rnn, self.pro_rnn, self.fc0, self.fc1):
+            op.pack(need_grad)
+        s_img, s_pro = state if state is not None else ((None, None), (None, None))
+        h1, h1_last, c1_last, rctx1 = self.img_rnn.forward(cat, S, N, s_img[0], s_img[1], need_grad)
+        h2, h2_last, c2_last, rctx2 = self.pro_rnn.forward(x0p, S, N, s_pro[0], s_pro[1], need_grad)
+        Hc = self.H1 + self.H2
+        hcat = torch.empty(M, Hc, device=dev, dtype=torch.float32)          # torch.cat((img_h, proprio_h), -1)
+        L.pe_copy_cols(P(h1), self.H1, P(hcat), Hc, M, self.H1, 0, st)
+        L.pe_copy_cols(P(h2), self.H2, P(hcat[:, self.H1:]), Hc, M, self.H2, 0, st)
+        z = torch.empty(M, self.fc0.ld_out, device=dev, dtype=torch.float32)
+        self.fc0.forward(hcat, Hc, M, z, self.fc0.ld_out, relu=False, round_out=1)
+        out = torch.zeros(M, OUT_LD, device=dev, dtype=torch.float32)
+        self.fc1.forward(z, self.fc0.ld_out, M, out, OUT_LD, relu=False, round_out=0)
+        saved = (eng, tctx, rctx1, rctx2, cat, hcat, z, S, N)
+        return (out[:, :7].reshape(S, N, 7),), saved, ((h1_last, c1_last), (h2_last, c2_last))
+
+    def backward(self, saved, douts, grad_of, on_ready=None):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        eng, tctx, rctx1, rctx2, cat, hcat, z, S, N = saved
+        M = S * N
+        dev = cat.device
+        Hc = self.H1 + self.H2
+        d = _pad_grad(douts[0], M, dev, 1)
+        dz = torch.empty(M, self.fc0.ld_out, device=dev, dtype=torch.float32)
+        self.fc1.backward(z, self.fc0.ld_out, M, d, OUT_LD, grad_of, dz, self.fc0.ld_out)
+        L.pe_copy_cols(P(dz), self.fc0.ld_out, P(dz), self.fc0.ld_out, M, self.fc0.nout, 1, st)
+        dhcat = torch.empty(M, Hc, device=dev, dtype=torch.float32)
+        self.fc0.backward(hcat, Hc, M, dz, self.fc0.ld_out, grad_of, dhcat, Hc)
+        dh1 = torch.empty(M, self.H1, device=dev, dtype=torch.float32)
+        dh2 = torch.empty(M, self.H2, device=dev, dtype=torch.float32)
+        L.pe_copy_cols(P(dhcat), Hc, P(dh1), self.H1, M, self.H1, 0, st)
+        L.pe_copy_cols(P(dhcat[:, self.H1:]), Hc, P(dh2), self.H2, M, self.H2, 0, st)
+        self.pro_rnn.backward(rctx2, dh2, grad_of)
+        dcat = torch.empty(M, self.ld_cat, device=dev, dtype=torch.float32)
+        self.img_rnn.backward(rctx1, dh1, grad_of, dcat, self.ld_cat, dx_cols=self.n_in)
+        if on_ready is not None:
+            m = self.m
+            on_ready(list(m.img_rnn.parameters()) + list(m.proprio_rnn.parameters()) + list(m.fc.parameters()))
+        eng.backward(tctx, dcat, self.ld_cat, dcat[:, self.latent:] if self.use_aux else None, self.ld_cat, grad_of,
+                     on_ready)
+
+
 class TDCore:
     """TemporallyDependentStateEstimator (reference models/time_sensitive.py:8-274): two LSTMs in series;
     the aux conv is an unregistered, frozen module (reference quirk, :77-78,102-115)."""

@@ -34,6 +34,9 @@ class StreamingEstimator:
         name = type(m).__name__
         if name == "TemporallyDependentObjectStateEstimator":
             return (torch.zeros(N, m.hidden_dim, device=dev), torch.zeros(N, m.hidden_dim, device=dev))
+        if name == "TemporallyDependentObjectStateEstimatorV2":
+            return ((torch.zeros(N, m.img_hidden_dim, device=dev), torch.zeros(N, m.img_hidden_dim, device=dev)),
+                    (torch.zeros(N, m.proprio_hidden_dim, device=dev), torch.zeros(N, m.proprio_hidden_dim, device=dev)))
         if name == "TemporallyDependentStateEstimator":
             return ((torch.zeros(N, m.pre_measurement_hidden_dim, device=dev),
                      torch.zeros(N, m.pre_measurement_hidden_dim, device=dev)),

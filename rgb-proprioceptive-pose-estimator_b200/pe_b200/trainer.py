@@ -28,6 +28,7 @@ def get_core(model):
         cls = {"NaiveObjectStateEstimator": est.NaiveObjectCore,
                "NaiveEndEffectorStateEstimator": est.NaiveEefCore,
                "TemporallyDependentObjectStateEstimator": est.TDOCore,
+               "TemporallyDependentObjectStateEstimatorV2": est.TDOV2Core,
                "TemporallyDependentStateEstimator": est.TDCore}[name]
         core = cls(model)
         object.__setattr__(model, "_core", core)

@@ -22,6 +22,7 @@ CONFIGS = {
     # kind: (ctor kwargs, loss kwargs)  -- hyper-parameters from scripts/train_no.sbatch / train_tdo.sbatch
     "no": dict(latent=512, hidden=[1024, 256, 64], loss=dict(distance_metric="combined", alpha=0.5, mode="pose")),
     "tdo": dict(latent=512, hidden=512, loss=dict(distance_metric="combined", alpha=0.5, mode="pose")),
+    "tdo_v2": dict(latent=512, hidden=512, loss=dict(distance_metric="combined", alpha=0.5, mode="pose")),
     "td": dict(latent=1024, hidden=512, loss=dict(distance_metric="l2", alpha=0.5, mode="pose")),
     "n": dict(latent=1024, hidden=[512], loss=dict(distance_metric="l2", alpha=0.5, mode="pose")),
 }
@@ -44,6 +45,9 @@ def build_model(kind, seed=0):
         if kind == "tdo":
             return mt.TemporallyDependentObjectStateEstimator("robot1_eef", cfg["hidden"], 50, cfg["latent"], 20,
                                                               feature_extract=False, use_pretrained=False)
+        if kind == "tdo_v2":
+            return mt.TemporallyDependentObjectStateEstimatorV2("robot1_eef", cfg["hidden"], 64, 50, cfg["latent"], 20,
+                                                                feature_extract=False, use_pretrained=False)
         if kind == "td":
             return mt.TemporallyDependentStateEstimator(cfg["hidden"], cfg["hidden"], 50, cfg["latent"], 10,
                                                         feature_extract=False, use_pretrained=False)
@@ -87,7 +91,7 @@ def check_train_step(kind, n=2, s=2, seed=1, verbose=False):
         img, x0, tgt = po.synthetic_batch(kind, n, s=s, seed=seed)
     lk = cfg["loss"]
     t0 = time.time()
-    if kind in ("no", "tdo"):
+    if kind in ("no", "tdo", "tdo_v2"):
         outs_ref, loss_ref, grads_ref = orc.loss_and_grads(img, x0, tgt, lk)
         outs_ref = (outs_ref,)
     else:
@@ -107,11 +111,11 @@ def check_train_step(kind, n=2, s=2, seed=1, verbose=False):
 
     model.cuda().train()
     crit = PoseDistanceLoss(distance_metric=lk["distance_metric"], alpha=lk["alpha"], mode=lk["mode"])
-    if kind in ("td", "tdo"):
+    if kind in ("td", "tdo", "tdo_v2"):
         model.reset_initial_state(n)
     out = model(img.cuda(), None, x0.cuda())
     outs = out if isinstance(out, tuple) else (out,)
-    if kind in ("no", "tdo"):
+    if kind in ("no", "tdo", "tdo_v2"):
         loss = crit(outs[0], tgt.cuda())
     else:
         loss = crit(outs[0], x0.cuda()) + crit(outs[1], tgt.cuda())
@@ -154,7 +158,7 @@ def check_train_step(kind, n=2, s=2, seed=1, verbose=False):
     # eval-mode forward with the same (now updated) running statistics
     model.eval()
     with torch.no_grad():
-        if kind in ("td", "tdo"):
+        if kind in ("td", "tdo", "tdo_v2"):
             model.reset_initial_state(n)
         oe = model(img.cuda(), None, x0.cuda())
     oe = oe if isinstance(oe, tuple) else (oe,)

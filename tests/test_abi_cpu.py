@@ -58,7 +58,7 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
 
 
-@pytest.mark.parametrize("kind", ["no", "n", "td", "tdo"])
+@pytest.mark.parametrize("kind", ["no", "n", "td", "tdo", "tdo_v2"])
 def test_state_dict_layout_matches_reference_manifest(kind):
     """Keys, order, shapes, dtypes, parameter order and the seed-0 init values equal the reference's
     (tests/golden/state_dicts.json, generated from the reference constructors)."""

@@ -39,11 +39,11 @@ def _split(rows):
     return fwd, grads, struct
 
 
-@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n"])
+@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n", "tdo_v2"])
 def test_shallow_trunk_parity(kind):
     mc.SHALLOW[0] = True
     rows = mc.check_train_step(kind, n=4, verbose=True)
-    if kind in ("tdo", "td"):
+    if kind in ("tdo", "td", "tdo_v2"):
         rows += mc.check_rollout(kind)
     fwd, grads, struct = _split(rows)
     bad = [(n, e) for n, e, t in fwd if not e <= max(t, 5e-3)] + [(n, e) for n, e, t in struct if e != 0.0]
@@ -68,7 +68,7 @@ def test_full_depth_parity(kind):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n"])
+@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n", "tdo_v2"])
 def test_against_reference_fixture(kind):
     """Outputs / loss / eval outputs of the CUDA path vs numbers produced by the reference's own modules
     (tests/golden/forward_<kind>.json)."""
@@ -78,11 +78,11 @@ def test_against_reference_fixture(kind):
     img, x0, tgt = po.synthetic_batch(kind, seed=1, **fx["shapes"])
     img, x0, tgt = img.cuda(), x0.cuda(), tgt.cuda()
     crit = PoseDistanceLoss(**fx["loss_cfg"])
-    if kind in ("td", "tdo"):
+    if kind in ("td", "tdo", "tdo_v2"):
         model.reset_initial_state(img.shape[1])
     out = model(img, None, x0)
     outs = list(out) if isinstance(out, tuple) else [out]
-    loss = crit(outs[0], tgt) if kind in ("no", "tdo") else crit(outs[0], x0) + crit(outs[1], tgt)
+    loss = crit(outs[0], tgt) if kind in ("no", "tdo", "tdo_v2") else crit(outs[0], x0) + crit(outs[1], tgt)
     loss.backward()
     def close(a, b, tol=3e-2):
         b = torch.tensor(b)
@@ -100,7 +100,7 @@ def test_against_reference_fixture(kind):
         assert (named[n].grad is None) == (gn is None), n
     model.eval()
     with torch.no_grad():
-        if kind in ("td", "tdo"):
+        if kind in ("td", "tdo", "tdo_v2"):
             model.reset_initial_state(img.shape[1])
         oe = model(img, None, x0)
     oe = list(oe) if isinstance(oe, tuple) else [oe]

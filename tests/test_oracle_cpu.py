@@ -45,7 +45,7 @@ def test_survey_appendix_c_values():
     assert torch.isnan(nan)
 
 
-@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n"])
+@pytest.mark.parametrize("kind", ["no", "tdo", "td", "n", "tdo_v2"])
 def test_forward_backward_golden(kind):
     """Oracle forward / loss / gradients / BN running stats / eval outputs == reference fixtures."""
     import model_checks as mc
@@ -58,7 +58,7 @@ def test_forward_backward_golden(kind):
         orc.sd[k].requires_grad_(True)
     out = orc.forward(img, x0, training=True)
     outs = list(out) if isinstance(out, tuple) else [out]
-    loss = po.pose_loss(outs[0], tgt, **lk) if kind in ("no", "tdo") else \
+    loss = po.pose_loss(outs[0], tgt, **lk) if kind in ("no", "tdo", "tdo_v2") else \
         po.pose_loss(outs[0], x0, **lk) + po.pose_loss(outs[1], tgt, **lk)
     loss.backward()
     for o, g in zip(outs, fx["outputs"]):
@@ -98,7 +98,7 @@ def test_adam_loss_curve_golden():
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
-@pytest.mark.parametrize("kind", ["no", "tdo"])
+@pytest.mark.parametrize("kind", ["no", "tdo", "tdo_v2"])
 def test_oracle_vs_live_reference(kind):
     """Direct comparison with the unmodified reference modules (build container only)."""
     ref = ref_shim.load()
@@ -107,7 +107,7 @@ def test_oracle_vs_live_reference(kind):
     shape = dict(n=2) if kind == "no" else dict(n=2, s=2)
     img, x0, tgt = po.synthetic_batch(kind, seed=3, **shape)
     m.train()
-    if kind == "tdo":
+    if kind in ("tdo", "tdo_v2"):
         m.reset_initial_state(2)
     with ref_shim.quiet():
         want = m(img, None, x0)
