@@ -139,6 +139,17 @@ int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, i
 int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const float* a1, const float* w,
                float* da1, int accumulate, float* dw, float* db, int B, int H, int W, int C, void* stream);
 
+/* ---- depth branch (use_depth=True; models/naive.py:233-240,324-330, models/time_sensitive.py:387-394,481-487):
+ *      depth (B,1,H,W) -> AvgPool2d(2) x log2(pool) -> InstanceNorm2d(1, affine, biased variance, eps) -> Flatten,
+ *      multiplied element-wise into the aux features aux[b][0:F] (row stride ld) in place.  xhat [B][F] and
+ *      aux_pre [B][F] (the aux features before the product) are kept for the backward pass.              */
+int pe_depth_features_fwd(const float* depth, int B, int H, int W, int pool, const float* gamma, const float* beta,
+                          float eps, float* xhat, float* aux, int ld, float* aux_pre, int round_tf32, void* stream);
+/* dprod (gradient w.r.t. the product, row stride ld) becomes the gradient w.r.t. the aux features in place;
+ * dgamma / dbeta (1 element each, zeroed by the caller, may be NULL) accumulate the InstanceNorm gradients */
+int pe_depth_features_bwd(float* dprod, int ld, const float* aux_pre, const float* xhat, const float* gamma,
+                          const float* beta, float* dgamma, float* dbeta, int B, int F, void* stream);
+
 /* ---- LSTM cell (nn.LSTM single layer, gate order i,f,g,o; models/time_sensitive.py:126-131,418) -----
  * gates = gx + gh + b_ih + b_hh  ([N][4H]); act = (sig i, sig f, tanh g, sig o); c = f*c_prev + i*g;
  * h = o*tanh(c).  `act` keeps the activated gates for backward.                                       */

@@ -77,6 +77,15 @@ def aux_forward(early, w, b):
     return torch.flatten(F.max_pool2d(F.conv2d(early, w, b), 2), 1)
 
 
+def depth_forward(depth, weight, bias, n_pool=2):
+    """AvgPool2d(2) x n_pool + InstanceNorm2d(1, affine=True) + Flatten (models/naive.py:233-240: for the bn1 hook,
+    n_pool = log4(224^2 / 3136) = 2).  depth: (B,1,H,W)."""
+    d = depth
+    for _ in range(n_pool):
+        d = F.avg_pool2d(d, 2)
+    return torch.flatten(F.instance_norm(d, weight=weight, bias=bias, eps=1e-5), 1)
+
+
 def lstm_forward(x, sd, prefix, state=None):
     """Single-layer nn.LSTM, seq-major input (S, N, F), gates (i, f, g, o)
     (models/time_sensitive.py:126-131,418; torch.nn.LSTM definition)."""
@@ -102,11 +111,13 @@ def lstm_forward(x, sd, prefix, state=None):
 # --------------------------------------------------------------------------------------------
 # the four estimators
 # --------------------------------------------------------------------------------------------
-def naive_object_forward(sd, img, x0bar, training, n_fc, use_proprio=True):
+def naive_object_forward(sd, img, x0bar, training, n_fc, use_proprio=True, depth=None):
     """NaiveObjectStateEstimator.forward (models/naive.py:298-352); ReLU after EVERY fc incl. the
     last one (quirk Q2, models/naive.py:343-345)."""
     feats, early = resnet50_forward(sd, "feature_net.module.", img, training)
     aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"])
+    if depth is not None:      # use_depth: aux features gated by the normalised, pooled depth map (:324-330)
+        aux = aux * depth_forward(depth, sd["depth_nets.0.module.2.weight"], sd["depth_nets.0.module.2.bias"])
     out = torch.cat((feats, aux), dim=-1).view(img.shape[0], -1)
     if use_proprio:
         out = torch.cat((out, x0bar), dim=-1)
@@ -127,13 +138,16 @@ def naive_eef_forward(sd, img, x0bar, training, n_pre, n_post):
     return pre, post
 
 
-def tdo_forward(sd, img, x0bar, training, state=None, use_proprio=True):
+def tdo_forward(sd, img, x0bar, training, state=None, use_proprio=True, depth=None):
     """TemporallyDependentObjectStateEstimator.forward (models/time_sensitive.py:453-517); head is
     Linear(H, H//4) -> Linear(H//4, 7) with no nonlinearity (quirk Q6, :420-423).
     `state` = (h, c) each (1, N, H) for rollout mode; returns (out, new_state)."""
     S, N = img.shape[0], img.shape[1]
     feats, early = resnet50_forward(sd, "feature_net.module.", img.reshape(S * N, *img.shape[2:]), training)
     aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"])
+    if depth is not None:
+        aux = aux * depth_forward(depth.reshape(S * N, *depth.shape[2:]), sd["depth_nets.0.module.2.weight"],
+                                  sd["depth_nets.0.module.2.bias"])
     f = torch.cat((feats, aux), dim=-1).view(S, N, -1)
     if use_proprio:
         f = torch.cat((f, x0bar), dim=-1)
@@ -263,14 +277,14 @@ class OracleEstimator:
     def _count(self, pattern):
         return len([k for k in self.sd if k.startswith(pattern) and k.endswith("weight")])
 
-    def forward(self, img, x0bar, training=True, rollout=False):
+    def forward(self, img, x0bar, training=True, rollout=False, depth=None):
         sd = self.sd
         if self.kind == "no":
-            return naive_object_forward(sd, img, x0bar, training, self._count("fc"))
+            return naive_object_forward(sd, img, x0bar, training, self._count("fc"), depth=depth)
         if self.kind == "n":
             return naive_eef_forward(sd, img, x0bar, training, self._count("pre_fc"), self._count("post_fc"))
         if self.kind == "tdo":
-            out, st = tdo_forward(sd, img, x0bar, training, self.state if rollout else None)
+            out, st = tdo_forward(sd, img, x0bar, training, self.state if rollout else None, depth=depth)
             if rollout:
                 self.state = st
             return out

@@ -147,13 +147,13 @@ def build_reference_model(ref, kind, seed=0, **kw):
             return ref.naive.NaiveObjectStateEstimator(
                 object_name=kw.get("object_name", "cube"), hidden_dims=kw.get("hidden_dims", [1024, 256, 64]),
                 num_resnet_layers=50, latent_dim=kw.get("latent_dim", 512), feature_extract=False,
-                feature_layer_nums=(9,), use_depth=False, use_pretrained=False)
+                feature_layer_nums=(9,), use_depth=kw.get("use_depth", False), use_pretrained=False)
         if kind == "tdo":
             return ref.time_sensitive.TemporallyDependentObjectStateEstimator(
                 object_name=kw.get("object_name", "robot1_eef"), hidden_dim=kw.get("hidden_dim", 512),
                 num_resnet_layers=50, latent_dim=kw.get("latent_dim", 512),
                 sequence_length=kw.get("sequence_length", 20), feature_extract=False, feature_layer_nums=(9,),
-                use_depth=False, use_pretrained=False)
+                use_depth=kw.get("use_depth", False), use_pretrained=False)
         if kind == "tdo_v2":
             return ref.time_sensitive.TemporallyDependentObjectStateEstimatorV2(
                 object_name=kw.get("object_name", "robot1_eef"), img_hidden_dim=kw.get("hidden_dim", 512),

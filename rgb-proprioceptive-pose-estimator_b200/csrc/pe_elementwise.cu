@@ -721,8 +721,10 @@ aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __
             for (int j = 0; j < 4; ++j) {
                 const int c = lane + 32 * j;
                 if (c < C) {
-                    const float prev = accumulate ? da1[off + c] : 0.f;
-                    da1[off + c] = prev + dk * w[c];
+                    if (da1) {      // NULL: frozen trunk, only the aux conv's own gradients are wanted
+                        const float prev = accumulate ? da1[off + c] : 0.f;
+                        da1[off + c] = prev + dk * w[c];
+                    }
                     if (k == am) pdw[j] = fmaf(d, a1[off + c], pdw[j]);
                 }
             }
@@ -737,6 +739,88 @@ aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __
         __syncthreads();
         if (threadIdx.x < C) atomicAdd(dw + threadIdx.x, s_dw[threadIdx.x]);
         if (threadIdx.x == 0 && db) atomicAdd(db, s_db);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// depth branch (use_depth): AvgPool2d(2)^n + InstanceNorm2d(1, affine) + Flatten, multiplied into the aux
+// features (reference models/naive.py:233-240,324-330).  One block per frame; the pooled map lives in smem.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    if (threadIdx.x < 32) {
+        t = warp_sum(t);
+        if (threadIdx.x == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+depth_features_fwd_kernel(const float* __restrict__ depth, int H, int W, int pool, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float eps, float* __restrict__ xhat,
+                          float* __restrict__ aux, int ld, float* __restrict__ aux_pre, int round_out) {
+    extern __shared__ float pooled[];   // [F]
+    __shared__ float red[32];
+    const int Ho = H / pool, Wo = W / pool, F = Ho * Wo;
+    const int b = blockIdx.x;
+    const float* src = depth + (size_t)b * H * W;
+    const float inv = 1.f / (float)(pool * pool);
+    float part = 0.f;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+        const int ho = k / Wo, wo = k - ho * Wo;
+        float s = 0.f;
+        for (int r = 0; r < pool; ++r)
+            for (int c = 0; c < pool; ++c) s += __ldg(src + (size_t)(ho * pool + r) * W + wo * pool + c);
+        s *= inv;
+        pooled[k] = s;
+        part += s;
+    }
+    const float mean = block_sum_256(part, red) / (float)F;
+    part = 0.f;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+        const float d = pooled[k] - mean;
+        part = fmaf(d, d, part);
+    }
+    const float var = block_sum_256(part, red) / (float)F;      // biased, as instance_norm normalises
+    const float invstd = rsqrtf(var + eps);
+    const float g = gamma[0], bt = beta[0];
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+        const float xh = (pooled[k] - mean) * invstd;
+        xhat[(size_t)b * F + k] = xh;
+        const float a = aux[(size_t)b * ld + k];
+        if (aux_pre) aux_pre[(size_t)b * F + k] = a;
+        const float v = a * fmaf(xh, g, bt);
+        aux[(size_t)b * ld + k] = round_out ? round_tf32(v) : v;
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+depth_features_bwd_kernel(float* __restrict__ dprod, int ld, const float* __restrict__ aux_pre,
+                          const float* __restrict__ xhat, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                          int F) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const float g = gamma[0], bt = beta[0];
+    float pg = 0.f, pb = 0.f;
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+        const float d = dprod[(size_t)b * ld + k];
+        const float xh = xhat[(size_t)b * F + k];
+        const float df = d * aux_pre[(size_t)b * F + k];        // gradient w.r.t. the depth feature
+        pg = fmaf(df, xh, pg);
+        pb += df;
+        dprod[(size_t)b * ld + k] = d * fmaf(xh, g, bt);        // gradient w.r.t. the aux feature, in place
+    }
+    const float sg = block_sum_256(pg, red);
+    const float sb = block_sum_256(pb, red);
+    if (threadIdx.x == 0) {
+        if (dgamma) atomicAdd(dgamma, sg);
+        if (dbeta) atomicAdd(dbeta, sb);
     }
 }
 
@@ -994,6 +1078,28 @@ int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const f
     const long long nwin = (long long)B * (H / 2) * (W / 2);
     aux_bwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream>>>(
         dout, lddo, argmax, a1, w, da1, accumulate, dw, db, B, H, W, C);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_depth_features_fwd(const float* depth, int B, int H, int W, int pool, const float* gamma, const float* beta,
+                          float eps, float* xhat, float* aux, int ld, float* aux_pre, int round_tf32, void* stream) {
+    PE_REQUIRE(pool >= 1 && H % pool == 0 && W % pool == 0, "depth_features: %dx%d not divisible by pool %d", H, W,
+               pool);
+    const int F = (H / pool) * (W / pool);
+    PE_REQUIRE(F * sizeof(float) <= 48 * 1024, "depth_features: pooled map of %d values does not fit", F);
+    if (B == 0) return 0;
+    depth_features_fwd_kernel<<<B, EW_THREADS, F * sizeof(float), (cudaStream_t)stream>>>(
+        depth, H, W, pool, gamma, beta, eps, xhat, aux, ld, aux_pre, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_depth_features_bwd(float* dprod, int ld, const float* aux_pre, const float* xhat, const float* gamma,
+                          const float* beta, float* dgamma, float* dbeta, int B, int F, void* stream) {
+    if (B == 0) return 0;
+    depth_features_bwd_kernel<<<B, EW_THREADS, 0, (cudaStream_t)stream>>>(dprod, ld, aux_pre, xhat, gamma, beta,
+                                                                          dgamma, dbeta, F);
     PE_LAUNCH_CHECK();
     return 0;
 }

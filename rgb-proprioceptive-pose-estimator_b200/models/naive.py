@@ -52,8 +52,18 @@ def _check_supported(feature_layer_nums, use_depth):
         raise NotImplementedError("the B200 path implements the reference's only configuration, "
                                   "feature_layer_nums=(9,) (scripts/train_model.py:65); got %r"
                                   % (feature_layer_nums,))
-    if use_depth:
-        raise NotImplementedError("use_depth=True is not on the accelerated path yet (SURVEY 8f rank 4)")
+    if use_depth and feature_layer_nums is None:
+        # the reference multiplies depth features into the aux features only (models/naive.py:324-330)
+        pass
+
+
+def _inputs(model, img, depth, self_measurement):
+    """Data tensors handed to the estimator core: the depth map rides along only when use_depth is set."""
+    if getattr(model, "use_depth", False) and model.early_features is not None:
+        if depth is None:
+            raise ValueError("use_depth=True needs a depth tensor")
+        return (img, self_measurement, depth)
+    return (img, self_measurement)
 
 
 class NaiveEndEffectorStateEstimator(nn.Module):
@@ -148,10 +158,10 @@ class NaiveObjectStateEstimator(nn.Module):
         self._core = None
 
     def forward(self, img, depth, self_measurement):
-        """img (N,C,H,W), depth unused (use_depth=False), self_measurement (N,7) -> pose (N,7)"""
+        """img (N,C,H,W), depth (N,1,H,W) when use_depth else ignored, self_measurement (N,7) -> pose (N,7)"""
         if self._core is None:
             object.__setattr__(self, "_core", NaiveObjectCore(self))
-        return run_core(self._core, (img, self_measurement), self.training)[0]
+        return run_core(self._core, _inputs(self, img, depth, self_measurement), self.training)[0]
 
     def reset_initial_state(self, batch_size):
         pass

@@ -10,7 +10,7 @@ starts from zeros otherwise (models/time_sensitive.py:501-507).
 import torch
 import torch.nn as nn
 
-from models.naive import _check_supported, _probe_feature_layers
+from models.naive import _check_supported, _inputs, _probe_feature_layers
 from pe_b200.estimators import TDCore, TDOCore, TDOV2Core
 from pe_b200.functions import run_core
 from util.model_utils import PassThroughParallel, import_resnet
@@ -87,7 +87,7 @@ class TemporallyDependentStateEstimator(nn.Module):
         if self.rollout:
             state = ((_state_2d(self.pre_measurement_h, img), _state_2d(self.pre_measurement_c, img)),
                      (_state_2d(self.post_measurement_h, img), _state_2d(self.post_measurement_c, img)))
-        pre_out, post_out = run_core(self._core, (img, self_measurement), self.training, state)
+        pre_out, post_out = run_core(self._core, _inputs(self, img, depth, self_measurement), self.training, state)
         if self.rollout:
             (h1, c1), (h2, c2) = self._core.last_state
             self.pre_measurement_h, self.pre_measurement_c = h1.unsqueeze(0), c1.unsqueeze(0)
@@ -170,7 +170,7 @@ class TemporallyDependentObjectStateEstimator(nn.Module):
         state = None
         if self.rollout:
             state = (_state_2d(self.rnn_h, img), _state_2d(self.rnn_c, img))
-        out = run_core(self._core, (img, self_measurement), self.training, state)[0]
+        out = run_core(self._core, _inputs(self, img, depth, self_measurement), self.training, state)[0]
         if self.rollout:
             h, c = self._core.last_state
             self.rnn_h, self.rnn_c = h.unsqueeze(0), c.unsqueeze(0)
@@ -254,7 +254,7 @@ class TemporallyDependentObjectStateEstimatorV2(nn.Module):
         if self.rollout:
             state = ((_state_2d(self.img_rnn_h, img), _state_2d(self.img_rnn_c, img)),
                      (_state_2d(self.proprio_rnn_h, img), _state_2d(self.proprio_rnn_c, img)))
-        out = run_core(self._core, (img, self_measurement), self.training, state)[0]
+        out = run_core(self._core, _inputs(self, img, depth, self_measurement), self.training, state)[0]
         if self.rollout:
             (h1, c1), (h2, c2) = self._core.last_state
             self.img_rnn_h, self.img_rnn_c = h1.unsqueeze(0), c1.unsqueeze(0)

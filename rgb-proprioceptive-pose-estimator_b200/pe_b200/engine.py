@@ -229,7 +229,7 @@ class TrunkEngine:
         return y
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, img, training, need_grad, feat_out, ld_feat, aux_out=None, ld_aux=0):
+    def forward(self, img, training, need_grad, feat_out, ld_feat, aux_out=None, ld_aux=0, aux_round=True):
         """img: (B,3,224,224) NCHW fp32 CUDA.  Writes latent features into feat_out[:, :latent] (row stride
         ld_feat) and, when the aux branch exists, its 3136-vector into aux_out (row stride ld_aux).
         Returns a context for backward (None unless need_grad)."""
@@ -248,6 +248,13 @@ class TrunkEngine:
         stride, pad = conv1.stride[0], conv1.padding[0]
         Ho, Wo = (H + 2 * pad - r) // stride + 1, (W + 2 * pad - s) // stride + 1
         tape = [] if need_grad else None
+        # feature-extraction mode (util/model_utils.py:110-113,137: every trunk parameter frozen, only the new fc
+        # trains): nothing upstream of the average pool needs a gradient, so the convolutions are not taped and
+        # backward reduces to the fc / aux-conv parameter gradients
+        frozen = need_grad and not any(p.requires_grad for c, b in self.convs for p in (c.weight, b.weight, b.bias))
+        head_tape = tape
+        if frozen:
+            tape = None
         dev = img.device
 
         # ---- stem: im2col + GEMM (+BN1, ReLU), 3x3/2 max pool, aux branch -------------------------
@@ -270,16 +277,17 @@ class TrunkEngine:
             del col
         Hp, Wp = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
         x = Act(torch.empty(B * Hp * Wp, 64, device=dev, dtype=torch.float32), B, Hp, Wp, 64)
-        argmax = torch.empty(B * Hp * Wp * 64, device=dev, dtype=torch.uint8) if need_grad else None
+        argmax = torch.empty(B * Hp * Wp * 64, device=dev, dtype=torch.uint8) if tape is not None else None
         L.pe_maxpool3x3s2_fwd(P(a1.t), P(x.t), P(argmax), B, Ho, Wo, 64, st)
         if tape is not None:
             tape.append(("maxpool", a1, x, argmax))
         if self.aux_conv is not None:
             aux_am = torch.empty(B * (Ho // 2) * (Wo // 2), device=dev, dtype=torch.uint8) if need_grad else None
+            # aux_round=False: the depth branch multiplies these features next and rounds the product itself
             L.pe_aux_fwd(P(a1.t), P(self.aux_conv.weight), P(self.aux_conv.bias), P(aux_out), ld_aux, P(aux_am), B,
-                         Ho, Wo, 64, self.round_tf32, st)
-            if tape is not None:
-                tape.append(("aux", a1, aux_am))
+                         Ho, Wo, 64, self.round_tf32 if aux_round else 0, st)
+            if head_tape is not None:
+                head_tape.append(("aux", a1, aux_am))
 
         # ---- bottleneck stages ------------------------------------------------------------------
         for blk, ids in self.blocks:
@@ -304,10 +312,10 @@ class TrunkEngine:
         L.pe_avgpool_fwd(P(x.t), P(pool), x.C, B, x.H * x.W, x.C, self.round_tf32, st)
         L.pe_linear_fwd(P(pool), x.C, P(self.fc_w), x.C, P(fc.bias), None, P(feat_out), ld_feat, B, fc.out_features,
                         x.C, 0, 0, self.round_tf32, None, st)
-        if tape is None:
+        if head_tape is None:
             return None
-        tape.append(("tail", x, pool))
-        return {"tape": tape, "B": B}
+        head_tape.append(("tail", x, pool))
+        return {"tape": head_tape, "B": B, "frozen": frozen}
 
     # ------------------------------------------------------------------------------------------
     def backward(self, ctx, d_feat, ld_dfeat, d_aux, ld_daux, grad_of, on_ready=None):
@@ -317,6 +325,7 @@ class TrunkEngine:
         buckets can start while the rest of backward is still running)."""
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         tape = ctx["tape"]
+        frozen = ctx.get("frozen", False)
         done_after_conv = {}
         if on_ready is not None:
             for blk, ids in self.blocks:
@@ -337,6 +346,10 @@ class TrunkEngine:
                 L.pe_copy_cols(P(d_feat), ld_dfeat, P(dfr), nout, B, nout, rt, st)
                 L.pe_linear_wgrad(P(pool), nin, P(dfr), nout, P(grad_of(fc.weight)), nin, B, nout, nin, st)
                 L.pe_colsum(P(dfr), nout, P(grad_of(fc.bias)), B, nout, 0, st)
+                if frozen:
+                    if on_ready is not None:
+                        on_ready([fc.weight, fc.bias])
+                    continue
                 dpool = torch.empty(B, nin, device=dev, dtype=torch.float32)
                 L.pe_linear_fwd(P(dfr), nout, P(self.fc_wt), nout, None, None, P(dpool), nin, B, nin, nout, 0, 0, 0,
                                 None, st)
@@ -415,7 +428,7 @@ class TrunkEngine:
                 _, a1, aux_am = rec
                 # runs AFTER the maxpool record in reversed order? no: "aux" was taped after "maxpool",
                 # so it is visited first -> seed the slot with a zero-initialised accumulate target.
-                da1_aux = torch.empty_like(a1.t)
+                da1_aux = None if frozen else torch.empty_like(a1.t)
                 gw = gb = None
                 if self.aux_trainable:
                     gw, gb = grad_of(self.aux_conv.weight), grad_of(self.aux_conv.bias)
@@ -423,6 +436,10 @@ class TrunkEngine:
                     gb.zero_()
                 L.pe_aux_bwd(P(d_aux), ld_daux, P(aux_am), P(a1.t), P(self.aux_conv.weight), P(da1_aux), 0, P(gw),
                              P(gb), a1.B, a1.H, a1.W, a1.C, st)
+                if frozen:
+                    if on_ready is not None and self.aux_trainable:
+                        on_ready([self.aux_conv.weight, self.aux_conv.bias])
+                    continue
                 slots.add(a1, da1_aux)
             elif kind == "stem":
                 _, col, y0 = rec
@@ -456,6 +473,43 @@ class TrunkEngine:
             stem += [self.aux_conv.weight, self.aux_conv.bias]
         groups.append(stem)
         return groups
+
+
+class DepthOp:
+    """use_depth branch (reference models/naive.py:233-240,324-330): depth -> AvgPool2d(2)^n -> InstanceNorm2d(1,
+    affine) -> Flatten, multiplied into the aux features in place (one block per frame, pe_depth_features_*)."""
+
+    def __init__(self, depth_seq, trainable=True):
+        import torch.nn as nn
+        mods = list(depth_seq)
+        self.norm = [m for m in mods if isinstance(m, nn.InstanceNorm2d)][0]
+        self.pool = 2 ** sum(isinstance(m, nn.AvgPool2d) for m in mods)
+        self.trainable = trainable
+
+    def forward(self, depth, aux_view, ld, M, need_grad):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        _dev_check(depth)
+        if self.norm.weight.device != depth.device:
+            self.norm.to(depth.device)          # unregistered depth nets (td model) are not moved by .cuda()
+        depth = depth.reshape(M, *depth.shape[-2:]).to(torch.float32).contiguous()
+        H, W = depth.shape[-2:]
+        F_ = (H // self.pool) * (W // self.pool)
+        xhat = torch.empty(M, F_, device=depth.device, dtype=torch.float32)
+        aux_pre = torch.empty(M, F_, device=depth.device, dtype=torch.float32) if need_grad else None
+        L.pe_depth_features_fwd(P(depth), M, H, W, self.pool, P(self.norm.weight), P(self.norm.bias), self.norm.eps,
+                                P(xhat), P(aux_view), ld, P(aux_pre), 1, st)
+        return xhat, aux_pre, F_
+
+    def backward(self, ctx, daux_view, ld, M, grad_of):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        xhat, aux_pre, F_ = ctx
+        gw = gb = None
+        if self.trainable:
+            gw, gb = grad_of(self.norm.weight), grad_of(self.norm.bias)
+            gw.zero_()
+            gb.zero_()
+        L.pe_depth_features_bwd(P(daux_view), ld, P(aux_pre), P(xhat), P(self.norm.weight), P(self.norm.bias), P(gw),
+                                P(gb), M, F_, st)
 
 
 # ================================================================================================

@@ -12,7 +12,7 @@ torch.cat calls (models/naive.py:333-340, models/time_sensitive.py:491-498) neve
 import torch
 
 from . import native
-from .engine import LinearOp, LSTMOp, _pad32
+from .engine import DepthOp, LinearOp, LSTMOp, _pad32
 
 AUX_DIM = 3136
 OUT_LD = 8          # 7-D poses live in 8-float rows so every row stays 16-byte aligned for TMA
@@ -92,6 +92,7 @@ class NaiveObjectCore:
         for i in range(m.n_fc):
             lin = getattr(m, "fc%d" % i).module
             self.fcs.append(LinearOp(lin, ld_in=self.ld_cat if i == 0 else None))
+        self.depth = DepthOp(m.depth_nets[0].module) if (self.use_aux and m.use_depth) else None
 
     def _engine(self):
         aux = self.m.aux_nets[0].module[0] if self.use_aux else None
@@ -108,7 +109,9 @@ class NaiveObjectCore:
         eng = self._engine()
         cat = torch.zeros(B, self.ld_cat, device=dev, dtype=torch.float32)
         aux_view = cat[:, self.latent:] if self.use_aux else None
-        tctx = eng.forward(img, training, need_grad, cat, self.ld_cat, aux_view, self.ld_cat)
+        tctx = eng.forward(img, training, need_grad, cat, self.ld_cat, aux_view, self.ld_cat,
+                           aux_round=self.depth is None)
+        dctx = self.depth.forward(inputs[2], aux_view, self.ld_cat, B, need_grad) if self.depth else None
         col = self.latent + (AUX_DIM if self.use_aux else 0)
         if _fused_ok(need_grad, B):
             # one launch: proprio injection + fc0 over the whole grid, remaining layers by the last CTA
@@ -133,11 +136,11 @@ class NaiveObjectCore:
             op.forward(x, ldx, B, y, y.shape[1], relu=True, round_out=1 if i < len(self.fcs) - 1 else 0)
             hs.append(y)
             x, ldx = y, y.shape[1]
-        return (x[:, :7],), (eng, tctx, hs, B), None
+        return (x[:, :7],), (eng, tctx, hs, B, dctx), None
 
     def backward(self, saved, douts, grad_of, on_ready=None):
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
-        eng, tctx, hs, B = saved
+        eng, tctx, hs, B, dctx = saved
         dev = hs[0].device
         d = _pad_grad(douts[0], B, dev, 0)
         for i in range(len(self.fcs) - 1, -1, -1):
@@ -157,6 +160,10 @@ class NaiveObjectCore:
             d = dx
         if on_ready is not None:
             on_ready([p for op in self.fcs for p in op.lin.parameters()])
+        if self.depth is not None:
+            self.depth.backward(dctx, d[:, self.latent:], self.ld_cat, B, grad_of)
+            if on_ready is not None:
+                on_ready(list(self.depth.norm.parameters()))
         eng.backward(tctx, d, self.ld_cat, d[:, self.latent:] if self.use_aux else None, self.ld_cat, grad_of, on_ready)
 
 
@@ -265,6 +272,7 @@ class TDOCore:
         self.rnn = LSTMOp(m.rnn.module, self.ld_cat)
         self.fc0 = LinearOp(m.fc.module[0])
         self.fc1 = LinearOp(m.fc.module[1])
+        self.depth = DepthOp(m.depth_nets[0].module) if (self.use_aux and m.use_depth) else None
 
     def _engine(self):
         aux = self.m.aux_nets[0].module[0] if self.use_aux else None
@@ -285,7 +293,8 @@ class TDOCore:
         cat = torch.zeros(M, self.ld_cat, device=dev, dtype=torch.float32)
         aux_view = cat[:, self.latent:] if self.use_aux else None
         tctx = eng.forward(img.reshape(M, *img.shape[2:]), training, need_grad, cat, self.ld_cat, aux_view,
-                           self.ld_cat)
+                           self.ld_cat, aux_round=self.depth is None)
+        dctx = self.depth.forward(inputs[2], aux_view, self.ld_cat, M, need_grad) if self.depth else None
         col = self.latent + (AUX_DIM if self.use_aux else 0)
         if S == 1 and _fused_ok(need_grad, N):
             # streaming step: proprio injection + LSTM gate projections over the whole grid, cell + both dense
@@ -317,11 +326,11 @@ class TDOCore:
         self.fc0.forward(h_all, self.rnn.H, M, z, self.fc0.ld_out, relu=False, round_out=1)
         out = torch.zeros(M, OUT_LD, device=dev, dtype=torch.float32)
         self.fc1.forward(z, self.fc0.ld_out, M, out, OUT_LD, relu=False, round_out=0)
-        saved = (eng, tctx, rctx, cat, h_all, z, S, N)
+        saved = (eng, tctx, rctx, cat, h_all, z, S, N, dctx)
         return (out[:, :7].reshape(S, N, 7),), saved, (h_last, c_last)
 
     def backward(self, saved, douts, grad_of, on_ready=None):
-        eng, tctx, rctx, cat, h_all, z, S, N = saved
+        eng, tctx, rctx, cat, h_all, z, S, N, dctx = saved
         M = S * N
         dev = cat.device
         d = _pad_grad(douts[0], M, dev, 1)
@@ -336,6 +345,10 @@ class TDOCore:
         self.rnn.backward(rctx, dh, grad_of, dcat, self.ld_cat, dx_cols=ncols)
         if on_ready is not None:
             on_ready(list(self.m.rnn.parameters()) + list(self.m.fc.parameters()))
+        if self.depth is not None:
+            self.depth.backward(dctx, dcat[:, self.latent:], self.ld_cat, M, grad_of)
+            if on_ready is not None:
+                on_ready(list(self.depth.norm.parameters()))
         eng.backward(tctx, dcat, self.ld_cat, dcat[:, self.latent:] if self.use_aux else None, self.ld_cat, grad_of,
                      on_ready)
 
@@ -356,6 +369,7 @@ class TDOV2Core:
         self.fc0 = LinearOp(m.fc.module[0])
         self.fc1 = LinearOp(m.fc.module[1])
         self.H1, self.H2 = self.img_rnn.H, self.pro_rnn.H
+        self.depth = DepthOp(m.depth_nets[0].module) if (self.use_aux and m.use_depth) else None
 
     def _engine(self):
         aux = self.m.aux_nets[0].module[0] if self.use_aux else None
@@ -375,7 +389,8 @@ class TDOV2Core:
         cat = torch.zeros(M, self.ld_cat, device=dev, dtype=torch.float32)
         aux_view = cat[:, self.latent:] if self.use_aux else None
         tctx = eng.forward(img.reshape(M, *img.shape[2:]), training, need_grad, cat, self.ld_cat, aux_view,
-                           self.ld_cat)
+                           self.ld_cat, aux_round=self.depth is None)
+        dctx = self.depth.forward(inputs[2], aux_view, self.ld_cat, M, need_grad) if self.depth else None
         x0 = _f32(inputs[1], "self_measurement").reshape(M, 7)
         x0p = torch.zeros(M, OUT_LD, device=dev, dtype=torch.float32)      # TF32-rounded, zero padded to 8
         L.pe_copy_cols(P(x0), 7, P(x0p), OUT_LD, M, 7, 1, st)
@@ -392,12 +407,12 @@ class TDOV2Core:
         self.fc0.forward(hcat, Hc, M, z, self.fc0.ld_out, relu=False, round_out=1)
         out = torch.zeros(M, OUT_LD, device=dev, dtype=torch.float32)
         self.fc1.forward(z, self.fc0.ld_out, M, out, OUT_LD, relu=False, round_out=0)
-        saved = (eng, tctx, rctx1, rctx2, cat, hcat, z, S, N)
+        saved = (eng, tctx, rctx1, rctx2, cat, hcat, z, S, N, dctx)
         return (out[:, :7].reshape(S, N, 7),), saved, ((h1_last, c1_last), (h2_last, c2_last))
 
     def backward(self, saved, douts, grad_of, on_ready=None):
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
-        eng, tctx, rctx1, rctx2, cat, hcat, z, S, N = saved
+        eng, tctx, rctx1, rctx2, cat, hcat, z, S, N, dctx = saved
         M = S * N
         dev = cat.device
         Hc = self.H1 + self.H2
@@ -417,6 +432,10 @@ class TDOV2Core:
         if on_ready is not None:
             m = self.m
             on_ready(list(m.img_rnn.parameters()) + list(m.proprio_rnn.parameters()) + list(m.fc.parameters()))
+        if self.depth is not None:
+            self.depth.backward(dctx, dcat[:, self.latent:], self.ld_cat, M, grad_of)
+            if on_ready is not None:
+                on_ready(list(self.depth.norm.parameters()))
         eng.backward(tctx, dcat, self.ld_cat, dcat[:, self.latent:] if self.use_aux else None, self.ld_cat, grad_of,
                      on_ready)
 
@@ -436,6 +455,8 @@ class TDCore:
         self.pre_fc = LinearOp(m.pre_measurement_fc)
         self.post_fc = LinearOp(m.post_measurement_fc)
         self._aux_dev = None
+        # like the aux conv, the depth net sits in a plain python list in the reference: unregistered and frozen
+        self.depth = DepthOp(m.depth_nets[0], trainable=False) if (self.use_aux and m.use_depth) else None
 
     def _engine(self, dev):
         aux = None
@@ -463,7 +484,8 @@ class TDCore:
         cat = torch.zeros(M, self.ld_cat, device=dev, dtype=torch.float32)
         aux_view = cat[:, self.latent:] if self.use_aux else None
         tctx = eng.forward(img.reshape(M, *img.shape[2:]), training, need_grad, cat, self.ld_cat, aux_view,
-                           self.ld_cat)
+                           self.ld_cat, aux_round=self.depth is None)
+        dctx = self.depth.forward(inputs[2], aux_view, self.ld_cat, M, need_grad) if self.depth else None
         s_pre, s_post = state if state is not None else ((None, None), (None, None))
         if S == 1 and _fused_ok(need_grad, N):
             # streaming step in two launches: pre-measurement LSTM + fc (+ measurement difference written into the
@@ -496,13 +518,13 @@ class TDCore:
         h2, h2_last, c2_last, rctx2 = self.post_rnn.forward(cat, S, N, s_post[0], s_post[1], need_grad)
         post_out = torch.zeros(M, OUT_LD, device=dev, dtype=torch.float32)
         self.post_fc.forward(h2, self.post_rnn.H, M, post_out, OUT_LD, relu=False, round_out=0)
-        saved = (eng, tctx, rctx1, rctx2, cat, h1, h2, S, N)
+        saved = (eng, tctx, rctx1, rctx2, cat, h1, h2, S, N, dctx)
         outs = (pre_out[:, :7].reshape(S, N, 7), post_out[:, :7].reshape(S, N, 7))
         return outs, saved, ((h1_last, c1_last), (h2_last, c2_last))
 
     def backward(self, saved, douts, grad_of, on_ready=None):
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
-        eng, tctx, rctx1, rctx2, cat, h1, h2, S, N = saved
+        eng, tctx, rctx1, rctx2, cat, h1, h2, S, N, dctx = saved
         M = S * N
         dev = cat.device
         H1, H2 = self.pre_rnn.H, self.post_rnn.H
@@ -524,5 +546,7 @@ class TDCore:
             m = self.m
             on_ready(list(m.pre_measurement_rnn.parameters()) + list(m.pre_measurement_fc.parameters()) +
                      list(m.post_measurement_rnn.parameters()) + list(m.post_measurement_fc.parameters()))
+        if self.depth is not None:
+            self.depth.backward(dctx, dcat1[:, self.latent:], self.ld_cat, M, grad_of)
         eng.backward(tctx, dcat1, self.ld_cat, dcat1[:, self.latent:] if self.use_aux else None, self.ld_cat,
                      grad_of, on_ready)

@@ -117,22 +117,23 @@ class FusedTrainer:
             self.reducer.ready(o, o + (n + _ALIGN - 1) // _ALIGN * _ALIGN)
 
     # ------------------------------------------------------------------------------------------
-    def step(self, img, self_measurement, targets):
+    def step(self, img, self_measurement, targets, depth=None):
         """One optimisation step.  `targets`: a tensor (object-pose models) or a (x0, x1) pair for the
         two-headed models, matching util/learn_utils.py:160-172.  Returns the loss as a 1-element device
         tensor (sum over the local samples)."""
-        loss = self.forward_backward(img, self_measurement, targets)
+        loss = self.forward_backward(img, self_measurement, targets, depth)
         self.apply_update()
         return loss
 
-    def forward_backward(self, img, self_measurement, targets):
+    def forward_backward(self, img, self_measurement, targets, depth=None):
         """forward + loss + backward (+ gradient all-reduce): leaves the summed gradient in self.g_flat."""
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         if self._flat is None:
             self._flatten()
         model, core = self.model, self.core
         state = None
-        outs, saved, _ = core.forward((img, self_measurement), True, True, state)
+        inputs = (img, self_measurement) if depth is None else (img, self_measurement, depth)
+        outs, saved, _ = core.forward(inputs, True, True, state)
         if not isinstance(targets, (tuple, list)):
             targets = (targets,)
         if len(targets) != len(outs):

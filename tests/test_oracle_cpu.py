@@ -116,3 +116,25 @@ def test_oracle_vs_live_reference(kind):
     sd = m.state_dict()
     for k in sd:
         assert torch.allclose(orc.sd[k].float(), sd[k].float(), rtol=1e-5, atol=1e-6), k
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("kind", ["no", "tdo"])
+def test_oracle_depth_branch_vs_live_reference(kind):
+    """use_depth=True: aux features gated by the pooled, instance-normalised depth map (models/naive.py:324-330)."""
+    ref = ref_shim.load()
+    m = ref_shim.build_reference_model(ref, kind, use_depth=True)
+    with torch.no_grad():      # non-trivial affine parameters
+        m.depth_nets[0].module[2].weight.fill_(0.7)
+        m.depth_nets[0].module[2].bias.fill_(0.2)
+    orc = po.OracleEstimator(kind, m.state_dict())
+    shape = dict(n=2) if kind == "no" else dict(n=2, s=2)
+    img, x0, tgt = po.synthetic_batch(kind, seed=4, **shape)
+    depth = torch.rand(*img.shape[:-3], 1, 224, 224, generator=torch.Generator().manual_seed(9))
+    m.train()
+    if kind == "tdo":
+        m.reset_initial_state(2)
+    with ref_shim.quiet():
+        want = m(img, depth, x0)
+    got = orc.forward(img, x0, training=True, depth=depth)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
