@@ -1,0 +1,45 @@
+"""Frame preprocessing on the GPU: the step that sits right before the hot path in both reference loops.
+
+The reference converts every rendered uint8 HWC frame on the CPU with a torchvision pipeline --
+ToPILImage -> Resize(256) -> CenterCrop(224) -> ToTensor -> Normalize(ImageNet mean / std)
+(util/data_utils.py:48-54, util/learn_utils.py:299-305).  robosuite renders 256 x 256 by default, for which
+Resize(256) is the identity, so the whole pipeline is one pass: crop, /255, normalise, HWC -> CHW.  That pass is
+`pe_preprocess_u8`; frames stay uint8 across PCIe (4x fewer bytes than fp32) and are expanded on the device.
+"""
+import ctypes
+
+import torch
+
+from . import native
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+class FramePreprocessor:
+    def __init__(self, crop=224, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        self.crop = crop
+        self._mean = (ctypes.c_float * 3)(*mean)
+        self._std = (ctypes.c_float * 3)(*std)
+
+    def __call__(self, frames_u8, out=None):
+        """frames_u8: uint8 CUDA tensor (..., Hs, Ws, 3) with Hs, Ws >= crop (256 x 256 renders in the reference);
+        returns / fills float32 (..., 3, crop, crop)."""
+        if frames_u8.dtype != torch.uint8:
+            raise native.PeError("raw frames must be uint8 (got %s)" % frames_u8.dtype)
+        if not frames_u8.is_cuda:
+            raise native.PeError("raw frames must be on the CUDA device: there is no CPU fallback")
+        if frames_u8.shape[-1] != 3:
+            raise native.PeError("raw frames must be HWC with 3 channels")
+        lead = frames_u8.shape[:-3]
+        Hs, Ws = frames_u8.shape[-3], frames_u8.shape[-2]
+        B = 1
+        for d in lead:
+            B *= d
+        src = frames_u8.contiguous()
+        if out is None:
+            out = torch.empty(*lead, 3, self.crop, self.crop, device=src.device, dtype=torch.float32)
+        native.lib().pe_preprocess_u8(native.ptr(src), native.ptr(out), B, Hs, Ws, self.crop,
+                                      ctypes.cast(self._mean, ctypes.c_void_p), ctypes.cast(self._std, ctypes.c_void_p),
+                                      native.stream_ptr())
+        return out

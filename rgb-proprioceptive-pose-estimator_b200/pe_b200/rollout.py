@@ -12,7 +12,9 @@ from .trainer import get_core
 
 
 class StreamingEstimator:
-    def __init__(self, model, batch_size=1, use_graph=True, device=None):
+    def __init__(self, model, batch_size=1, use_graph=True, device=None, raw_hw=None):
+        """raw_hw: side length of raw uint8 HWC frames (256 for robosuite's default render) when the caller wants
+        to hand over un-preprocessed frames with `step_raw`; crop / scale / normalise then run inside the graph."""
         self.model = model
         self.core = get_core(model)
         self.N = batch_size
@@ -25,6 +27,11 @@ class StreamingEstimator:
         self.img = torch.zeros(*lead, 3, 224, 224, device=self.dev)
         self.x0 = torch.zeros(*lead, 7, device=self.dev)
         self.state = self._zero_state()
+        self.raw = None
+        if raw_hw is not None:
+            from .preprocess import FramePreprocessor
+            self.raw = torch.zeros(*lead, raw_hw, raw_hw, 3, device=self.dev, dtype=torch.uint8)
+            self.pre = FramePreprocessor(crop=224)
         self.graph = None
         self.outs = None
         model.eval()
@@ -56,6 +63,8 @@ class StreamingEstimator:
 
     def _forward(self):
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        if self.raw is not None:
+            self.pre(self.raw, out=self.img)
         outs, _, new_state = self.core.forward((self.img, self.x0), False, False, self.state)
 
         def carry(dst, src):
@@ -98,11 +107,25 @@ class StreamingEstimator:
         r(self.state, saved)
 
     @torch.no_grad()
+    def step_raw(self, frames_u8, self_measurement):
+        """Raw uint8 HWC frames (N, raw_hw, raw_hw, 3) straight from the renderer + measurement (N,7)."""
+        if self.raw is None:
+            raise native.PeError("construct StreamingEstimator(..., raw_hw=256) to feed raw frames")
+        self.raw.copy_(frames_u8.reshape(self.raw.shape), non_blocking=True)
+        self.x0.copy_(self_measurement.reshape(self.x0.shape), non_blocking=True)
+        return self._run()
+
+    @torch.no_grad()
     def step(self, img, self_measurement):
         """img (N,3,224,224) [or (1,N,...)], self_measurement (N,7): host or device tensors.  Returns the
         pose estimate(s) as device tensors that stay valid until the next step."""
+        if self.raw is not None:
+            raise native.PeError("this estimator was built for raw frames: call step_raw")
         self.img.copy_(img.reshape(self.img.shape), non_blocking=True)
         self.x0.copy_(self_measurement.reshape(self.x0.shape), non_blocking=True)
+        return self._run()
+
+    def _run(self):
         if not self.use_graph:
             outs = self._forward()
         else:

@@ -550,6 +550,18 @@ def check_fused_head(n_rows, mode):
     return rows
 
 
+def check_preprocess(B):
+    """uint8 HWC 256x256 -> CenterCrop(224) -> /255 -> Normalize -> CHW fp32 (util/data_utils.py:48-54)."""
+    from pe_b200.preprocess import IMAGENET_MEAN, IMAGENET_STD, FramePreprocessor
+    g = torch.Generator(device=DEV).manual_seed(B)
+    raw = torch.randint(0, 256, (B, 256, 256, 3), device=DEV, dtype=torch.uint8, generator=g)
+    out = FramePreprocessor()(raw)
+    mean = torch.tensor(IMAGENET_MEAN, device=DEV).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, device=DEV).view(1, 3, 1, 1)
+    ref = (raw[:, 16:240, 16:240, :].permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    return [("preprocess_u8 B%d" % B, relerr(out, ref), 1e-6)]
+
+
 ALL = [
     lambda: check_linear(128, 128, 32, bias=False),
     lambda: check_linear(128, 128, 256),
@@ -583,6 +595,7 @@ ALL = [
     lambda: check_lstm_cell(5, 512),
     lambda: check_loss(37),
     lambda: check_adam(100003),
+    lambda: check_preprocess(3),
     lambda: check_fused_head(1, "mlp"),
     lambda: check_fused_head(8, "mlp"),
     lambda: check_fused_head(1, "lstm"),

@@ -363,3 +363,26 @@ def test_use_depth_parity(kind):
         assert mc.rel(oe, oe_ref) <= 5e-3, mc.rel(oe, oe_ref)
     finally:
         mu._RESNET_LAYERS[50] = [3, 4, 6, 3]
+
+
+def test_streaming_estimator_raw_frames():
+    """step_raw (uint8 HWC 256x256 frames, preprocessing inside the captured graph) == step on frames preprocessed
+    with the reference's transform arithmetic."""
+    from pe_b200.preprocess import IMAGENET_MEAN, IMAGENET_STD
+    from pe_b200.rollout import StreamingEstimator
+    mc.SHALLOW[0] = True
+    model = mc.build_model("tdo").cuda().eval()
+    raw_est = StreamingEstimator(model, batch_size=2, use_graph=True, raw_hw=256)
+    ref_est = StreamingEstimator(model, batch_size=2, use_graph=False)
+    raw_est.reset()
+    ref_est.reset()
+    g = torch.Generator().manual_seed(3)
+    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    for t in range(3):
+        raw = torch.randint(0, 256, (2, 256, 256, 3), dtype=torch.uint8, generator=g)
+        x0 = torch.randn(2, 7, generator=g)
+        img = (raw[:, 16:240, 16:240, :].permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+        a = raw_est.step_raw(raw.pin_memory(), x0.pin_memory()).clone()
+        b = ref_est.step(img.cuda(), x0.cuda()).clone()
+        assert mc.rel(a, b) <= 1e-5, (t, mc.rel(a, b))
