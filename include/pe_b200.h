@@ -61,6 +61,12 @@ int pe_pack_conv_weight(const float* w_oihw, float* w_tck, float* w_tkc, int Cou
                         int round_tf32, void* stream);
 int pe_unpack_conv_wgrad(const float* dw_tck, float* dw_oihw, int Cout, int Cin, int R, int S, int accumulate,
                          void* stream);
+/* every conv layer of a model in one launch.  table_dev: DEVICE array of n_layers rows of 8 int64:
+ * {w_oihw pointer, w_tck pointer, w_tkc pointer or 0, Cout, Cin, R*S, first block index, Cout*Cin*R*S};
+ * block b packs pe_pack_block_elems() consecutive elements of the layer with first block <= b            */
+int pe_pack_conv_weights_batched(const long long* table_dev, int n_layers, int total_blocks, int round_tf32,
+                                 void* stream);
+int pe_pack_block_elems(void);
 /* 7x7/2 stem (Cin = 3): NCHW image -> im2col rows [B*Ho*Wo][ldc], columns ordered (c, r, s) like OIHW */
 int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W, int R, int S, int stride,
                    int pad, int ldc, int round_tf32, void* stream);
@@ -129,13 +135,17 @@ int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, con
 /* ---- stem pooling + auxiliary BN1 branch (torchvision resnet.py:268-272; models/naive.py:223-231,
  *      models/time_sensitive.py:377-385: Conv2d(64,1,1) + MaxPool2d(2) + Flatten on post-ReLU bn1) -- */
 int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, int H, int W, int C, void* stream);
+/* aux_* (optional, all or none): the gradient of the aux branch, which reads the same activation, is added in the
+ * same pass -- da1 += [aux_argmax(window) == pixel] * aux_dout[b][window] * aux_w[c] -- so dx is written once  */
 int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* argmax, float* dx, int accumulate,
-                        int B, int H, int W, int C, void* stream);
+                        int B, int H, int W, int C, const float* aux_dout, int aux_lddo,
+                        const unsigned char* aux_argmax, const float* aux_w, void* stream);
 int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int round_tf32, void* stream);
 int pe_avgpool_bwd(const float* dy, int lddy, float* dx, int B, int HW, int C, void* stream);
 int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, int ldo, unsigned char* argmax,
                int B, int H, int W, int C, int round_tf32, void* stream);
-/* da1 (+)= scatter(dout) * w ; dw[C] += ..., db[1] += ... (dw/db may be NULL: frozen aux conv, td model) */
+/* da1 (+)= scatter(dout) * w (da1 may be NULL: the scatter is then left to pe_maxpool3x3s2_bwd's aux term);
+ * dw[C] += ..., db[1] += ... (dw/db may be NULL: frozen aux conv, td model) */
 int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const float* a1, const float* w,
                float* da1, int accumulate, float* dw, float* db, int B, int H, int W, int C, void* stream);
 

@@ -398,6 +398,42 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
     }
 }
 
+// All conv layers of a trunk in ONE launch: table rows = {src OIHW, tck, tkc (or 0), Cout, Cin, RS, first block,
+// elements}; every block handles PACK_PER_BLOCK consecutive tck-order elements of the layer it falls into.
+constexpr int PACK_PER_BLOCK = 2048;
+__global__ void __launch_bounds__(EW_THREADS)
+pack_weights_batched_kernel(const long long* __restrict__ table, int n_layers, int round_out) {
+    __shared__ int s_layer;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n_layers - 1;                     // last layer whose first block <= blockIdx.x
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid * 8 + 6] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        s_layer = lo;
+    }
+    __syncthreads();
+    const long long* row = table + s_layer * 8;
+    const float* __restrict__ w = reinterpret_cast<const float*>(row[0]);
+    float* __restrict__ tck = reinterpret_cast<float*>(row[1]);
+    float* __restrict__ tkc = reinterpret_cast<float*>(row[2]);
+    const int Cout = (int)row[3], Cin = (int)row[4], RS = (int)row[5];
+    const long long n = row[7];
+    const long long i0 = ((long long)blockIdx.x - row[6]) * PACK_PER_BLOCK;
+    for (int k = threadIdx.x; k < PACK_PER_BLOCK; k += EW_THREADS) {
+        const long long i = i0 + k;
+        if (i >= n) break;
+        const int ci = (int)(i % Cin);
+        const long long r = i / Cin;
+        const int co = (int)(r % Cout);
+        const int t = (int)(r / Cout);
+        float v = w[((long long)co * Cin + ci) * RS + t];
+        if (round_out) v = round_tf32(v);
+        tck[i] = v;
+        if (tkc) tkc[((long long)t * Cin + ci) * Cout + co] = v;
+    }
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ tck, float* __restrict__ w, int Cout, int Cin, int RS,
                                     int accumulate) {
     const long long n = (long long)Cout * Cin * RS;
@@ -578,7 +614,8 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned 
 __global__ void __launch_bounds__(EW_THREADS)
 maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
                    const unsigned char* __restrict__ argmax, float* __restrict__ dx, int accumulate, int B, int H,
-                   int W, int C, int Ho, int Wo) {
+                   int W, int C, int Ho, int Wo, const float* __restrict__ aux_dout, int aux_lddo,
+                   const unsigned char* __restrict__ aux_argmax, const float* __restrict__ aux_w) {
     const int G = C >> 2;
     const long long n = (long long)B * H * W * G;
     const long long gs = (long long)gridDim.x * blockDim.x;
@@ -610,6 +647,17 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
                 if (am.y == k) acc.y += d.y;
                 if (am.z == k) acc.z += d.z;
                 if (am.w == k) acc.w += d.w;
+            }
+        }
+        if (aux_dout) {
+            // second consumer of this activation: the aux branch (1x1 conv to one channel + 2x2 max pool); its
+            // gradient reaches only the arg-max pixel of each 2x2 window
+            const long long win = ((long long)b * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+            if (aux_argmax[win] == (unsigned char)(((h & 1) << 1) | (w & 1))) {
+                const float d = aux_dout[(long long)b * aux_lddo + (h >> 1) * (W >> 1) + (w >> 1)];
+                const float4 w4 = ld4(aux_w + 4 * g);
+                acc.x = fmaf(d, w4.x, acc.x); acc.y = fmaf(d, w4.y, acc.y);
+                acc.z = fmaf(d, w4.z, acc.z); acc.w = fmaf(d, w4.w, acc.w);
             }
         }
         st4(dx + 4 * i, acc);
@@ -654,90 +702,122 @@ avgpool_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ d
 // ---------------------------------------------------------------------------------------------
 // auxiliary branch: per-pixel <a1[pixel,:], w> + bias, 2x2 max pool, flatten.  One warp per window.
 // ---------------------------------------------------------------------------------------------
+// Aux branch: Conv2d(C,1,1) + MaxPool2d(2).  A half-warp owns one 2x2 window: lane (l & 15) holds channels
+// 4*(l&15) + 64*j, so every pixel is one coalesced 256-byte read per 64 channels and the dot product closes with
+// four shuffles inside the half-warp.
 __global__ void __launch_bounds__(EW_THREADS)
 aux_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ w, const float* __restrict__ bias,
                float* __restrict__ out, int ldo, unsigned char* __restrict__ argmax, int B, int H, int W, int C,
                int round_out) {
     const int Ho = H >> 1, Wo = W >> 1;
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long nwin = (long long)B * Ho * Wo;
+    const long long npair = (nwin + 1) >> 1;
     const float b0 = bias[0];
-    for (long long win = warp; win < nwin; win += nwarps) {
-        const int wo = (int)(win % Wo);
-        const int ho = (int)((win / Wo) % Ho);
-        const int b = (int)(win / ((long long)Wo * Ho));
-        float best = 0.f;
-        int besti = -1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int h = 2 * ho + (k >> 1), x = 2 * wo + (k & 1);
-            const float* p = a1 + (((long long)b * H + h) * W + x) * C;
-            float s = 0.f;
-            for (int c = lane; c < C; c += 32) s = fmaf(p[c], w[c], s);
-            s = warp_sum(s) + b0;
-            if (besti < 0 || s > best) {
-                best = s;
-                besti = k;
-            }
+    for (long long pair = gwarp; pair < npair; pair += nwarps) {       // warp-uniform trip count
+        const long long win = pair * 2 + half;
+        const bool valid = win < nwin;
+        const long long wv = valid ? win : 0;
+        const int wo = (int)(wv % Wo);
+        const int ho = (int)((wv / Wo) % Ho);
+        const int b = (int)(wv / ((long long)Wo * Ho));
+        const float* p0 = a1 + (((long long)b * H + 2 * ho) * W + 2 * wo) * C;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int c = 4 * hl; c < C; c += 64) {
+            const float4 w4 = ld4(w + c);
+            const float4 v0 = ld4_stream(p0 + c), v1 = ld4_stream(p0 + C + c);
+            const float4 v2 = ld4_stream(p0 + (long long)W * C + c), v3 = ld4_stream(p0 + (long long)W * C + C + c);
+            s0 += v0.x * w4.x + v0.y * w4.y + v0.z * w4.z + v0.w * w4.w;
+            s1 += v1.x * w4.x + v1.y * w4.y + v1.z * w4.z + v1.w * w4.w;
+            s2 += v2.x * w4.x + v2.y * w4.y + v2.z * w4.z + v2.w * w4.w;
+            s3 += v3.x * w4.x + v3.y * w4.y + v3.z * w4.z + v3.w * w4.w;
         }
-        if (lane == 0) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        }
+        if (hl == 0 && valid) {
+            // first maximum wins ties, like torch's max_pool2d
+            float best = s0;
+            int besti = 0;
+            if (s1 > best) { best = s1; besti = 1; }
+            if (s2 > best) { best = s2; besti = 2; }
+            if (s3 > best) { best = s3; besti = 3; }
+            best += b0;
             out[(long long)b * ldo + ho * Wo + wo] = round_out ? round_tf32(best) : best;
             if (argmax) argmax[win] = (unsigned char)besti;
         }
     }
 }
 
+// Aux-branch backward.  da1 (optional): gradient scattered to the arg-max pixel of every window (zeros elsewhere);
+// dw / db (optional): the 1x1 conv's own gradients, which only need a1 at the arg-max pixels.
 __global__ void __launch_bounds__(EW_THREADS)
 aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __restrict__ argmax,
                const float* __restrict__ a1, const float* __restrict__ w, float* __restrict__ da1, int accumulate,
                float* __restrict__ dw, float* __restrict__ db, int B, int H, int W, int C) {
-    // C <= 64*? : each lane owns channels lane, lane+32, ... ; dw partials kept per lane (C <= 128)
-    __shared__ float s_dw[128];
+    __shared__ float s_dw[256];
     __shared__ float s_db;
     const int Ho = H >> 1, Wo = W >> 1;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x < 128) s_dw[threadIdx.x] = 0.f;
+    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_dw[i] = 0.f;
     if (threadIdx.x == 0) s_db = 0.f;
     __syncthreads();
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long nwin = (long long)B * Ho * Wo;
-    float pdw[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 pdw[4];                                  // channels 4*hl + 64*j, j < 4  (C <= 256)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pdw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     float pdb = 0.f;
-    for (long long win = warp; win < nwin; win += nwarps) {
+    for (long long win = gwarp * 2 + half; win < nwin; win += nwarps * 2) {
         const int wo = (int)(win % Wo);
         const int ho = (int)((win / Wo) % Ho);
         const int b = (int)(win / ((long long)Wo * Ho));
         const float d = dout[(long long)b * lddo + ho * Wo + wo];
         const int am = argmax[win];
+        const long long base = (((long long)b * H + 2 * ho) * W + 2 * wo) * C;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int h = 2 * ho + (k >> 1), x = 2 * wo + (k & 1);
-            const long long off = (((long long)b * H + h) * W + x) * C;
-            const float dk = (k == am) ? d : 0.f;
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * hl + 64 * j;
+            if (c < C) {
+                if (da1) {
+                    const float4 w4 = ld4(w + c);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = lane + 32 * j;
-                if (c < C) {
-                    if (da1) {      // NULL: frozen trunk, only the aux conv's own gradients are wanted
-                        const float prev = accumulate ? da1[off + c] : 0.f;
-                        da1[off + c] = prev + dk * w[c];
+                    for (int k = 0; k < 4; ++k) {
+                        const long long off = base + ((long long)(k >> 1) * W + (k & 1)) * C + c;
+                        const float dk = (k == am) ? d : 0.f;
+                        float4 r = accumulate ? ld4(da1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        r.x += dk * w4.x; r.y += dk * w4.y; r.z += dk * w4.z; r.w += dk * w4.w;
+                        st4(da1 + off, r);
                     }
-                    if (k == am) pdw[j] = fmaf(d, a1[off + c], pdw[j]);
+                }
+                if (dw) {
+                    const float4 av = ld4_stream(a1 + base + ((long long)(am >> 1) * W + (am & 1)) * C + c);
+                    pdw[j].x = fmaf(d, av.x, pdw[j].x); pdw[j].y = fmaf(d, av.y, pdw[j].y);
+                    pdw[j].z = fmaf(d, av.z, pdw[j].z); pdw[j].w = fmaf(d, av.w, pdw[j].w);
                 }
             }
         }
-        pdb += d;
+        if (hl == 0) pdb += d;
     }
     if (dw) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (lane + 32 * j < C) atomicAdd(&s_dw[lane + 32 * j], pdw[j]);
-        if (lane == 0) atomicAdd(&s_db, pdb);
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * hl + 64 * j;
+            if (c < C) {
+                atomicAdd(&s_dw[c], pdw[j].x); atomicAdd(&s_dw[c + 1], pdw[j].y);
+                atomicAdd(&s_dw[c + 2], pdw[j].z); atomicAdd(&s_dw[c + 3], pdw[j].w);
+            }
+        }
+        if (hl == 0) atomicAdd(&s_db, pdb);
         __syncthreads();
-        if (threadIdx.x < C) atomicAdd(dw + threadIdx.x, s_dw[threadIdx.x]);
+        for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dw + c, s_dw[c]);
         if (threadIdx.x == 0 && db) atomicAdd(db, s_db);
     }
 }
@@ -937,6 +1017,16 @@ int pe_pack_conv_weight(const float* w_oihw, float* w_tck, float* w_tkc, int Cou
     return 0;
 }
 
+int pe_pack_conv_weights_batched(const long long* table_dev, int n_layers, int total_blocks, int round_tf32,
+                                 void* stream) {
+    if (n_layers <= 0 || total_blocks <= 0) return 0;
+    pack_weights_batched_kernel<<<total_blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(table_dev, n_layers, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_pack_block_elems(void) { return PACK_PER_BLOCK; }
+
 int pe_unpack_conv_wgrad(const float* dw_tck, float* dw_oihw, int Cout, int Cin, int R, int S, int accumulate,
                          void* stream) {
     const long long n = (long long)Cout * Cin * R * S;
@@ -1035,12 +1125,15 @@ int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, 
 }
 
 int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* argmax, float* dx, int accumulate,
-                        int B, int H, int W, int C, void* stream) {
+                        int B, int H, int W, int C, const float* aux_dout, int aux_lddo,
+                        const unsigned char* aux_argmax, const float* aux_w, void* stream) {
     PE_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
+    PE_REQUIRE(!aux_dout || (aux_argmax && aux_w && H % 2 == 0 && W % 2 == 0),
+               "maxpool_bwd: the aux term needs its arg-max map, weights and even H, W");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * H * W * (C / 4);
     maxpool_bwd_kernel<<<grid_for(n, EW_THREADS, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dy, dy2, argmax, dx, accumulate, B, H, W, C, Ho, Wo);
+        dy, dy2, argmax, dx, accumulate, B, H, W, C, Ho, Wo, aux_dout, aux_lddo, aux_argmax, aux_w);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1064,9 +1157,9 @@ int pe_avgpool_bwd(const float* dy, int lddy, float* dx, int B, int HW, int C, v
 
 int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, int ldo, unsigned char* argmax, int B,
                int H, int W, int C, int round_tf32, void* stream) {
-    PE_REQUIRE(H % 2 == 0 && W % 2 == 0, "aux: H, W must be even");
+    PE_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "aux: H, W must be even and C a multiple of 4");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    aux_fwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 4, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    aux_fwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 2 * 4, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
         a1, w, bias, out, ldo, argmax, B, H, W, C, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
@@ -1074,9 +1167,9 @@ int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, i
 
 int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const float* a1, const float* w, float* da1,
                int accumulate, float* dw, float* db, int B, int H, int W, int C, void* stream) {
-    PE_REQUIRE(C <= 128, "aux_bwd: C <= 128 required");
+    PE_REQUIRE(C <= 256 && C % 4 == 0, "aux_bwd: C <= 256, C %% 4 == 0 required");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    aux_bwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    aux_bwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream>>>(
         dout, lddo, argmax, a1, w, da1, accumulate, dw, db, B, H, W, C);
     PE_LAUNCH_CHECK();
     return 0;

@@ -95,6 +95,7 @@ class TrunkEngine:
         self._dev = None
         self._packed_version = None
         self._eval_version = None
+        self._pack_key = None
         self.round_tf32 = 1
 
     # ------------------------------------------------------------------------------------------
@@ -123,6 +124,7 @@ class TrunkEngine:
         self.fc_wt = torch.empty(fc.in_features, fc.out_features, **f32)
         self._packed_version = None
         self._eval_version = None
+        self._pack_key = None
 
     def _weights(self):
         return [c.weight for c, _ in self.convs] + [self.net.fc.weight]
@@ -138,15 +140,29 @@ class TrunkEngine:
         if ver == self._packed_version and not force:
             return
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
-        for i, (conv, _) in enumerate(self.convs):
-            w = conv.weight
-            _dev_check(w)
-            co, ci, r, s = w.shape
-            if i == 0:
-                L.pe_copy_cols(P(w), ci * r * s, P(self.w_tck[0]), 160, co, ci * r * s, self.round_tf32, st)
-            else:
-                L.pe_pack_conv_weight(P(w), P(self.w_tck[i]), P(self.w_tkc[i]) if need_dgrad else None, co, ci, r, s,
-                                      self.round_tf32, st)
+        w0 = self.convs[0][0].weight
+        _dev_check(w0)
+        co, ci, r, s = w0.shape
+        L.pe_copy_cols(P(w0), ci * r * s, P(self.w_tck[0]), 160, co, ci * r * s, self.round_tf32, st)
+        # all bottleneck convs in one launch; the pointer table is rebuilt only when a parameter moved
+        key = (tuple(c.weight.data_ptr() for c, _ in self.convs[1:]), need_dgrad)
+        if self._pack_key != key:
+            per = L.pe_pack_block_elems()
+            rows, blk = [], 0
+            for i, (conv, _) in enumerate(self.convs):
+                if i == 0:
+                    continue
+                w = conv.weight
+                _dev_check(w)
+                co, ci, r, s = w.shape
+                n = co * ci * r * s
+                rows.append([P(w), P(self.w_tck[i]), P(self.w_tkc[i]) if need_dgrad else 0, co, ci, r * s, blk, n])
+                blk += (n + per - 1) // per
+            self._pack_table = torch.tensor(rows, dtype=torch.int64).to(w0.device)
+            self._pack_blocks = blk
+            self._pack_key = key
+        L.pe_pack_conv_weights_batched(P(self._pack_table), self._pack_table.shape[0], self._pack_blocks,
+                                       self.round_tf32, st)
         fc = self.net.fc
         L.pe_copy_cols(P(fc.weight), fc.in_features, P(self.fc_w), fc.in_features, fc.out_features, fc.in_features,
                        self.round_tf32, st)
@@ -332,6 +348,7 @@ class TrunkEngine:
                 done_after_conv[ids[1]] = [p for p in blk.parameters()]
         B = ctx["B"]
         slots = GradSlots()
+        pending_aux = None
         dev = self.scale.device
         self.sums.zero_()
         rt = self.round_tf32
@@ -422,25 +439,28 @@ class TrunkEngine:
                 _, a1, x, argmax = rec
                 d1, d2 = slots.pop_plain(x, 2)
                 da1 = torch.empty_like(a1.t)
-                L.pe_maxpool3x3s2_bwd(P(d1), P(d2), P(argmax), P(da1), 0, a1.B, a1.H, a1.W, a1.C, st)
+                # the aux branch reads the same activation: its gradient is scattered in the same pass
+                ad, ald, aam = pending_aux if pending_aux is not None else (None, 0, None)
+                L.pe_maxpool3x3s2_bwd(P(d1), P(d2), P(argmax), P(da1), 0, a1.B, a1.H, a1.W, a1.C, P(ad), ald, P(aam),
+                                      P(self.aux_conv.weight) if ad is not None else None, st)
+                pending_aux = None
                 slots.add(a1, da1)
             elif kind == "aux":
                 _, a1, aux_am = rec
-                # runs AFTER the maxpool record in reversed order? no: "aux" was taped after "maxpool",
-                # so it is visited first -> seed the slot with a zero-initialised accumulate target.
-                da1_aux = None if frozen else torch.empty_like(a1.t)
-                gw = gb = None
+                # taped after "maxpool", hence visited first in the reversed walk
                 if self.aux_trainable:
                     gw, gb = grad_of(self.aux_conv.weight), grad_of(self.aux_conv.bias)
                     gw.zero_()
                     gb.zero_()
-                L.pe_aux_bwd(P(d_aux), ld_daux, P(aux_am), P(a1.t), P(self.aux_conv.weight), P(da1_aux), 0, P(gw),
-                             P(gb), a1.B, a1.H, a1.W, a1.C, st)
+                    # the 1x1 conv's own gradients (reads a1 at the arg-max pixels only); the scatter into da1 is
+                    # fused into the max-pool backward below
+                    L.pe_aux_bwd(P(d_aux), ld_daux, P(aux_am), P(a1.t), P(self.aux_conv.weight), None, 0, P(gw),
+                                 P(gb), a1.B, a1.H, a1.W, a1.C, st)
                 if frozen:
                     if on_ready is not None and self.aux_trainable:
                         on_ready([self.aux_conv.weight, self.aux_conv.bias])
                     continue
-                slots.add(a1, da1_aux)
+                pending_aux = (d_aux, ld_daux, aux_am)
             elif kind == "stem":
                 _, col, y0 = rec
                 dy, = slots.pop_plain(y0, 1)

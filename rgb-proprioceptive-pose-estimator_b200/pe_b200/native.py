@@ -67,6 +67,10 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+# entry points whose int return value is a VALUE, not a status code
+_VALUE_RETURNING = ("pe_version", "pe_device_error", "pe_pack_block_elems", "pe_head_desc_size")
+
+
 class PeError(RuntimeError):
     pass
 
@@ -85,7 +89,7 @@ class _Lib:
             fn.argtypes = argtypes
         for name, (restype, _) in self.protos.items():
             raw = getattr(self._dll, name)
-            if restype is ctypes.c_int and name not in ("pe_version", "pe_device_error"):
+            if restype is ctypes.c_int and name not in _VALUE_RETURNING:
                 setattr(self, name, self._checked(name, raw))
             else:
                 setattr(self, name, raw)

@@ -319,7 +319,7 @@ def check_pools(B):
     L.pe_maxpool3x3s2_fwd(P(xn), P(y), P(am), B, 112, 112, 64, S())
     out.append(("maxpool fwd B%d" % B, relerr(y, nhwc(yd.detach())), 0.0))
     dx = torch.full((B, 112, 112, 64), float("nan"), device=DEV)
-    L.pe_maxpool3x3s2_bwd(P(nhwc(dyv.float())), None, P(am), P(dx), 0, B, 112, 112, 64, S())
+    L.pe_maxpool3x3s2_bwd(P(nhwc(dyv.float())), None, P(am), P(dx), 0, B, 112, 112, 64, None, 0, None, None, S())
     # ties only happen at 0 where the ReLU mask kills the gradient anyway -> compare on x > 0
     mask = (xn > 0).double()
     out.append(("maxpool bwd B%d" % B, relerr(dx.double() * mask, nhwc(gx) * mask), 1e-6))
@@ -356,6 +356,14 @@ def check_pools(B):
     do[:, :3136] = dref.float()
     L.pe_aux_bwd(P(do), ldo, P(am2), P(a1n), P(w), P(da1), 0, P(dw), P(db), B, 112, 112, 64, S())
     out.append(("aux bwd da1 B%d" % B, relerr(da1, nhwc(ga)), 1e-5))
+    # fused stem backward: max-pool gradient + aux gradient written in one pass == sum of the two separate ones
+    dsum = torch.full((B, 112, 112, 64), float("nan"), device=DEV)
+    L.pe_maxpool3x3s2_bwd(P(nhwc(dyv.float())), None, P(am), P(dsum), 0, B, 112, 112, 64, P(do), ldo, P(am2), P(w), S())
+    out.append(("maxpool bwd + aux term B%d" % B, relerr(dsum, dx.double() + nhwc(ga)), 1e-5))
+    dw_only = torch.zeros(64, device=DEV)
+    db_only = torch.zeros(1, device=DEV)
+    L.pe_aux_bwd(P(do), ldo, P(am2), P(a1n), P(w), None, 0, P(dw_only), P(db_only), B, 112, 112, 64, S())
+    out.append(("aux bwd dw (no da1) B%d" % B, relerr(dw_only, gw_.flatten()), 1e-4))
     out.append(("aux bwd dw B%d" % B, relerr(dw, gw_.flatten()), 1e-4))
     out.append(("aux bwd db B%d" % B, relerr(db, gb), 1e-4))
     return out
