@@ -38,6 +38,8 @@ void pe_debug_max_bn(int bn);
 void pe_debug_wgrad_halo(int mode);
 /* debug: 0 = epilogue reads residual rows with plain global loads instead of TMA-prefetched tiles */
 void pe_debug_residual_tma(int on);
+/* debug: force the number of epilogue warp groups of the tap-GEMM (2 or 4); 0 = automatic */
+void pe_debug_epilogue_groups(int groups);
 
 /* ---- convolutions: torchvision resnet.py:143-163,266-282 Conv2d calls reached from
  *      models/naive.py:316 and models/time_sensitive.py:185,472 (bias-free, NHWC here) ------------

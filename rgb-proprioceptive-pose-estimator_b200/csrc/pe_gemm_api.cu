@@ -158,6 +158,7 @@ static void init_params(TapParams& p) {
 
 static int g_dbg_max_bn = 256;
 static int g_dbg_res_tma = 1;
+static int g_dbg_epi_groups = 0;      // 0 = automatic, 2 / 4 = forced
 static int pick_bn(int n_total) {
     if (n_total >= 256 && g_dbg_max_bn >= 256) return 256;
     return n_total >= 128 ? 128 : ((n_total + 15) / 16) * 16;
@@ -171,8 +172,12 @@ static void pick_pipeline(TapParams& p, int ksteps) {
     // residual tiles are prefetched by TMA (two 16 KB buffers per epilogue group) when the output goes out by TMA
     p.nres = (p.residual && p.store_mode == TG_STORE_TMA && g_dbg_res_tma) ? 4 : 0;
     const int budget = TG_SMEM_BYTES - (p.stats ? 2 * p.stats_cols * (int)sizeof(float) + 8192 : 0) - p.nres * TG_A_BYTES;
-    // (two epilogue groups: the staging buffers are split evenly between them)
-    int nout = (p.store_mode == TG_STORE_TMA) ? (ksteps >= 24 ? 2 : 4) : 0;
+    // Store-bound launches (training-mode conv with batch statistics, wide tile, short K loop) are limited by the
+    // epilogue's instruction latency, not by HBM: they run four epilogue groups (16 warps) instead of two.
+    p.epi_groups = (g_dbg_epi_groups == 4 || (g_dbg_epi_groups == 0 && p.stats && p.store_mode == TG_STORE_TMA &&
+                                              p.bn >= 128 && ksteps < 24 && !p.residual)) ? 4 : 2;
+    // (the staging buffers are split evenly between the epilogue groups)
+    int nout = (p.store_mode == TG_STORE_TMA) ? (p.epi_groups == 4 ? 4 : (ksteps >= 24 ? 2 : 4)) : 0;
     if (p.nres && p.bn > 128) nout = 2;
     if (g_dbg_nout > 0 && p.store_mode == TG_STORE_TMA) nout = g_dbg_nout;
     int stages = (budget - nout * TG_A_BYTES) / p.stage_bytes;
@@ -629,6 +634,8 @@ void pe_debug_max_bn(int bn) { g_dbg_max_bn = bn > 0 ? bn : 256; }
 void pe_debug_wgrad_halo(int mode) { g_dbg_wgrad_halo = mode; }
 
 void pe_debug_residual_tma(int on) { g_dbg_res_tma = on; }
+
+void pe_debug_epilogue_groups(int groups) { g_dbg_epi_groups = groups; }
 
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
     g_dbg_desc[0] = a_lbo;

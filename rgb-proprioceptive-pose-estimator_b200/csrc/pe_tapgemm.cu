@@ -89,14 +89,16 @@ __device__ __forceinline__ void issue_halo_stage(uint32_t tmem_d, uint32_t bn, u
     }
 }
 
-__global__ void __launch_bounds__(TG_THREADS, 1)
+template <int G>      // epilogue groups (2 or 4)
+__global__ void __launch_bounds__(64 + 128 * G, 1)
 tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ TapParams p) {
+    constexpr int EPI_THREADS = 128 * G;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_full[TG_STAGES];
     __shared__ __align__(8) uint64_t s_empty[TG_STAGES];
     __shared__ __align__(8) uint64_t s_tmem_full[2];
     __shared__ __align__(8) uint64_t s_tmem_empty[2];
-    __shared__ __align__(8) uint64_t s_res_full[4];
+    __shared__ __align__(8) uint64_t s_res_full[2 * G];
     __shared__ uint32_t s_tmem_base;
     __shared__ __align__(16) float s_scale[TG_MAX_BN];
     __shared__ __align__(16) float s_shift[TG_MAX_BN];
@@ -113,7 +115,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     const uint32_t res_base = stage_base + p.nout * TG_A_BYTES;          // nres x 16 KB residual tiles
     float* s_sum = reinterpret_cast<float*>(smem_raw + p.stages * p.stage_bytes + (p.nout + p.nres) * TG_A_BYTES);
     float* s_sq = s_sum + p.stats_cols;
-    // per-tile scratch of the statistics: [group 2][chunk 4][warp 4][sum 32 | sq 32] (8 KB, only with stats)
+    // per-tile scratch of the statistics: [group][chunk slot][warp 4][sum 32 | sq 32] (8 KB, only with stats)
     float* s_part = s_sum + 2 * p.stats_cols;
 
     // ---- one-time setup --------------------------------------------------------------------
@@ -122,10 +124,10 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             mbar_init(smem_u32(&s_full[s]), 1);
             mbar_init(smem_u32(&s_empty[s]), 1);
         }
-        for (int a = 0; a < 4; ++a) mbar_init(smem_u32(&s_res_full[a]), 1);
+        for (int a = 0; a < 2 * G; ++a) mbar_init(smem_u32(&s_res_full[a]), 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&s_tmem_full[a]), 1);
-            mbar_init(smem_u32(&s_tmem_empty[a]), 256);
+            mbar_init(smem_u32(&s_tmem_empty[a]), EPI_THREADS);
         }
         fence_mbar_init();
     }
@@ -386,10 +388,12 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         const int q = warp & 3;            // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;     // tile row == TMEM lane
         const int et = (ew & 3) * 32 + lane;      // 0..127 within the group
-        const int eall = ew * 32 + lane;          // 0..255 over both groups
-        const int bar_id = 1 + grp;
-        const int nbuf = p.nout >> 1 > 0 ? p.nout >> 1 : 1;      // staging buffers per group
-        const uint32_t my_stage = stage_base + (p.nout >= 2 ? grp * nbuf : 0) * TG_A_BYTES;
+        const int eall = ew * 32 + lane;          // 0..EPI_THREADS-1 over all groups
+        const int bar_id = 1 + grp;               // named barriers 1..G: one per group; G+1: all epilogue threads
+        constexpr int BAR_ALL = G + 1;
+        constexpr int SLOTS = (TG_MAX_BN / 32 + G - 1) / G;      // chunks of one tile a group can own
+        const int nbuf = p.nout / G > 0 ? p.nout / G : 1;        // staging buffers per group
+        const uint32_t my_stage = stage_base + (p.nout >= G ? grp * nbuf : 0) * TG_A_BYTES;
         const bool affine = (p.scale != nullptr) || (p.bias != nullptr);
         uint32_t tile_i = 0, cc = 0;
         bool ok = true;
@@ -407,7 +411,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             const uint32_t bar = smem_u32(&s_res_full[grp * 2 + buf]);
             mbar_arrive_expect_tx(bar, static_cast<uint32_t>(p.m_rows) * 128u);
             tma_load_4d(my_res + buf * TG_A_BYTES, &maps.r, bar, w2.nt * p.bn + pc * 32, o2.w0, o2.h0, o2.n0);
-            pc += 2;
+            pc += G;
             if (pc >= res_chunks) {
                 pc = grp;
                 pw += gridDim.x;
@@ -418,8 +422,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             res_issue(1);
         }
         if (p.stats) {
-            for (int cidx = eall; cidx < 2 * p.stats_cols; cidx += 256) s_sum[cidx] = 0.f;
-            asm volatile("bar.sync 3, 256;" ::: "memory");
+            for (int cidx = eall; cidx < 2 * p.stats_cols; cidx += EPI_THREADS) s_sum[cidx] = 0.f;
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_ALL), "n"(EPI_THREADS) : "memory");
         }
         for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
             const Work wk = decode_work(p, w);
@@ -430,8 +434,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 
             // per-tile column constants (everyone is past the previous tile's reads after this barrier)
             if (affine) {
-                asm volatile("bar.sync 3, 256;" ::: "memory");
-                for (int cidx = eall; cidx < p.bn; cidx += 256) {
+                asm volatile("bar.sync %0, %1;" ::"n"(BAR_ALL), "n"(EPI_THREADS) : "memory");
+                for (int cidx = eall; cidx < p.bn; cidx += EPI_THREADS) {
                     const int col = n_off + cidx;
                     float sc = 1.f, sh = 0.f;
                     if (col < p.n_total) {
@@ -445,7 +449,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     s_scale[cidx] = sc;
                     s_shift[cidx] = sh;
                 }
-                asm volatile("bar.sync 3, 256;" ::: "memory");
+                asm volatile("bar.sync %0, %1;" ::"n"(BAR_ALL), "n"(EPI_THREADS) : "memory");
             }
 
             if (wk.nk > 0) {
@@ -485,9 +489,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             const int nchunks = p.mode == 2 ? chunks_per_tap * min(p.tg_taps, p.n_taps - wk.tap) : chunks_per_tap;
             float* const out_row0 = out_row;
             int last_c = -1;                       // last chunk this group reads from TMEM
-            for (int c = grp; c < nchunks; c += 2) last_c = c;
+            for (int c = grp; c < nchunks; c += G) last_c = c;
             if (last_c < 0 && wk.nk > 0) mbar_arrive(smem_u32(&s_tmem_empty[acc]));
-            for (int c = grp; c < nchunks; c += 2) {
+            for (int c = grp; c < nchunks; c += G) {
                 float v[32];
                 if (wk.nk > 0) {
                     tmem_ld_32x32(tmem_base + acc * TG_MAX_BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
@@ -650,7 +654,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         // per-warp partials go to the tile scratch; they are folded once per tile (below) by threads
                         // that own their columns exclusively -- no shared-memory atomics on the per-chunk path
                         if (lane < 8) {
-                            float* dst = s_part + (((grp * 4 + (c >> 1)) * 4 + (ew & 3)) << 6) + cg * 4;
+                            float* dst = s_part + (((grp * SLOTS + c / G) * 4 + (ew & 3)) << 6) + cg * 4;
                             *reinterpret_cast<float4*>(dst) = sm;
                             *reinterpret_cast<float4*>(dst + 32) = sq;
                         }
@@ -685,13 +689,13 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                 // fold this tile's per-warp partials into the CTA-wide sums: (group, chunk, column) -> unique owner
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < (SLOTS * 64 + 127) / 128; ++h) {
                     const int idx = et + h * 128;
                     const int ci = idx >> 6, k = idx & 63;
-                    const int c = 2 * ci + grp;
+                    const int c = G * ci + grp;
                     const int col = n_off + c * 32 + (k & 31);
-                    if (c < nchunks && col < p.n_total) {
-                        const float* src = s_part + ((grp * 4 + ci) << 8) + k;
+                    if (ci < SLOTS && c < nchunks && col < p.n_total) {
+                        const float* src = s_part + ((grp * SLOTS + ci) << 8) + k;
                         const float t = (src[0] + src[64]) + (src[128] + src[192]);
                         float* dst = (k < 32 ? s_sum : s_sq) + col;
                         *dst += t;
@@ -700,8 +704,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             }
         }
         if (p.stats) {
-            asm volatile("bar.sync 3, 256;" ::: "memory");
-            for (int col = eall; col < p.n_total; col += 256) {
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_ALL), "n"(EPI_THREADS) : "memory");
+            for (int col = eall; col < p.n_total; col += EPI_THREADS) {
                 atomicAdd(p.stats + col, static_cast<double>(s_sum[col]));
                 atomicAdd(p.stats + p.n_total + col, static_cast<double>(s_sq[col]));
             }
@@ -723,16 +727,22 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TG_SMEM_BYTES));
+        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TG_SMEM_BYTES));
         configured = true;
     }
+    if (p.epi_groups != 4) p.epi_groups = 2;
     p.work_n = work.x;
     p.work_m = work.y;
     p.work_total = static_cast<int>(work.x * work.y * work.z);
     int grid = p.work_total < num_sms() ? p.work_total : num_sms();
     if (grid < 1) return 0;
-    tapgemm_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, stream>>>(maps, p);
+    if (p.epi_groups == 4)
+        tapgemm_kernel<4><<<grid, 64 + 128 * 4, TG_SMEM_BYTES, stream>>>(maps, p);
+    else
+        tapgemm_kernel<2><<<grid, 64 + 128 * 2, TG_SMEM_BYTES, stream>>>(maps, p);
     PE_LAUNCH_CHECK();
     return 0;
 }

@@ -24,7 +24,8 @@ constexpr int TG_STAGES = 6;                    // maximum ring depth (runtime: 
 constexpr int TG_A_BYTES = TG_BM * 128;        // 16 KB
 constexpr int TG_B_BYTES = TG_MAX_BN * 128;    // 32 KB (16 KB when bn <= 128: TapParams::stage_bytes)
 constexpr int TG_SMEM_BYTES = 223 * 1024;       // ring (stages x 32|48 KB) + store staging (nout x 16 KB)
-constexpr int TG_THREADS = 320;                // TMA warp + MMA warp + 2 epilogue groups of 4 warps
+constexpr int TG_THREADS = 320;                // TMA warp + MMA warp + 2 epilogue groups of 4 warps (default)
+constexpr int TG_MAX_EPI_GROUPS = 4;           // store-bound launches use 4 groups (576 threads), see TapParams::epi_groups
 constexpr int TG_MAX_TAPS = 16;
 
 enum TgStore { TG_STORE_TMA = 0, TG_STORE_DIRECT = 1, TG_STORE_ATOMIC = 2 };
@@ -67,6 +68,7 @@ struct TapParams {
     // debug overrides for the smem descriptors (bytes, <0 = default)
     int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;
     int stages, nout;         // smem split: ring depth and number of 16 KB store-staging buffers
+    int epi_groups;           // 2 or 4 epilogue groups of 4 warps; group g drains the 32-column chunks c with c % G == g
     int nres;                 // 16 KB residual tiles prefetched by TMA for the epilogue (0 or 4: two per group)
     int stage_bytes;          // 16 KB (A) + 16 or 32 KB (B)
     int stats_cols;           // columns of the CTA-wide statistics scratch (n_total rounded up to 32; 0 = none)

@@ -16,8 +16,8 @@ for (H, ci, co) in ((56, 256, 64), (28, 512, 128), (14, 1024, 256)):
     res = torch.randn_like(x)
     bits = torch.randint(-2 ** 31, 2 ** 31 - 1, ((x.numel() // 4 + 31) // 32 * 4,), device="cuda", dtype=torch.int32)
     row = []
-    for (tma, st, nout, maxbn, flags) in ((-1, 0, 0, 256, 0), (0, 0, 0, 256, 0), (1, 0, 0, 256, 0), (1, 0, 0, 128, 0), (1, 2, 4, 128, 0), (1, 0, 0, 256, 1),
-                                         (1, 0, 0, 256, 3)):
+    for (tma, st, nout, maxbn, flags) in ((-1, 0, 0, 256, 0), (1, 0, 0, 256, 0), (1, 2, 8, 128, 0), (1, 3, 4, 128, 0),
+                                         (1, 2, 4, 128, 0), (1, 0, 0, 256, 1)):
         L.pe_debug_residual_tma(max(tma, 0))
         L.pe_debug_pipeline(st, nout)
         L.pe_debug_max_bn(maxbn)
