@@ -174,8 +174,10 @@ static void pick_pipeline(TapParams& p, int ksteps) {
     const int budget = TG_SMEM_BYTES - (p.stats ? 2 * p.stats_cols * (int)sizeof(float) + 8192 : 0) - p.nres * TG_A_BYTES;
     // Store-bound launches (training-mode conv with batch statistics, wide tile, short K loop) are limited by the
     // epilogue's instruction latency, not by HBM: they run four epilogue groups (16 warps) instead of two.
-    p.epi_groups = (g_dbg_epi_groups == 4 || (g_dbg_epi_groups == 0 && p.stats && p.store_mode == TG_STORE_TMA &&
-                                              p.bn >= 128 && ksteps < 24 && !p.residual)) ? 4 : 2;
+    // (the residual prefetch buffers are laid out for two groups: residual launches always run two)
+    p.epi_groups = (!p.residual && (g_dbg_epi_groups == 4 ||
+                                    (g_dbg_epi_groups == 0 && p.stats && p.store_mode == TG_STORE_TMA &&
+                                     p.bn >= 128 && ksteps < 24))) ? 4 : 2;
     // (the staging buffers are split evenly between the epilogue groups)
     int nout = (p.store_mode == TG_STORE_TMA) ? (p.epi_groups == 4 ? 4 : (ksteps >= 24 ? 2 : 4)) : 0;
     if (p.nres && p.bn > 128) nout = 2;

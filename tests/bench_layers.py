@@ -50,7 +50,11 @@ def main():
         flop = 2.0 * B * Ho * Ho * co * ci * k * k / TF32 * 1e6
         cols = []
         for f in flags:
-            if f == 2000:
+            if f == 4000:
+                L.pe_debug_epilogue_groups(4)
+            elif f == 2002:
+                L.pe_debug_epilogue_groups(2)
+            elif f == 2000:
                 L.pe_debug_wgrad_halo(0)
             elif f == 1128:
                 L.pe_debug_max_bn(128)
@@ -77,6 +81,7 @@ def main():
             L.pe_debug_pipeline(0, 0)
             L.pe_debug_flags(0)
             L.pe_debug_wgrad_halo(1)
+            L.pe_debug_epilogue_groups(0)
         L.pe_debug_flags(0)
         L.pe_debug_pipeline(0, 0)
         L.pe_debug_max_bn(256)
