@@ -611,31 +611,40 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned 
     }
 }
 
+// 3x3 / stride 2 / pad 1 max-pool backward as a gather.  One thread owns a 2x2 block of input pixels (x 4
+// channels): the block is touched by exactly the four windows (i, i+1) x (j, j+1), so each window's gradient and
+// arg-max byte is read once per block instead of once per pixel (2.25x fewer loads).  The aux branch (1x1 conv to
+// one channel + 2x2 max pool over the same activation) pools exactly these 2x2 blocks: its gradient goes to the
+// block's arg-max pixel in the same pass.
 __global__ void __launch_bounds__(EW_THREADS)
 maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
                    const unsigned char* __restrict__ argmax, float* __restrict__ dx, int accumulate, int B, int H,
                    int W, int C, int Ho, int Wo, const float* __restrict__ aux_dout, int aux_lddo,
                    const unsigned char* __restrict__ aux_argmax, const float* __restrict__ aux_w) {
     const int G = C >> 2;
-    const long long n = (long long)B * H * W * G;
+    const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;          // 2x2 blocks
+    const long long n = (long long)B * Hb * Wb * G;
     const long long gs = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
-        const int g = (int)(i % G);
-        long long r = i / G;
-        const int w = (int)(r % W);
-        r /= W;
-        const int h = (int)(r % H);
-        const int b = (int)(r / H);
-        float4 acc = accumulate ? ld4(dx + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int ho_lo = h / 2, ho_hi = (h + 1) / 2;  // windows with 2ho-1 <= h <= 2ho+1
-        const int wo_lo = w / 2, wo_hi = (w + 1) / 2;
-        for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gs) {
+        const int g = (int)(idx % G);
+        long long r = idx / G;
+        const int j = (int)(r % Wb);
+        r /= Wb;
+        const int i = (int)(r % Hb);
+        const int b = (int)(r / Hb);
+        float4 acc[4];                                        // pixels (2i + (k>>1), 2j + (k&1))
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // window ho covers input rows 2ho-1 .. 2ho+1: row 2i is tap row 1 of window i only, row 2i+1 is tap row 2 of
+        // window i and tap row 0 of window i+1 (same along w); taps outside 0..2 are filtered below
+#pragma unroll
+        for (int dh = 0; dh < 2; ++dh) {
+            const int ho = i + dh;
             if (ho >= Ho) continue;
-            const int kh = h - (2 * ho - 1);
-            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+#pragma unroll
+            for (int dw = 0; dw < 2; ++dw) {
+                const int wo = j + dw;
                 if (wo >= Wo) continue;
-                const int kw = w - (2 * wo - 1);
-                const unsigned char k = (unsigned char)(kh * 3 + kw);
                 const long long o = (((long long)b * Ho + ho) * Wo + wo) * G + g;
                 const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + 4 * o);
                 float4 d = ld4(dy + 4 * o);
@@ -643,24 +652,44 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
                     const float4 e = ld4(dy2 + 4 * o);
                     d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
                 }
-                if (am.x == k) acc.x += d.x;
-                if (am.y == k) acc.y += d.y;
-                if (am.z == k) acc.z += d.z;
-                if (am.w == k) acc.w += d.w;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int h = 2 * i + (k >> 1), w = 2 * j + (k & 1);
+                    const int kh = h - (2 * ho - 1), kw = w - (2 * wo - 1);     // tap of this pixel in the window
+                    if (kh < 0 || kh > 2 || kw < 0 || kw > 2) continue;
+                    const unsigned char t = (unsigned char)(kh * 3 + kw);
+                    if (am.x == t) acc[k].x += d.x;
+                    if (am.y == t) acc[k].y += d.y;
+                    if (am.z == t) acc[k].z += d.z;
+                    if (am.w == t) acc[k].w += d.w;
+                }
             }
         }
         if (aux_dout) {
-            // second consumer of this activation: the aux branch (1x1 conv to one channel + 2x2 max pool); its
-            // gradient reaches only the arg-max pixel of each 2x2 window
-            const long long win = ((long long)b * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
-            if (aux_argmax[win] == (unsigned char)(((h & 1) << 1) | (w & 1))) {
-                const float d = aux_dout[(long long)b * aux_lddo + (h >> 1) * (W >> 1) + (w >> 1)];
-                const float4 w4 = ld4(aux_w + 4 * g);
-                acc.x = fmaf(d, w4.x, acc.x); acc.y = fmaf(d, w4.y, acc.y);
-                acc.z = fmaf(d, w4.z, acc.z); acc.w = fmaf(d, w4.w, acc.w);
+            const long long win = ((long long)b * (H >> 1) + i) * (W >> 1) + j;
+            const int ak = aux_argmax[win];
+            const float d = aux_dout[(long long)b * aux_lddo + i * (W >> 1) + j];
+            const float4 w4 = ld4(aux_w + 4 * g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k == ak) {
+                    acc[k].x = fmaf(d, w4.x, acc[k].x); acc[k].y = fmaf(d, w4.y, acc[k].y);
+                    acc[k].z = fmaf(d, w4.z, acc[k].z); acc[k].w = fmaf(d, w4.w, acc[k].w);
+                }
             }
         }
-        st4(dx + 4 * i, acc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int h = 2 * i + (k >> 1), w = 2 * j + (k & 1);
+            if (h >= H || w >= W) continue;
+            float* p = dx + ((((long long)b * H + h) * W + w) * G + g) * 4;
+            float4 v = acc[k];
+            if (accumulate) {
+                const float4 prev = ld4(p);
+                v.x += prev.x; v.y += prev.y; v.z += prev.z; v.w += prev.w;
+            }
+            st4(p, v);
+        }
     }
 }
 
@@ -1131,7 +1160,7 @@ int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* 
     PE_REQUIRE(!aux_dout || (aux_argmax && aux_w && H % 2 == 0 && W % 2 == 0),
                "maxpool_bwd: the aux term needs its arg-max map, weights and even H, W");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-    const long long n = (long long)B * H * W * (C / 4);
+    const long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
     maxpool_bwd_kernel<<<grid_for(n, EW_THREADS, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
         dy, dy2, argmax, dx, accumulate, B, H, W, C, Ho, Wo, aux_dout, aux_lddo, aux_argmax, aux_w);
     PE_LAUNCH_CHECK();
