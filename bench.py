@@ -10,7 +10,8 @@ HBM; `e2e` is the same step driven from pinned HOST buffers (H2D of the frames /
 a D2H read of the loss inside the timed region).  Weak scaling: each rank owns its own 256 frames.
 
 `--impl reference` times the reference algorithm's CPU path (the oracle restatement of the reference
-modules; the reference tree itself cannot travel to the GPU box) on all host cores.
+modules; the reference tree itself cannot travel to the GPU box) on all host cores.  `oracle/` is imported only by
+that leg and by the `cpu_baseline` leg; the GPU arm builds its models and synthetic data on its own.
 """
 import argparse
 import json
@@ -73,16 +74,48 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+# Model hyper-parameters of the reference's launchers (scripts/train_no.sbatch:61-83, train_tdo.sbatch:61-83,
+# train_td.sbatch:61-62 -> scripts/train_model.py:22-42 defaults)
+MODEL_CFG = {"no": dict(latent=512, hidden=[1024, 256, 64]), "tdo": dict(latent=512, hidden=512),
+             "tdo_v2": dict(latent=512, hidden=512), "td": dict(latent=1024, hidden=512),
+             "n": dict(latent=1024, hidden=[512])}
+
+
 def build(kind, seed=0):
-    """Reference constructor under torch.manual_seed(seed), random init.  The one-shot models put a ReLU after
-    their LAST layer (reference quirk, models/naive.py:343-345), so a random-init network emits all-zero
-    quaternions and the reference loss (no epsilon in the normalisation, models/losses.py:68-69) is NaN from
-    step 0.  The bench keeps the arithmetic finite by starting the last layer's bias at +0.5; shapes, FLOPs
-    and bytes are unchanged."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import model_checks
+    """Reference constructor (the drop-in mirrors in rgb-proprioceptive-pose-estimator_b200/models) under
+    torch.manual_seed(seed), random init.  The one-shot models put a ReLU after their LAST layer (reference quirk,
+    models/naive.py:343-345), so a random-init network emits all-zero quaternions and the reference loss (no
+    epsilon in the normalisation, models/losses.py:68-69) is NaN from step 0.  The bench keeps the arithmetic
+    finite by starting the last layer's bias at +0.5; shapes, FLOPs and bytes are unchanged."""
+    import contextlib
+    import io
     import torch
-    model = model_checks.build_model(kind, seed)
+    import models.naive as mn
+    import models.time_sensitive as mt
+    cfg = MODEL_CFG[kind]
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if kind == "no":
+            model = mn.NaiveObjectStateEstimator("hammer", list(cfg["hidden"]), 50, cfg["latent"], False, (9,), False,
+                                                 False)
+        elif kind == "tdo":
+            model = mt.TemporallyDependentObjectStateEstimator("robot1_eef", cfg["hidden"], 50, cfg["latent"], 20,
+                                                               feature_extract=False, use_pretrained=False)
+        elif kind == "tdo_v2":
+            model = mt.TemporallyDependentObjectStateEstimatorV2("robot1_eef", cfg["hidden"], 64, 50, cfg["latent"],
+                                                                 20, feature_extract=False, use_pretrained=False)
+        elif kind == "td":
+            model = mt.TemporallyDependentStateEstimator(cfg["hidden"], cfg["hidden"], 50, cfg["latent"], 10,
+                                                         feature_extract=False, use_pretrained=False)
+        else:
+            # the "n" constructor cannot pass use_pretrained (models/naive.py:42); there is no network here
+            orig = mn.import_resnet
+            mn.import_resnet = lambda n, o, fe=True, use_pretrained=True: orig(n, o, fe, use_pretrained=False)
+            try:
+                model = mn.NaiveEndEffectorStateEstimator(list(cfg["hidden"]), list(cfg["hidden"]), 50, cfg["latent"],
+                                                          False)
+            finally:
+                mn.import_resnet = orig
     with torch.no_grad():
         if kind == "no":
             getattr(model, "fc%d" % (model.n_fc - 1)).module.bias.fill_(0.5)
@@ -93,8 +126,21 @@ def build(kind, seed=0):
 
 
 def synth(kind, n, s, seed):
-    from oracle import pose_oracle as po
-    return po.synthetic_batch(kind, n, s=s, seed=seed) if kind in SEQ_KINDS else po.synthetic_batch(kind, n, seed=seed)
+    """Synthetic inputs of SURVEY 8(d): img ~ N(0,1) (normalised frames); positions U(-0.5,0.5)^3, unit quaternions
+    with w >= 0 (util/data_utils.py:207-211).  Returns (img, x0bar, target) as CPU fp32 tensors."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    lead = (s, n) if kind in SEQ_KINDS else (n,)
+    img = torch.randn(*lead, 3, 224, 224, generator=g)
+
+    def pose():
+        pos = torch.rand(*lead, 3, generator=g) - 0.5
+        q = torch.randn(*lead, 4, generator=g)
+        q = q / q.norm(dim=-1, keepdim=True)
+        q[..., 3] = q[..., 3].abs()
+        return torch.cat([pos, q], dim=-1)
+
+    return img, pose(), pose()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -103,7 +149,7 @@ def cpu_reference_rate(kind, batch, seq, steps, warmup):
     import torch
     from oracle import pose_oracle as po
     torch.set_num_threads(os.cpu_count())
-    model = build(kind)
+    model = build(kind)          # parameter container only (CPU); the arithmetic below is the oracle's
     extra = None
     if kind == "td":
         extra = {"aux_w": model.aux_nets[0][0].weight, "aux_b": model.aux_nets[0][0].bias}

@@ -58,6 +58,30 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
 
 
+def test_bench_gpu_arm_is_independent_of_the_oracle():
+    """bench.py may execute oracle/ only in its cpu_baseline / --impl reference leg (cpu_reference_rate); the GPU
+    arm builds its models and synthetic data itself and never touches tests/ helpers either."""
+    import ast
+    path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py")
+    tree = ast.parse(open(path).read())
+    offenders = []
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            names = []
+            if isinstance(node, ast.ImportFrom) and node.module:
+                names = [node.module]
+            elif isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            for name in names:
+                if (name.split(".")[0] in ("oracle", "model_checks", "kernel_checks")) and fn.name != "cpu_reference_rate":
+                    offenders.append((fn.name, name))
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    for node in top:
+        names = [node.module] if isinstance(node, ast.ImportFrom) else [a.name for a in node.names]
+        offenders += [("<module>", n) for n in names if n and n.split(".")[0] == "oracle"]
+    assert not offenders, offenders
+
+
 @pytest.mark.parametrize("kind", ["no", "n", "td", "tdo", "tdo_v2"])
 def test_state_dict_layout_matches_reference_manifest(kind):
     """Keys, order, shapes, dtypes, parameter order and the seed-0 init values equal the reference's
