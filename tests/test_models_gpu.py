@@ -397,3 +397,77 @@ def test_streaming_estimator_raw_frames():
         a = raw_est.step_raw(raw.pin_memory(), x0.pin_memory()).clone()
         b = ref_est.step(img.cuda(), x0.cuda()).clone()
         assert mc.rel(a, b) <= 1e-5, (t, mc.rel(a, b))
+
+
+@pytest.mark.parametrize("kind", ["no", "tdo"])
+def test_no_proprioception_variant(kind):
+    """no_proprioception=True (models/naive.py:147, models/time_sensitive.py:295): the 7 proprio columns vanish from
+    the fusion rows (first head layer has 7 fewer inputs); forward, loss and head gradients against the oracle, in
+    training (GEMM head) and rollout-sized eval (fused head) modes."""
+    import contextlib
+    import io
+    import models.naive as mn
+    import models.time_sensitive as mt
+    import util.model_utils as mu
+    from models.losses import PoseDistanceLoss
+    mu._RESNET_LAYERS[50] = [1, 1, 1, 1]
+    try:
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            if kind == "no":
+                model = mn.NaiveObjectStateEstimator("cube", [1024, 256, 64], 50, 512, False, (9,), False, False,
+                                                     no_proprioception=True)
+            else:
+                model = mt.TemporallyDependentObjectStateEstimator("robot1_eef", 512, 50, 512, 20, feature_extract=False,
+                                                                   use_pretrained=False, no_proprioception=True)
+        with torch.no_grad():
+            if kind == "no":
+                getattr(model, "fc%d" % (model.n_fc - 1)).module.bias.fill_(0.5)
+        sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point and "running_" not in k)
+              for k, v in model.state_dict().items()}
+        shape = dict(n=3) if kind == "no" else dict(n=2, s=2)
+        img, x0, tgt = po.synthetic_batch(kind, seed=8, **shape)
+        lk = dict(distance_metric="l2", alpha=0.5, mode="pose")
+        if kind == "no":
+            ref_out = po.naive_object_forward(sd, img, x0, True, model.n_fc, use_proprio=False)
+        else:
+            ref_out, _ = po.tdo_forward(sd, img, x0, True, None, use_proprio=False)
+        ref_loss = po.pose_loss(ref_out, tgt, **lk)
+        ref_loss.backward()
+        model.cuda().train()
+        if kind == "tdo":
+            model.reset_initial_state(2)
+        out = model(img.cuda(), None, x0.cuda())
+        loss = PoseDistanceLoss(**lk)(out, tgt.cuda())
+        loss.backward()
+        assert mc.rel(out, ref_out.detach()) <= 5e-3, mc.rel(out, ref_out.detach())
+        assert abs(float(loss) - float(ref_loss)) <= 5e-3 * abs(float(ref_loss))
+        named = dict(model.named_parameters())
+        first = "fc0.module.weight" if kind == "no" else "rnn.module.weight_ih_l0"
+        assert named[first].shape[1] == 512 + 3136
+        assert mc.relnorm(named[first].grad, sd[first].grad) <= 5e-2
+        model.eval()
+        with torch.no_grad():
+            if kind == "tdo":
+                model.reset_initial_state(2)
+            oe = model(img.cuda(), None, x0.cuda())
+        sd2 = {k: v.detach() for k, v in sd.items()}
+        # eval uses the running statistics the training forward just updated on the GPU model
+        sd2.update({k: v.detach().cpu() for k, v in model.state_dict().items() if "running_" in k})
+        if kind == "no":
+            oe_ref = po.naive_object_forward(sd2, img, x0, False, model.n_fc, use_proprio=False)
+        else:
+            oe_ref, _ = po.tdo_forward(sd2, img, x0, False, None, use_proprio=False)
+        assert mc.rel(oe, oe_ref) <= 5e-3, mc.rel(oe, oe_ref)
+    finally:
+        mu._RESNET_LAYERS[50] = [3, 4, 6, 3]
+
+
+@pytest.mark.parametrize("n", [1, 5])
+def test_odd_batch_sizes(n):
+    """Ragged sizes: 1 and 5 frames (tiles of 128 pixels never divide evenly; BatchNorm over a single frame)."""
+    mc.SHALLOW[0] = True
+    rows = mc.check_train_step("no", n=n)
+    fwd, grads, struct = _split(rows)
+    bad = [(name, e) for name, e, t in fwd if not e <= max(t, 5e-3)] + [(name, e) for name, e, t in struct if e != 0.0]
+    assert not bad, bad
