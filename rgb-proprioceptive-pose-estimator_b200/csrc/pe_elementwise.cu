@@ -17,6 +17,20 @@ inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
     return (int)blocks;
 }
 
+// Grid of a grid-stride streaming kernel: exactly one wave -- (SM count) x (CTAs of this kernel resident per SM,
+// from the occupancy calculator for its register / shared-memory footprint) -- or fewer when the work is small.
+// 1184 CTAs of a kernel that fits 6 per SM would run as 1.33 waves with a thin tail.
+template <typename K>
+inline int one_wave_grid(K kernel, size_t smem, long long work_items, int per_block) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, EW_THREADS, smem) != cudaSuccess || occ < 1) occ = 4;
+    long long blocks = (work_items + per_block - 1) / per_block;
+    const long long cap = (long long)num_sms() * occ;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 ld4_stream(const float* p) {
@@ -157,10 +171,13 @@ channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ a2,
     }
 }
 
-dim3 reduce_grid(long long P, int C) {
+template <typename K>
+dim3 reduce_grid(K kernel, long long P, int C) {
     const int G = C / 4;
     const int gy = G > EW_THREADS ? G / EW_THREADS : 1;
-    long long gx = (long long)num_sms() * 4 / gy;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, EW_THREADS, 0) != cudaSuccess || occ < 1) occ = 2;
+    long long gx = (long long)num_sms() * occ / gy;          // one wave of resident CTAs
     const long long max_gx = (P + 31) / 32;  // at least ~32 rows per block
     if (gx > max_gx) gx = max_gx;
     if (gx < 1) gx = 1;
@@ -268,36 +285,50 @@ bn_train_apply_kernel(const float* __restrict__ y, const double* __restrict__ st
     const long long n4 = P * G;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    // warp-uniform loop (the ballots below need every lane)
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n4; i0 += stride) {
-        const long long i = i0 + lane;
-        const bool valid = i < n4;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-            const int g = (int)(i % G);
-            const float4 v = ld4_stream(y + 4 * i);
-            const float4 sc = ld4(csc + 4 * g);
-            const float4 sh = ld4(csh + 4 * g);
-            o.x = fmaf(v.x, sc.x, sh.x);
-            o.y = fmaf(v.y, sc.y, sh.y);
-            o.z = fmaf(v.z, sc.z, sh.z);
-            o.w = fmaf(v.w, sc.w, sh.w);
-            if (residual) {
-                const float4 r = ld4_stream(residual + 4 * i);
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    // warp-uniform loop (the ballots below need every lane); two chunks per trip so that every thread keeps two
+    // (four with a residual) independent 128-bit loads in flight
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n4; i0 += 2 * stride) {
+        long long ii[2];
+        bool valid[2];
+        float4 v[2], r[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            ii[u] = i0 + u * stride + lane;
+            valid[u] = ii[u] < n4;
+            if (valid[u]) {
+                v[u] = ld4_stream(y + 4 * ii[u]);
+                if (residual) r[u] = ld4_stream(residual + 4 * ii[u]);
             }
-            if (relu) {
-                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
-            if (round_out) o = round4(o);
-            st4(out + 4 * i, o);
         }
-        if (maskbits) {
-            const unsigned bx = __ballot_sync(0xffffffffu, o.x > 0.f);
-            const unsigned by = __ballot_sync(0xffffffffu, o.y > 0.f);
-            const unsigned bz = __ballot_sync(0xffffffffu, o.z > 0.f);
-            const unsigned bw = __ballot_sync(0xffffffffu, o.w > 0.f);
-            if (lane == 0) *(reinterpret_cast<uint4*>(maskbits) + (i0 >> 5)) = make_uint4(bx, by, bz, bw);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[u]) {
+                const int g = (int)(ii[u] % G);
+                const float4 sc = ld4(csc + 4 * g);
+                const float4 sh = ld4(csh + 4 * g);
+                o.x = fmaf(v[u].x, sc.x, sh.x);
+                o.y = fmaf(v[u].y, sc.y, sh.y);
+                o.z = fmaf(v[u].z, sc.z, sh.z);
+                o.w = fmaf(v[u].w, sc.w, sh.w);
+                if (residual) {
+                    o.x += r[u].x; o.y += r[u].y; o.z += r[u].z; o.w += r[u].w;
+                }
+                if (relu) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                if (round_out) o = round4(o);
+                st4(out + 4 * ii[u], o);
+            }
+            // (a chunk that starts past the end has no mask words: i0 + u*stride < n4 is warp-uniform)
+            if (maskbits && i0 + u * stride < n4) {
+                const unsigned bx = __ballot_sync(0xffffffffu, o.x > 0.f);
+                const unsigned by = __ballot_sync(0xffffffffu, o.y > 0.f);
+                const unsigned bz = __ballot_sync(0xffffffffu, o.z > 0.f);
+                const unsigned bw = __ballot_sync(0xffffffffu, o.w > 0.f);
+                if (lane == 0)
+                    *(reinterpret_cast<uint4*>(maskbits) + ((i0 + u * stride) >> 5)) = make_uint4(bx, by, bz, bw);
+            }
         }
     }
 }
@@ -961,7 +992,7 @@ extern "C" {
 int pe_bn_stats(const float* y, long long P, int C, double* stats, void* stream) {
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_stats: unsupported channel count %d", C);
-    channel_reduce_kernel<0><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    channel_reduce_kernel<0><<<reduce_grid(channel_reduce_kernel<0>, P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
         y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
     PE_LAUNCH_CHECK();
     return 0;
@@ -981,7 +1012,7 @@ int pe_bn_apply(const float* y, const float* scale, const float* shift, const fl
                 long long P, int C, int relu, int round_tf32, void* stream) {
     PE_REQUIRE(C % 4 == 0, "bn_apply: C %% 4 != 0");
     const long long n4 = P * (C / 4);
-    bn_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    bn_apply_kernel<<<one_wave_grid(bn_apply_kernel, 0, n4, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
         y, scale, shift, residual, out, n4, C / 4, relu, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
@@ -997,7 +1028,8 @@ int pe_bn_train_apply(const float* y, const double* stats, const float* gamma, c
     PE_REQUIRE(!maskbits || (reinterpret_cast<uintptr_t>(maskbits) & 15) == 0,
                "bn_train_apply: mask bits need a 16-byte aligned pointer");
     const long long n4 = P * (C / 4);
-    bn_train_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+    bn_train_apply_kernel<<<one_wave_grid(bn_train_apply_kernel, 2 * C * sizeof(float), n4, EW_THREADS * 4), EW_THREADS,
+                            2 * C * sizeof(float), (cudaStream_t)stream>>>(
         y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd, residual,
         out, maskbits, P, C, momentum, eps, relu, round_tf32);
     PE_LAUNCH_CHECK();
@@ -1012,7 +1044,7 @@ int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, co
     PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_reduce: ReLU mask needs `out` or scale/shift");
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_bwd_reduce: unsupported channel count %d", C);
-    channel_reduce_kernel<1><<<reduce_grid(P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    channel_reduce_kernel<1><<<reduce_grid(channel_reduce_kernel<1>, P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
         dout, dout2, out, y, mean, invstd, mask_scale, mask_shift, maskbits, sums, P, C, relu);
     PE_LAUNCH_CHECK();
     return 0;
@@ -1028,7 +1060,8 @@ int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, con
     PE_REQUIRE(C % 4 == 0 && C <= 4096, "bn_bwd_apply: unsupported channel count %d", C);
     PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_apply: ReLU mask needs `out` or scale/shift");
     const long long n4 = P * (C / 4);
-    bn_bwd_apply_kernel<<<grid_for(n4, EW_THREADS * 4), EW_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream>>>(
+    bn_bwd_apply_kernel<<<one_wave_grid(bn_bwd_apply_kernel, 3 * C * sizeof(float), n4, EW_THREADS * 4), EW_THREADS,
+                          3 * C * sizeof(float), (cudaStream_t)stream>>>(
         dout, dout2, out, y, mean, invstd, gamma, mask_scale, mask_shift, maskbits, sums, dy, dres, dres_accumulate,
         dgamma,
         dbeta, param_accumulate,
@@ -1147,7 +1180,7 @@ int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, 
     PE_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * Ho * Wo * (C / 4);
-    maxpool_fwd_kernel<<<grid_for(n, EW_THREADS, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(x, y, argmax, B, H, W,
+    maxpool_fwd_kernel<<<one_wave_grid(maxpool_fwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(x, y, argmax, B, H, W,
                                                                                              C, Ho, Wo);
     PE_LAUNCH_CHECK();
     return 0;
@@ -1161,7 +1194,7 @@ int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* 
                "maxpool_bwd: the aux term needs its arg-max map, weights and even H, W");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
-    maxpool_bwd_kernel<<<grid_for(n, EW_THREADS, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    maxpool_bwd_kernel<<<one_wave_grid(maxpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
         dy, dy2, argmax, dx, accumulate, B, H, W, C, Ho, Wo, aux_dout, aux_lddo, aux_argmax, aux_w);
     PE_LAUNCH_CHECK();
     return 0;
@@ -1179,7 +1212,7 @@ int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int 
 int pe_avgpool_bwd(const float* dy, int lddy, float* dx, int B, int HW, int C, void* stream) {
     PE_REQUIRE(C % 4 == 0 && lddy % 4 == 0, "avgpool: C, lddy must be multiples of 4");
     const long long n = (long long)B * HW * (C / 4);
-    avgpool_bwd_kernel<<<grid_for(n, EW_THREADS * 2), EW_THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, B, HW, C);
+    avgpool_bwd_kernel<<<one_wave_grid(avgpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, B, HW, C);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1188,7 +1221,7 @@ int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, i
                int H, int W, int C, int round_tf32, void* stream) {
     PE_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "aux: H, W must be even and C a multiple of 4");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    aux_fwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 2 * 4, 16), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    aux_fwd_kernel<<<one_wave_grid(aux_fwd_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0, (cudaStream_t)stream>>>(
         a1, w, bias, out, ldo, argmax, B, H, W, C, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
