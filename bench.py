@@ -181,7 +181,7 @@ def run_reference(args):
     sample = "%d-frame batches of the %s training step, %d timed steps (median)" % (frames, args.model, args.steps)
     out = {"impl": "reference", "metric": "train_samples_per_s", "value": rate, "unit": "samples/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": workload_config(args),
            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -325,7 +325,7 @@ def run_ours(args):
     out = {
         "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "tf32",
         "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -375,10 +375,19 @@ def main():
     ap.add_argument("--seq", type=int, default=None)
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--lr", type=float, default=1e-4)
+    ap.add_argument("--global-batch", type=int, default=None,
+                    help="strong scaling: total frames / episodes over all ranks (per-rank batch = this / world size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.seq is None:
         args.seq = {"tdo": 20, "td": 10, "tdo_v2": 20}.get(args.model, 1)
+    args.scaling = "weak"
+    if args.global_batch is not None:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.global_batch % world:
+            ap.error("--global-batch must be divisible by the number of ranks")
+        args.batch = args.global_batch // world
+        args.scaling = "strong"
     if args.batch is None:
         args.batch = {"no": 256, "n": 256, "tdo": 32, "td": 64, "tdo_v2": 32}[args.model]
     if args.impl == "reference":
