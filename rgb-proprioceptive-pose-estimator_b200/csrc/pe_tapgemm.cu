@@ -1,11 +1,16 @@
 // tcgen05 / TMEM / TMA tap-GEMM kernel (see pe_tapgemm.cuh for the contract).
 //
 // Persistent, warp-specialised: one CTA per SM walks the (n-tile, m-tile, z) work list round-robin.
-//   warp 0      TMA producer     : runs ahead through a TG_STAGES-deep smem ring, across tile boundaries
-//   warp 1      MMA issuer       : one thread issues tcgen05.mma into one of TWO 128-column TMEM
-//                                  accumulators, so tile i+1 accumulates while tile i is drained
-//   warps 2..5  epilogue         : TMEM -> registers -> (affine / residual / ReLU / TF32 round / BN stats)
-//                                  -> swizzled smem staging (double buffered) -> TMA store
+//   warp 0        TMA producer   : runs ahead through a 2-6 stage smem ring, across tile boundaries
+//   warp 1        MMA issuer     : tcgen05.mma into one of TWO 256-column TMEM accumulators, so tile i+1
+//                                  accumulates while tile i is drained (mode 2: all 512 columns hold one set of
+//                                  per-tap accumulators)
+//   warps 2..     epilogue       : G groups of four warps (G = 2, or 4 for store-bound launches); group g drains the
+//                                  32-column chunks c with c % G == g:  TMEM -> registers -> (affine / TMA-prefetched
+//                                  residual / ReLU / TF32 round) -> swizzled smem staging -> TMA store, plus the
+//                                  per-channel batch statistics as a column pass over the staged tile
+// Warps 0 and 1 run warp-convergent (role dispatch on a shfl-broadcast warp index, vote-derived barrier results,
+// elect.sync inside the issuing asm) so that descriptors, coordinates and counters stay on the uniform datapath.
 #include "pe_tapgemm.cuh"
 
 namespace pe {

@@ -5,13 +5,16 @@
 //                     A rows are a 4-D TMA box of output pixels (w, h, n) shifted per filter tap;
 //                     zero padding comes from TMA out-of-bounds fill.  Plain GEMMs (1x1 convs,
 //                     linear layers, LSTM projections) are the 1-tap, 1-D-box special case.
-//   mode 1 ("wgrad"): D[M, N] = sum_pixels A[pixel, M]^T * B[pixel+tap, N]
+//   mode 1 ("wgrad"): D[M, N] = sum_pixels A[pixel, M]^T * B[pixel+tap, N]      (one tap per work item)
 //                     A (dY) and B (X) MN-major in shared memory: the reduction runs over pixels.
+//   mode 2 ("haloed wgrad", stride 1): one dY pixel tile and ONE X tile with an (R-1, S-1) halo per stage; each
+//                     tap of a group reads its shifted window of that X tile through its own shared-memory
+//                     descriptor and accumulates into its own TMEM columns (3-5 taps per work item).
 //
 // Persistent CTAs (one per SM) walk a list of 128 x bn output tiles; warp 0 = TMA producer,
 // warp 1 = TMEM owner + MMA issuer (two accumulators, so the next tile overlaps the epilogue),
-// warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store, with optional
-// bias / scale-shift / residual / ReLU / TF32 rounding / per-channel batch statistics).
+// warps 2.. = 2 or 4 epilogue groups (TMEM -> registers -> swizzled smem -> TMA store, with optional
+// bias / scale-shift / TMA-prefetched residual (+bit mask) / ReLU / TF32 rounding / per-channel batch statistics).
 #pragma once
 #include "pe_common.cuh"
 
