@@ -40,6 +40,8 @@ void pe_debug_wgrad_halo(int mode);
 void pe_debug_residual_tma(int on);
 /* debug: force the number of epilogue warp groups of the tap-GEMM (2 or 4); 0 = automatic */
 void pe_debug_epilogue_groups(int groups);
+/* debug: haloed-tile path for 3x3 stride-1 forward / dgrad with <= 128 input channels (0 = per-tap boxes) */
+void pe_debug_conv_halo(int on);
 
 /* ---- convolutions: torchvision resnet.py:143-163,266-282 Conv2d calls reached from
  *      models/naive.py:316 and models/time_sensitive.py:185,472 (bias-free, NHWC here) ------------

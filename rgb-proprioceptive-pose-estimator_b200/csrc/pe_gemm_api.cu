@@ -189,6 +189,57 @@ static void pick_pipeline(TapParams& p, int ksteps) {
     p.nout = nout > 0 ? nout : 2;
 }
 
+static int g_dbg_halo_btaps = 0;      // taps per weight stage of the haloed conv (0 = default 3)
+static int g_dbg_conv_halo = 0;       // 0: off, 1: on for <= 128 input channels (3x3 stride-1 forward / dgrad)
+
+// Geometry of the haloed stride-1 conv (TapParams::conv_halo): 8-pixel-wide tiles of bh rows inside one image, the
+// A ring holds (bh + R - 1) x (8 + S - 1) haloed tiles, weights stream through their own ring.  Returns false when
+// the shape is not handled (the caller then uses the per-tap box path).
+static bool setup_conv_halo(TapParams& p, int B, int H, int W, int Cin, int R, int S, int pad) {
+    if (!g_dbg_conv_halo || R != 3 || S != 3 || pad != 1 || Cin > 128 || Cin % 32 != 0 || H < 14) return false;
+    p.conv_halo = 1;
+    p.box_w = 8;
+    p.box_h = (H % 14 == 0) ? 14 : 16;
+    p.box_n = 1;
+    p.m_rows = p.box_w * p.box_h;
+    p.tiles_w = (W + p.box_w - 1) / p.box_w;
+    p.tiles_h = (H + p.box_h - 1) / p.box_h;
+    p.tiles_n = B;
+    p.halo_w = p.box_w + S - 1;
+    p.halo_h = p.box_h + R - 1;
+    p.halo_dw = -pad;
+    p.halo_dh = -pad;
+    return true;
+}
+
+static void pick_pipeline_halo_taps(TapParams& p) {
+    p.b_taps = g_dbg_halo_btaps > 0 ? g_dbg_halo_btaps : 3;
+    if (p.n_taps % p.b_taps) p.b_taps = 1;
+}
+
+// shared-memory split of the haloed conv: A ring (haloed tiles), B ring (one weight tile per tap), store staging
+static void pick_pipeline_halo(TapParams& p) {
+    p.stage_bytes = (p.halo_w * p.halo_h * 128 + 1023) / 1024 * 1024;
+    // weights of several taps per B stage: one barrier round then covers 4 * b_taps MMAs (the per-round overhead of
+    // the producer / MMA warps, ~400 clk, is what limits narrow tiles otherwise)
+    pick_pipeline_halo_taps(p);
+    p.b_bytes = p.bn * p.b_taps * 128;
+    p.stats_cols = p.stats ? (p.n_total + 31) / 32 * 32 : 0;
+    p.nres = 0;
+    p.epi_groups = 2;
+    p.nout = 2;
+    const int budget = TG_SMEM_BYTES - (p.stats ? 2 * p.stats_cols * (int)sizeof(float) + 8192 : 0) - p.nout * TG_A_BYTES;
+    p.b_stages = p.b_bytes <= 32768 ? 3 : 2;
+    if (budget - p.b_stages * p.b_bytes < 2 * p.stage_bytes) {       // does not fit: fewer taps per weight stage
+        p.b_taps = (p.n_taps % 3 == 0 && p.bn * 3 * 128 * 2 + 2 * p.stage_bytes <= budget) ? 3 : 1;
+        p.b_bytes = p.bn * p.b_taps * 128;
+        p.b_stages = 2;
+    }
+    p.stages = (budget - p.b_stages * p.b_bytes) / p.stage_bytes;
+    if (p.stages > 4) p.stages = 4;
+    p.b_ring_bytes = p.b_stages * p.b_bytes;
+}
+
 struct Epilogue {
     const float* bias = nullptr;
     const float* scale = nullptr;
@@ -231,18 +282,32 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
     init_params(p);
     p.mode = 0;
     p.bn = pick_bn(Cout);
-    choose_box(Wo, Ho, B, TG_BM, &p.box_w, &p.box_h, &p.box_n);
-    p.m_rows = p.box_w * p.box_h * p.box_n;
-    p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
-    p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
-    p.tiles_n = (B + p.box_n - 1) / p.box_n;
+    const bool halo = stride == 1 && !ep.residual && setup_conv_halo(p, B, H, W, Cin, R, S, pad);
+    if (!halo) {
+        choose_box(Wo, Ho, B, TG_BM, &p.box_w, &p.box_h, &p.box_n);
+        p.m_rows = p.box_w * p.box_h * p.box_n;
+        p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
+        p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
+        p.tiles_n = (B + p.box_n - 1) / p.box_n;
+    }
     p.out_w = Wo;
     p.out_h = Ho;
     p.out_n = B;
     p.chunks = (Cin + TG_BK - 1) / TG_BK;
     if (fill_taps_fwd(p, R, S, stride, pad)) return 1;
+    if (halo) {
+        // taps as (row, column) offsets inside the haloed tile: tap (r, s) starts r rows / s pixels in
+        for (int r = 0; r < R; ++r)
+            for (int q = 0; q < S; ++q) {
+                p.tap_dh[r * S + q] = (signed char)r;
+                p.tap_dw[r * S + q] = (signed char)q;
+            }
+    }
     const int box[4] = {TG_BK, p.box_w, p.box_h, p.box_n};
-    if (stride == 1) {
+    if (halo) {
+        const int hbox[4] = {TG_BK, p.halo_w, p.halo_h, 1};
+        if (make_nhwc_map(&maps.a[0], x, B, H, W, Cin, 0, 0, 1, hbox)) return 1;
+    } else if (stride == 1) {
         if (make_nhwc_map(&maps.a[0], x, B, H, W, Cin, 0, 0, 1, box)) return 1;
     } else {
         for (int ph = 0; ph < 2; ++ph)
@@ -269,7 +334,16 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
     p.stats = ep.stats;
     PE_REQUIRE(!ep.stats || !(ep.scale || ep.bias || ep.residual || ep.relu || ep.round_out),
                "conv_fwd: batch statistics are taken from the raw output (no affine / residual / ReLU / rounding)");
-    pick_pipeline(p, p.n_taps * p.chunks);
+    if (halo) {
+        pick_pipeline_halo(p);
+        // weight tiles of b_taps consecutive taps per TMA box
+        const long long dims[4] = {Cin, Cout, (long long)R * S, 1};
+        const long long strides[3] = {Cin, (long long)Cin * Cout, (long long)Cin * Cout * R * S};
+        const int bbox[4] = {TG_BK, p.bn, p.b_taps, 1};
+        if (make_map(&maps.b[1], w_tck, dims, strides, bbox)) return 1;
+    } else {
+        pick_pipeline(p, p.n_taps * p.chunks);
+    }
     dim3 grid((Cout + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
     return launch_tapgemm(maps, p, grid, stream);
 }
@@ -321,17 +395,28 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
                 }
             if (t == 0) continue;
             p.n_taps = t;
-            choose_box(Wp, Hp, B, TG_BM, &p.box_w, &p.box_h, &p.box_n);
-            p.m_rows = p.box_w * p.box_h * p.box_n;
-            p.tiles_w = (Wp + p.box_w - 1) / p.box_w;
-            p.tiles_h = (Hp + p.box_h - 1) / p.box_h;
-            p.tiles_n = (B + p.box_n - 1) / p.box_n;
+            // stride-1 3x3: dy has the shape of dx, tap (r, s) reads dy at (h + pad - r, w + pad - s), i.e. at
+            // row 2*pad - r / column 2*pad - s of the haloed tile
+            const bool halo = stride == 1 && !residual && setup_conv_halo(p, B, Ho, Wo, Cout, R, S, pad);
+            if (halo) {
+                for (int k = 0; k < t; ++k) {
+                    p.tap_dh[k] = (signed char)(p.tap_dh[k] + pad);
+                    p.tap_dw[k] = (signed char)(p.tap_dw[k] + pad);
+                }
+            } else {
+                choose_box(Wp, Hp, B, TG_BM, &p.box_w, &p.box_h, &p.box_n);
+                p.m_rows = p.box_w * p.box_h * p.box_n;
+                p.tiles_w = (Wp + p.box_w - 1) / p.box_w;
+                p.tiles_h = (Hp + p.box_h - 1) / p.box_h;
+                p.tiles_n = (B + p.box_n - 1) / p.box_n;
+            }
             p.out_w = Wp;
             p.out_h = Hp;
             p.out_n = B;
             p.chunks = (Cout + TG_BK - 1) / TG_BK;
             const int box[4] = {TG_BK, p.box_w, p.box_h, p.box_n};
-            if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, box)) return 1;
+            const int hbox[4] = {TG_BK, p.halo_w, p.halo_h, 1};
+            if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, halo ? hbox : box)) return 1;
             const long long dims[4] = {Cout, Cin, (long long)R * S, 1};
             const long long strides[3] = {Cout, (long long)Cin * Cout, (long long)Cin * Cout * R * S};
             const int bbox[4] = {TG_BK, p.bn, 1, 1};
@@ -343,7 +428,14 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             p.residual = residual;
             p.res_mask = res_mask;
             p.ld_res = Cin;
-            pick_pipeline(p, p.n_taps * p.chunks);
+            if (halo) {
+                pick_pipeline_halo(p);
+                for (int k = 0; k < t; ++k) PE_REQUIRE(p.tap_b[k] == k, "conv_dgrad halo: taps out of order");
+                const int tbox[4] = {TG_BK, p.bn, p.b_taps, 1};
+                if (make_map(&maps.b[1], w_tkc, dims, strides, tbox)) return 1;
+            } else {
+                pick_pipeline(p, p.n_taps * p.chunks);
+            }
             dim3 grid((Cin + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
             if (launch_tapgemm(maps, p, grid, stream)) return 2;
         }
@@ -638,6 +730,11 @@ void pe_debug_wgrad_halo(int mode) { g_dbg_wgrad_halo = mode; }
 void pe_debug_residual_tma(int on) { g_dbg_res_tma = on; }
 
 void pe_debug_epilogue_groups(int groups) { g_dbg_epi_groups = groups; }
+
+void pe_debug_conv_halo(int on) {
+    g_dbg_conv_halo = on & 1;
+    g_dbg_halo_btaps = on >> 4;      // optional: taps per weight stage in bits 4..
+}
 
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
     g_dbg_desc[0] = a_lbo;

@@ -101,6 +101,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_full[TG_STAGES];
     __shared__ __align__(8) uint64_t s_empty[TG_STAGES];
+    __shared__ __align__(8) uint64_t s_bfull[8];      // weight ring of the haloed conv (conv_halo)
+    __shared__ __align__(8) uint64_t s_bempty[8];
     __shared__ __align__(8) uint64_t s_tmem_full[2];
     __shared__ __align__(8) uint64_t s_tmem_empty[2];
     __shared__ __align__(8) uint64_t s_res_full[2 * G];
@@ -115,10 +117,12 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 
     // 1024-byte aligned tile storage (SWIZZLE_128B atoms are 1024 B)
     const uint32_t smem_base = smem_u32(smem_raw);
-    const uint32_t stage_base = smem_base + p.stages * p.stage_bytes;   // nout x 16 KB epilogue staging
+    const uint32_t bring_base = smem_base + p.stages * p.stage_bytes;   // weight ring of the haloed conv (or empty)
+    const uint32_t stage_base = bring_base + p.b_ring_bytes;            // nout x 16 KB epilogue staging
     // CTA-wide per-channel statistics (one global atomic per channel per CTA instead of per tile)
     const uint32_t res_base = stage_base + p.nout * TG_A_BYTES;          // nres x 16 KB residual tiles
-    float* s_sum = reinterpret_cast<float*>(smem_raw + p.stages * p.stage_bytes + (p.nout + p.nres) * TG_A_BYTES);
+    float* s_sum = reinterpret_cast<float*>(smem_raw + p.stages * p.stage_bytes + p.b_ring_bytes +
+                                            (p.nout + p.nres) * TG_A_BYTES);
     float* s_sq = s_sum + p.stats_cols;
     // per-tile scratch of the statistics: [group][chunk slot][warp 4][sum 32 | sq 32] (8 KB, only with stats)
     float* s_part = s_sum + 2 * p.stats_cols;
@@ -128,6 +132,10 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         for (int s = 0; s < TG_STAGES; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
             mbar_init(smem_u32(&s_empty[s]), 1);
+        }
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(smem_u32(&s_bfull[s]), 1);
+            mbar_init(smem_u32(&s_bempty[s]), 1);
         }
         for (int a = 0; a < 2 * G; ++a) mbar_init(smem_u32(&s_res_full[a]), 1);
         for (int a = 0; a < 2; ++a) {
@@ -156,12 +164,46 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         // =============================== TMA producer ========================================
         // The whole warp runs this loop convergently; every barrier result is vote-derived, so coordinates,
         // stage counters and addresses stay in uniform registers and one elected lane issues each TMA.
-        uint32_t s = 0, ph = 0;
+        uint32_t s = 0, ph = 0, sb = 0, phb = 0;
         bool ok = true;
         for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
             const Work wk = decode_work(p, w);
             const int n_off = wk.nt * p.bn;
-            if (p.mode == 0) {
+            if (p.mode == 0 && p.conv_halo) {
+                // haloed stride-1 conv: one haloed A tile per channel chunk, then one weight tile per tap
+                const TileOrigin o = tile_origin(p, wk.mt);
+                const uint32_t a_bytes = static_cast<uint32_t>(p.halo_w * p.halo_h) * 128u;
+                const uint32_t b_bytes = static_cast<uint32_t>(p.bn * p.b_taps) * 128u;
+                for (int ch = 0; ch < p.chunks && ok; ++ch) {
+                    if (!mbar_wait_warp(smem_u32(&s_empty[s]), ph ^ 1, spin)) {
+                        atomicOr(p.error_flag, 1);
+                        ok = false;
+                        break;
+                    }
+                    mbar_arrive_expect_tx_elect(smem_u32(&s_full[s]), a_bytes);
+                    tma_load_4d_elect(smem_base + s * p.stage_bytes, &maps.a[0], smem_u32(&s_full[s]), ch * TG_BK,
+                                      o.w0 + p.halo_dw, o.h0 + p.halo_dh, o.n0);
+                    if (++s == static_cast<uint32_t>(p.stages)) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                    for (int t = 0; t < p.n_taps; t += p.b_taps) {
+                        if (!mbar_wait_warp(smem_u32(&s_bempty[sb]), phb ^ 1, spin)) {
+                            atomicOr(p.error_flag, 1);
+                            ok = false;
+                            break;
+                        }
+                        mbar_arrive_expect_tx_elect(smem_u32(&s_bfull[sb]), b_bytes);
+                        // one box {32 ch, bn rows, b_taps taps}: the weight tiles of b_taps consecutive taps
+                        tma_load_4d_elect(bring_base + sb * p.b_bytes, &maps.b[1], smem_u32(&s_bfull[sb]), ch * TG_BK,
+                                          n_off, t, 0);
+                        if (++sb == static_cast<uint32_t>(p.b_stages)) {
+                            sb = 0;
+                            phb ^= 1;
+                        }
+                    }
+                }
+            } else if (p.mode == 0) {
                 const TileOrigin o = tile_origin(p, wk.mt);
                 uint32_t nbytes = static_cast<uint32_t>(p.m_rows + p.bn) * 128u;
                 if (p.dbg_flags & 4) nbytes -= static_cast<uint32_t>(p.m_rows) * 128u;
@@ -299,7 +341,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         const uint64_t b_desc0 = p.mode == 2 ? make_smem_desc(0, p.b_atom_bytes, 512, 1u)
                                              : make_smem_desc(0, b_lbo, b_sbo, ltype);
         const uint32_t kstep16 = (p.mode ? 1024u : 32u) >> 4;  // 8 tf32 along K, in 16-byte units
-        uint32_t s = 0, ph = 0, tile_i = 0;   // tile_i counts tiles that really use an accumulator
+        uint32_t s = 0, ph = 0, sb = 0, phb = 0, tile_i = 0;   // tile_i counts tiles that really use an accumulator
         bool ok = true;
         for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
             const Work wk = decode_work(p, w);
@@ -354,6 +396,52 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         }
                     }
                     tc_commit_elect(smem_u32(&s_empty[s]));
+                    if (++s == static_cast<uint32_t>(p.stages)) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+                if (ok) tc_commit_elect(smem_u32(&s_tmem_full[acc]));
+                continue;
+            }
+            if (p.conv_halo) {
+                // A descriptors: 8-pixel row groups are halo_w rows apart; tap (r, s) starts r * halo_w + s rows in
+                const uint64_t ah_desc0 = make_smem_desc(0, 16, static_cast<uint32_t>(p.halo_w) * 128u, 2u);
+                uint32_t accf = 0u;
+                for (int ch = 0; ch < p.chunks && ok; ++ch) {
+                    if (!mbar_wait_warp(smem_u32(&s_full[s]), ph, spin)) {
+                        atomicOr(p.error_flag, 4);
+                        ok = false;
+                        break;
+                    }
+                    tc_fence_after();
+                    const uint64_t ad0 = ah_desc0 + ((smem_base + s * p.stage_bytes) >> 4);
+                    for (int t = 0; t < p.n_taps; t += p.b_taps) {
+                        if (!mbar_wait_warp(smem_u32(&s_bfull[sb]), phb, spin)) {
+                            atomicOr(p.error_flag, 4);
+                            ok = false;
+                            break;
+                        }
+                        tc_fence_after();
+                        const uint64_t bd0 = b_desc0 + ((bring_base + sb * p.b_bytes) >> 4);
+                        const uint32_t tap16 = static_cast<uint32_t>(p.bn) * 8u;      // one weight tile, 16-byte units
+                        for (int tl = 0; tl < p.b_taps; ++tl) {
+                            const uint64_t ad =
+                                ad0 + static_cast<uint32_t>(p.tap_dh[t + tl] * p.halo_w + p.tap_dw[t + tl]) * 8u;
+                            const uint64_t bd = bd0 + tl * tap16;
+#pragma unroll
+                            for (int kk = 0; kk < TG_BK / 8; ++kk) {
+                                tc_mma_tf32_elect(tmem_d, ad + kk * 2u, bd + kk * 2u, idesc, accf);
+                                accf = 1u;
+                            }
+                        }
+                        tc_commit_elect(smem_u32(&s_bempty[sb]));
+                        if (++sb == static_cast<uint32_t>(p.b_stages)) {
+                            sb = 0;
+                            phb ^= 1;
+                        }
+                    }
+                    tc_commit_elect(smem_u32(&s_empty[s]));       // the haloed tile is free once its taps retire
                     if (++s == static_cast<uint32_t>(p.stages)) {
                         s = 0;
                         ph ^= 1;
@@ -739,6 +827,15 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
         configured = true;
     }
     if (p.epi_groups != 4) p.epi_groups = 2;
+    {
+        // the carve-up of dynamic shared memory must fit: ring + weight ring + store staging + residual tiles +
+        // statistics scratch (a violation here would be an out-of-bounds shared-memory access on the device)
+        const long long need = (long long)p.stages * p.stage_bytes + p.b_ring_bytes +
+                               (long long)(p.store_mode == TG_STORE_TMA ? p.nout + p.nres : 0) * TG_A_BYTES +
+                               (p.stats ? 2ll * p.stats_cols * (long long)sizeof(float) + 8192 : 0);
+        PE_REQUIRE(p.stages >= 1 && need <= TG_SMEM_BYTES, "tap-GEMM shared-memory plan of %lld bytes does not fit in %d",
+                   need, TG_SMEM_BYTES);
+    }
     p.work_n = work.x;
     p.work_m = work.y;
     p.work_total = static_cast<int>(work.x * work.y * work.z);

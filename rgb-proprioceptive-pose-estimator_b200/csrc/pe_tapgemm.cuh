@@ -83,6 +83,13 @@ struct TapParams {
     int a_atom_bytes, b_atom_bytes;   // bytes between 32-channel atoms of the dY / X tiles in a stage
     int a_region_bytes;       // offset of the B (X) region inside a stage
     int base_offset_mode;     // debug: 1 = put (start >> 7) & 7 into the descriptors' base-offset field
+    // haloed stride-1 conv (mode 0 with conv_halo = 1): the A ring holds one haloed pixel tile per channel chunk
+    // (halo_w x halo_h x 1 rows of 128 B, stage_bytes each); every tap reads its shifted window of it through its own
+    // descriptor (8-pixel row groups SBO = halo_w * 128 B apart); weights stream through a separate B ring.
+    int conv_halo;
+    int b_stages, b_bytes;    // B ring: stages and bytes per stage (b_taps * bn * 128)
+    int b_taps;               // filter taps per B stage (one TMA box {32, bn, b_taps}); divides n_taps
+    int b_ring_bytes;         // b_stages * b_bytes (0 when conv_halo == 0): offset of the store staging after the A ring
 };
 
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream);

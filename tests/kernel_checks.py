@@ -570,6 +570,18 @@ def check_preprocess(B):
     return [("preprocess_u8 B%d" % B, relerr(out, ref), 1e-6)]
 
 
+def check_conv_halo_path(*args):
+    """The haloed-tile 3x3 stride-1 forward / dgrad (off by default: pe_debug_conv_halo) must stay correct."""
+    L = native.lib()
+    L.pe_debug_conv_halo(1)
+    try:
+        rows = [(n.replace("conv_", "conv_halo_"), e, t) for n, e, t in check_conv(*args)
+                if n.startswith("conv_fwd") or (n.startswith("conv_dgrad") and "+" not in n)]
+    finally:
+        L.pe_debug_conv_halo(0)
+    return rows
+
+
 ALL = [
     lambda: check_linear(128, 128, 32, bias=False),
     lambda: check_linear(128, 128, 256),
@@ -593,6 +605,8 @@ ALL = [
     lambda: check_conv(3, 14, 14, 512, 512, 3, 2),
     lambda: check_conv(1, 7, 7, 2048, 512, 1, 1),
     lambda: check_conv(2, 14, 14, 1024, 2048, 1, 2),
+    lambda: check_conv_halo_path(2, 56, 56, 64, 64, 3, 1),
+    lambda: check_conv_halo_path(3, 28, 28, 128, 128, 3, 1),
     lambda: check_conv_fused_eval(2, 28, 28, 128, 512, 1),
     lambda: check_stem(2),
     lambda: check_bn(6272, 64),
