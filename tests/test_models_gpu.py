@@ -471,3 +471,20 @@ def test_odd_batch_sizes(n):
     fwd, grads, struct = _split(rows)
     bad = [(name, e) for name, e, t in fwd if not e <= max(t, 5e-3)] + [(name, e) for name, e, t in struct if e != 0.0]
     assert not bad, bad
+
+
+def test_device_prefetcher_order_and_values():
+    """DevicePrefetcher yields every batch, in order, with the host values, while copying one batch ahead."""
+    from pe_b200.loader import DevicePrefetcher
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(4, 3, 8, 8, generator=g).pin_memory(), (torch.randn(4, 7, generator=g).pin_memory(),
+                                                                     torch.randn(4, 7, generator=g).pin_memory()))
+               for _ in range(5)]
+    seen = 0
+    for k, (img, (a, b)) in enumerate(DevicePrefetcher(batches, dev)):
+        # consume on the compute stream before the slot can be recycled
+        assert torch.equal(img.cpu(), batches[k][0]) and torch.equal(a.cpu(), batches[k][1][0])
+        assert torch.equal(b.cpu(), batches[k][1][1])
+        seen += 1
+    assert seen == 5
