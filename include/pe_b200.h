@@ -33,6 +33,8 @@ void pe_debug_flags(int flags);
 void pe_debug_pipeline(int stages, int nout);
 /* debug: cap the tile width (128 or 256 columns) */
 void pe_debug_max_bn(int bn);
+/* debug: narrowest tile (32 by default) the few-tiles heuristic may pick for launches that cannot fill the SMs */
+void pe_debug_min_bn(int bn);
 /* debug: stride-1 multi-tap wgrad path: 0 one tap per work item, 1 haloed tile (default), 2 haloed tile with the
  * descriptors' base-offset field set */
 void pe_debug_wgrad_halo(int mode);

@@ -158,10 +158,17 @@ static void init_params(TapParams& p) {
 
 static int g_dbg_max_bn = 256;
 static int g_dbg_res_tma = 1;
+static int g_dbg_min_bn = 32;         // narrowest tile the small-launch heuristic of pick_bn may choose
 static int g_dbg_epi_groups = 0;      // 0 = automatic, 2 / 4 = forced
-static int pick_bn(int n_total) {
-    if (n_total >= 256 && g_dbg_max_bn >= 256) return 256;
-    return n_total >= 128 ? 128 : ((n_total + 15) / 16) * 16;
+// Tile width.  Wide tiles halve the operand traffic per MMA, but a launch with only a handful of tiles (rollout at
+// batch 1: 49-3136 pixels per image) would leave most SMs idle behind one long serial K loop: there the width is
+// halved (down to 64) until the tile count reaches half the SM count.
+static int pick_bn(int n_total, long long m_tiles = 1 << 20) {
+    int bn;
+    if (n_total >= 256 && g_dbg_max_bn >= 256) bn = 256;
+    else bn = n_total >= 128 ? 128 : ((n_total + 15) / 16) * 16;
+    while (bn > g_dbg_min_bn && m_tiles * ((n_total + bn - 1) / bn) * 2 <= num_sms()) bn >>= 1;
+    return bn;
 }
 
 // Split the 216 KB of dynamic shared memory between the operand ring and the store staging buffers.
@@ -281,7 +288,7 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
     TapParams p;
     init_params(p);
     p.mode = 0;
-    p.bn = pick_bn(Cout);
+    p.bn = pick_bn(Cout, ((long long)B * Ho * Wo + TG_BM - 1) / TG_BM);
     const bool halo = stride == 1 && !ep.residual && setup_conv_halo(p, B, H, W, Cin, R, S, pad);
     if (!halo) {
         choose_box(Wo, Ho, B, TG_BM, &p.box_w, &p.box_h, &p.box_n);
@@ -380,8 +387,8 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             TapParams p;
             init_params(p);
             p.mode = 0;
-            p.bn = pick_bn(Cin);
             const int Hp = (H - ph + stride - 1) / stride, Wp = (W - pw + stride - 1) / stride;
+            p.bn = pick_bn(Cin, ((long long)B * Hp * Wp + TG_BM - 1) / TG_BM);
             int t = 0;
             for (int r = 0; r < R; ++r)
                 for (int s = 0; s < S; ++s) {
@@ -600,7 +607,7 @@ static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, flo
     TapParams p;
     init_params(p);
     p.mode = 0;
-    p.bn = pick_bn(N);
+    p.bn = pick_bn(N, (M + TG_BM - 1) / TG_BM);
     p.box_w = TG_BM;
     p.box_h = p.box_n = 1;
     p.m_rows = TG_BM;
@@ -724,6 +731,8 @@ void pe_debug_pipeline(int stages, int nout) {
 }
 
 void pe_debug_max_bn(int bn) { g_dbg_max_bn = bn > 0 ? bn : 256; }
+
+void pe_debug_min_bn(int bn) { g_dbg_min_bn = bn >= 16 ? bn : 32; }
 
 void pe_debug_wgrad_halo(int mode) { g_dbg_wgrad_halo = mode; }
 

@@ -19,6 +19,11 @@ def main():
     global RAW
     argv = [a for a in sys.argv[1:] if a != "--raw"]
     RAW = "--raw" in sys.argv
+    for a in list(argv):
+        if a.startswith("--min-bn="):
+            from pe_b200 import native
+            native.lib().pe_debug_min_bn(int(a.split("=")[1]))
+            argv.remove(a)
     kind = argv[0] if argv else "tdo"
     batches = [int(a) for a in argv[1:]] or [1, 8, 64, 256, 1024]
     model = mc.build_model(kind).cuda().eval()
