@@ -12,6 +12,8 @@
 
 namespace pe {
 
+extern int g_pdl;      // pe_tapgemm.cu: programmatic dependent launch switch
+
 // ---------------------------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------------------------
@@ -739,6 +741,8 @@ void pe_debug_wgrad_halo(int mode) { g_dbg_wgrad_halo = mode; }
 void pe_debug_residual_tma(int on) { g_dbg_res_tma = on; }
 
 void pe_debug_epilogue_groups(int groups) { g_dbg_epi_groups = groups; }
+
+void pe_debug_pdl(int on) { pe::g_pdl = on ? 1 : 0; }
 
 void pe_debug_conv_halo(int on) {
     g_dbg_conv_halo = on & 1;

@@ -11,6 +11,8 @@
 //                                  per-channel batch statistics as a column pass over the staged tile
 // Warps 0 and 1 run warp-convergent (role dispatch on a shfl-broadcast warp index, vote-derived barrier results,
 // elect.sync inside the issuing asm) so that descriptors, coordinates and counters stay on the uniform datapath.
+#include <stdlib.h>
+
 #include "pe_tapgemm.cuh"
 
 namespace pe {
@@ -158,6 +160,11 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) touched no
+    // global memory, so it may overlap the tail of the previous kernel in the stream.  Let the NEXT kernel start its
+    // own prologue now, then wait until the previous grid has completed and flushed before reading its outputs.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int spin = (p.dbg_flags & 128) ? 1 : 0;   // probe: non-blocking barrier polls in the producer / MMA warps
 
     if (warp == 0) {
@@ -817,6 +824,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 
 }  // namespace
 
+int g_pdl = 1;      // programmatic dependent launch of the tap-GEMM (pe_debug_pdl)
+
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
@@ -824,6 +833,7 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
                                            TG_SMEM_BYTES));
         PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TG_SMEM_BYTES));
+        if (const char* e = getenv("PE_B200_PDL")) g_pdl = atoi(e) != 0;
         configured = true;
     }
     if (p.epi_groups != 4) p.epi_groups = 2;
@@ -841,10 +851,20 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
     p.work_total = static_cast<int>(work.x * work.y * work.z);
     int grid = p.work_total < num_sms() ? p.work_total : num_sms();
     if (grid < 1) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(64 + 128 * p.epi_groups, 1, 1);
+    cfg.dynamicSmemBytes = TG_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
     if (p.epi_groups == 4)
-        tapgemm_kernel<4><<<grid, 64 + 128 * 4, TG_SMEM_BYTES, stream>>>(maps, p);
+        PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<4>, maps, p));
     else
-        tapgemm_kernel<2><<<grid, 64 + 128 * 2, TG_SMEM_BYTES, stream>>>(maps, p);
+        PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, maps, p));
     PE_LAUNCH_CHECK();
     return 0;
 }

@@ -20,7 +20,11 @@ def main():
     argv = [a for a in sys.argv[1:] if a != "--raw"]
     RAW = "--raw" in sys.argv
     for a in list(argv):
-        if a.startswith("--min-bn="):
+        if a == "--no-pdl":
+            from pe_b200 import native
+            native.lib().pe_debug_pdl(0)
+            argv.remove(a)
+        elif a.startswith("--min-bn="):
             from pe_b200 import native
             native.lib().pe_debug_min_bn(int(a.split("=")[1]))
             argv.remove(a)
