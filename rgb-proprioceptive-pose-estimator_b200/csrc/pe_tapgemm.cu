@@ -457,6 +457,10 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                 if (ok) tc_commit_elect(smem_u32(&s_tmem_full[acc]));
                 continue;
             }
+            // descriptor arithmetic on the low words only (the 14-bit address field cannot carry): half the uniform ALU
+            // work per MMA of a 64-bit add
+            const uint32_t a_hi0 = static_cast<uint32_t>(a_desc0 >> 32), b_hi0 = static_cast<uint32_t>(b_desc0 >> 32);
+            const uint32_t a_lo00 = static_cast<uint32_t>(a_desc0), b_lo00 = static_cast<uint32_t>(b_desc0);
             for (int j = 0; j < wk.nk; ++j) {
                 if (!mbar_wait_warp(smem_u32(&s_full[s]), ph, spin)) {
                     atomicOr(p.error_flag, 4);
@@ -464,12 +468,14 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     break;
                 }
                 tc_fence_after();
-                const uint32_t sa = smem_base + s * p.stage_bytes;
-                const uint64_t ad = a_desc0 + (sa >> 4);
-                const uint64_t bd = b_desc0 + ((sa + TG_A_BYTES) >> 4);
+                const uint32_t sa16 = (smem_base + s * p.stage_bytes) >> 4;
+                const uint32_t a_lo = a_lo00 + sa16;
+                const uint32_t b_lo = b_lo00 + sa16 + (static_cast<uint32_t>(TG_A_BYTES) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < TG_BK / 8; ++kk)
-                    tc_mma_tf32_elect(tmem_d, ad + kk * kstep16, bd + kk * kstep16, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                    tc_mma_tf32_elect(tmem_d, (static_cast<uint64_t>(a_hi0) << 32) | (a_lo + kk * kstep16),
+                                      (static_cast<uint64_t>(b_hi0) << 32) | (b_lo + kk * kstep16), idesc,
+                                      (j > 0 || kk > 0) ? 1u : 0u);
                 tc_commit_elect(smem_u32(&s_empty[s]));  // frees the stage when these MMAs retire
                 if (++s == static_cast<uint32_t>(p.stages)) {
                     s = 0;
