@@ -32,6 +32,38 @@ SEQ_KINDS = ("td", "tdo", "tdo_v2")
 TRAIN_MB_PER_FRAME = 223.0                                                # SURVEY 8(d) compulsory fp32 traffic
 
 
+def resnet50_convs():
+    """(H, Cin, Cout, k, stride, pad) of every convolution of torchvision's resnet50 at 224x224 input
+    (util/model_utils.py:10-31 builds exactly this trunk)."""
+    convs = [(224, 3, 64, 7, 2, 3)]
+    H, cin = 56, 64
+    for planes, blocks, stride in ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)):
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            convs += [(H, cin, planes, 1, 1, 0), (H, planes, planes, 3, s, 1), (H // s, planes, planes * 4, 1, 1, 0)]
+            if b == 0:
+                convs.append((H, cin, planes * 4, 1, s, 0))
+            H, cin = H // s, planes * 4
+    return convs
+
+
+def layerwise_bound_ms(batch, hbm_gbs, tf32_tflops):
+    """Sum over every conv pass (forward, dgrad, wgrad; no dgrad for the stem) of max(algorithmic bytes / HBM peak,
+    flops / TF32 peak): the time the convolutions would take if each ran at whichever roofline bounds it.  The narrow
+    1x1 convolutions (K or N = 64..128) are HBM-bound, the 3x3 ones tensor-bound, so neither peak alone describes the
+    family.  Returns (bound ms, algorithmic GB, GFLOP)."""
+    t = by_tot = fl_tot = 0.0
+    for i, (H, ci, co, k, s, p) in enumerate(resnet50_convs()):
+        Ho = (H + 2 * p - k) // s + 1
+        by = 4.0 * (batch * H * H * ci + batch * Ho * Ho * co + co * ci * k * k)
+        fl = 2.0 * batch * Ho * Ho * co * ci * k * k
+        n_pass = 2 if i == 0 else 3
+        t += n_pass * max(by / (hbm_gbs * 1e9), fl / (tf32_tflops * 1e12))
+        by_tot += n_pass * by
+        fl_tot += n_pass * fl
+    return t * 1e3, by_tot / 1e9, fl_tot / 1e9
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -321,6 +353,7 @@ def run_ours(args):
                 rate = gb / (fam[fname] / 1e3)
                 hbm_kernels[fname] = {"ms": round(fam[fname], 3), "dram_GB": round(gb, 3), "GB_per_s": round(rate, 1),
                                       "frac_of_peak": round(rate / pk["hbm"], 3)}
+    lw_ms, lw_gb, _ = layerwise_bound_ms(frames, pk["hbm"], tf32_peak)
     gemm_launches = prof.get("tapgemm_kernel", {}).get("launches")
     gemm_traffic = None
     if kind == "no" and args.batch == 256 and gemm_launches:
@@ -342,7 +375,12 @@ def run_ours(args):
                      "algorithmic_flop_per_step": TRAIN_GFLOP_PER_FRAME[kind] * frames * 1e9,
                      "launches_per_step": gemm_launches,
                      "peak_source": "%s bf16 sustained / 2 (TF32 runs at half the bf16 rate)" % pk["which"],
-                     "share_of_step": gemm_ms / total_ms if total_ms else None},
+                     "share_of_step": gemm_ms / total_ms if total_ms else None,
+                     "layerwise_bound": {"ms": round(lw_ms, 3), "measured_ms": round(gemm_ms, 3),
+                                         "frac": round(lw_ms / gemm_ms, 3) if gemm_ms else None,
+                                         "algorithmic_GB_per_step": round(lw_gb, 2),
+                                         "note": "sum over conv passes of max(bytes/HBM peak, flops/TF32 peak): the "
+                                                 "narrow 1x1 convs are HBM-bound, the 3x3 convs tensor-bound"}},
         "roofline_step": {"bound": "hbm", "achieved": TRAIN_MB_PER_FRAME * frames / 1e3 / (ms / args.steps / 1e3),
                           "peak": pk["hbm"], "unit": "GB/s",
                           "frac": TRAIN_MB_PER_FRAME * frames / 1e3 / (ms / args.steps / 1e3) / pk["hbm"],
