@@ -82,6 +82,27 @@ def test_bench_gpu_arm_is_independent_of_the_oracle():
     assert not offenders, offenders
 
 
+def test_bench_conv_table_matches_the_trunk():
+    """bench.py's analytic per-layer roofline walks the same 53 convolutions as the mirrored trunk
+    (util/model_utils.py:10-31) and its flop count agrees with SURVEY 8(d)'s 24.3 GFLOP per training frame."""
+    import importlib.util
+    import torch
+    path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py")
+    spec = importlib.util.spec_from_file_location("bench_for_test", path)
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    import model_checks as mc
+    convs = [m for n, m in mc.build_model("no").named_modules()
+             if isinstance(m, torch.nn.Conv2d) and n.startswith("feature_net.")]
+    table = b.resnet50_convs()
+    assert len(table) == len(convs) == 53
+    assert sorted((ci, co, k, s, p) for _, ci, co, k, s, p in table) == \
+        sorted((m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.padding[0]) for m in convs)
+    ms, gb, gflop = b.layerwise_bound_ms(256, 6455.6, 709.0)
+    assert abs(gflop / 256 - b.TRAIN_GFLOP_PER_FRAME["no"]) < 0.1
+    assert 8.0 < ms < 20.0 and 60.0 < gb < 70.0
+
+
 @pytest.mark.parametrize("kind", ["no", "n", "td", "tdo", "tdo_v2"])
 def test_state_dict_layout_matches_reference_manifest(kind):
     """Keys, order, shapes, dtypes, parameter order and the seed-0 init values equal the reference's
