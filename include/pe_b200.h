@@ -157,6 +157,21 @@ int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, i
  * dw[C] += ..., db[1] += ... (dw/db may be NULL: frozen aux conv, td model) */
 int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const float* a1, const float* w,
                float* da1, int accumulate, float* dw, float* db, int B, int H, int W, int C, void* stream);
+/* The aux conv's own gradients when bn1's output was never materialised (pe_stem_post_train): the activation at
+ * every arg-max pixel is rebuilt as relu(y*scale + shift) (rounded to TF32 when round_tf32) from conv1's output y. */
+int pe_aux_bwd_params(const float* dout, int lddo, const unsigned char* argmax, const float* y, const float* scale,
+                      const float* shift, int round_tf32, float* dw, float* db, int B, int H, int W, int C,
+                      void* stream);
+/* Training-mode stem tail in one pass over conv1's output y [B,H,W,64] (torchvision resnet.py:268-272 bn1, relu,
+ * maxpool + the aux branch above): pe_bn_train_apply (batch statistics from `stats`, running-stat update, ReLU),
+ * pe_maxpool3x3s2_fwd and pe_aux_fwd without ever writing the normalised activation.  pool [B,H/2,W/2,64] and
+ * pool_argmax as pe_maxpool3x3s2_fwd; aux_* as pe_aux_fwd (aux_w NULL: no aux branch); argmax maps may be NULL.  */
+int pe_stem_post_train(const float* y, const double* stats, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, long long* num_batches_tracked, float* scale,
+                       float* shift, float* mean, float* invstd, float* pool, unsigned char* pool_argmax,
+                       const float* aux_w, const float* aux_bias, float* aux_out, int ld_aux,
+                       unsigned char* aux_argmax, int B, int H, int W, int C, float momentum, float eps,
+                       int round_tf32, int aux_round_tf32, void* stream);
 
 /* ---- depth branch (use_depth=True; models/naive.py:233-240,324-330, models/time_sensitive.py:387-394,481-487):
  *      depth (B,1,H,W) -> AvgPool2d(2) x log2(pool) -> InstanceNorm2d(1, affine, biased variance, eps) -> Flatten,

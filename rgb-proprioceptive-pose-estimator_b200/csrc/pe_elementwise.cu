@@ -820,7 +820,8 @@ aux_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ w, const 
 __global__ void __launch_bounds__(EW_THREADS)
 aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __restrict__ argmax,
                const float* __restrict__ a1, const float* __restrict__ w, float* __restrict__ da1, int accumulate,
-               float* __restrict__ dw, float* __restrict__ db, int B, int H, int W, int C) {
+               float* __restrict__ dw, float* __restrict__ db, int B, int H, int W, int C,
+               const float* __restrict__ pre_scale, const float* __restrict__ pre_shift, int pre_round) {
     __shared__ float s_dw[256];
     __shared__ float s_db;
     const int Ho = H >> 1, Wo = W >> 1;
@@ -858,7 +859,13 @@ aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __
                     }
                 }
                 if (dw) {
-                    const float4 av = ld4_stream(a1 + base + ((long long)(am >> 1) * W + (am & 1)) * C + c);
+                    float4 av = ld4_stream(a1 + base + ((long long)(am >> 1) * W + (am & 1)) * C + c);
+                    if (pre_scale) {   // `a1` is the pre-BN tensor: the activation is rebuilt on the fly
+                        const float4 sc = ld4(pre_scale + c), sh = ld4(pre_shift + c);
+                        av.x = fmaxf(fmaf(av.x, sc.x, sh.x), 0.f); av.y = fmaxf(fmaf(av.y, sc.y, sh.y), 0.f);
+                        av.z = fmaxf(fmaf(av.z, sc.z, sh.z), 0.f); av.w = fmaxf(fmaf(av.w, sc.w, sh.w), 0.f);
+                        if (pre_round) av = round4(av);
+                    }
                     pdw[j].x = fmaf(d, av.x, pdw[j].x); pdw[j].y = fmaf(d, av.y, pdw[j].y);
                     pdw[j].z = fmaf(d, av.z, pdw[j].z); pdw[j].w = fmaf(d, av.w, pdw[j].w);
                 }
@@ -879,6 +886,125 @@ aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __
         __syncthreads();
         for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dw + c, s_dw[c]);
         if (threadIdx.x == 0 && db) atomicAdd(db, s_db);
+    }
+}
+
+// Training-mode stem tail in ONE pass over the conv1 output y [B,H,W,64]: BatchNorm with batch statistics + ReLU,
+// the 3x3 / stride 2 / pad 1 max pool and the aux branch (1x1 conv to one channel + 2x2 max pool, whose window is
+// the lower-right 2x2 of the pooling window).  The normalised activation is never written: the backward pass needs
+// the two arg-max maps, y and scale / shift only (bn_train_apply + maxpool_fwd + aux_fwd would write it once and
+// read it twice: 2.5 GB per 256-frame step).  A half-warp owns one pooled pixel (16 lanes x 4 channels); the
+// arithmetic is that of the three separate kernels, expression for expression.
+__global__ void __launch_bounds__(EW_THREADS)
+stem_post_train_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                       long long* __restrict__ num_batches_tracked, float* __restrict__ scale_out,
+                       float* __restrict__ shift_out, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                       float* __restrict__ pool, unsigned char* __restrict__ pool_argmax,
+                       const float* __restrict__ aux_w, const float* __restrict__ aux_bias,
+                       float* __restrict__ aux_out, int ld_aux, unsigned char* __restrict__ aux_argmax, int B, int H,
+                       int W, float momentum, float eps, int round_out, int aux_round) {
+    constexpr int C = 64;
+    __shared__ __align__(16) float csc[C];
+    __shared__ __align__(16) float csh[C];
+    const double count = (double)B * H * W;
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        const double m = stats[c] / count;
+        double var = stats[C + c] / count - m * m;
+        if (var < 0.0) var = 0.0;
+        const float mean = (float)m;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = gamma[c] * invstd;
+        const float sh = beta[c] - mean * sc;
+        csc[c] = sc;
+        csh[c] = sh;
+        if (blockIdx.x == 0) {
+            scale_out[c] = sc;
+            shift_out[c] = sh;
+            mean_out[c] = mean;
+            invstd_out[c] = invstd;
+            if (running_mean) {
+                const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+            if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+        }
+    }
+    __syncthreads();
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    const float4 sc = ld4(csc + 4 * hl), sh = ld4(csh + 4 * hl);
+    const float4 w4 = aux_w ? ld4(aux_w + 4 * hl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float b0 = aux_w ? aux_bias[0] : 0.f;
+    const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nwin = (long long)B * Ho * Wo;
+    const long long npair = (nwin + 1) >> 1;
+    for (long long pair = gwarp; pair < npair; pair += nwarps) {       // warp-uniform trip count
+        const long long win = pair * 2 + half;
+        const bool valid = win < nwin;
+        const long long wv = valid ? win : 0;
+        const int wo = (int)(wv % Wo);
+        const int ho = (int)((wv / Wo) % Ho);
+        const int b = (int)(wv / ((long long)Wo * Ho));
+        float4 v[9];
+        bool in[9];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int h = 2 * ho - 1 + kh;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int w = 2 * wo - 1 + kw;
+                in[kh * 3 + kw] = h >= 0 && w >= 0;          // h < H, w < W always hold for even H, W
+                if (in[kh * 3 + kw]) v[kh * 3 + kw] = ld4(y + (((long long)b * H + h) * W + w) * C + 4 * hl);
+            }
+        }
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        uchar4 am = make_uchar4(255, 255, 255, 255);
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (!in[k]) continue;
+            float4 o;
+            o.x = fmaxf(fmaf(v[k].x, sc.x, sh.x), 0.f);
+            o.y = fmaxf(fmaf(v[k].y, sc.y, sh.y), 0.f);
+            o.z = fmaxf(fmaf(v[k].z, sc.z, sh.z), 0.f);
+            o.w = fmaxf(fmaf(v[k].w, sc.w, sh.w), 0.f);
+            if (round_out) o = round4(o);
+            const unsigned char kk = (unsigned char)k;
+            if (o.x > m.x || am.x == 255) { m.x = o.x; am.x = kk; }
+            if (o.y > m.y || am.y == 255) { m.y = o.y; am.y = kk; }
+            if (o.z > m.z || am.z == 255) { m.z = o.z; am.z = kk; }
+            if (o.w > m.w || am.w == 255) { m.w = o.w; am.w = kk; }
+            if (k == 4 || k == 5 || k == 7 || k == 8)        // the aux window: rows 2ho, 2ho+1 x cols 2wo, 2wo+1
+                s[(k / 3 - 1) * 2 + (k % 3 - 1)] += o.x * w4.x + o.y * w4.y + o.z * w4.z + o.w * w4.w;
+        }
+        if (valid) {
+            st4(pool + win * C + 4 * hl, m);
+            if (pool_argmax) *reinterpret_cast<uchar4*>(pool_argmax + win * C + 4 * hl) = am;
+        }
+        if (aux_w) {                                         // warp-uniform
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+                s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+                s[2] += __shfl_xor_sync(0xffffffffu, s[2], o);
+                s[3] += __shfl_xor_sync(0xffffffffu, s[3], o);
+            }
+            if (hl == 0 && valid) {
+                float best = s[0];                           // first maximum wins ties, like torch's max_pool2d
+                int besti = 0;
+                if (s[1] > best) { best = s[1]; besti = 1; }
+                if (s[2] > best) { best = s[2]; besti = 2; }
+                if (s[3] > best) { best = s[3]; besti = 3; }
+                best += b0;
+                aux_out[(long long)b * ld_aux + ho * Wo + wo] = aux_round ? round_tf32(best) : best;
+                if (aux_argmax) aux_argmax[win] = (unsigned char)besti;
+            }
+        }
     }
 }
 
@@ -1232,7 +1358,40 @@ int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const f
     PE_REQUIRE(C <= 256 && C % 4 == 0, "aux_bwd: C <= 256, C %% 4 == 0 required");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
     aux_bwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dout, lddo, argmax, a1, w, da1, accumulate, dw, db, B, H, W, C);
+        dout, lddo, argmax, a1, w, da1, accumulate, dw, db, B, H, W, C, nullptr, nullptr, 0);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_aux_bwd_params(const float* dout, int lddo, const unsigned char* argmax, const float* y, const float* scale,
+                      const float* shift, int round_tf32, float* dw, float* db, int B, int H, int W, int C,
+                      void* stream) {
+    PE_REQUIRE(C <= 256 && C % 4 == 0, "aux_bwd_params: C <= 256, C %% 4 == 0 required");
+    PE_REQUIRE(y && scale && shift && dw, "aux_bwd_params: y, scale, shift and dw are required");
+    const long long nwin = (long long)B * (H / 2) * (W / 2);
+    aux_bwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        dout, lddo, argmax, y, nullptr, nullptr, 0, dw, db, B, H, W, C, scale, shift, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_stem_post_train(const float* y, const double* stats, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, long long* num_batches_tracked, float* scale,
+                       float* shift, float* mean, float* invstd, float* pool, unsigned char* pool_argmax,
+                       const float* aux_w, const float* aux_bias, float* aux_out, int ld_aux,
+                       unsigned char* aux_argmax, int B, int H, int W, int C, float momentum, float eps,
+                       int round_tf32, int aux_round_tf32, void* stream) {
+    PE_REQUIRE(C == 64, "stem_post_train: the fused stem tail is written for 64 channels (got %d)", C);
+    PE_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem_post_train: H, W must be even");
+    PE_REQUIRE(stats && scale && shift && mean && invstd && pool, "stem_post_train: stats / scale / shift / mean / "
+               "invstd / pool required");
+    PE_REQUIRE(!aux_w || (aux_bias && aux_out), "stem_post_train: aux_w needs aux_bias and aux_out");
+    const long long nwin = (long long)B * (H / 2) * (W / 2);
+    if (nwin == 0) return 0;
+    stem_post_train_kernel<<<one_wave_grid(stem_post_train_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0,
+                             (cudaStream_t)stream>>>(
+        y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd, pool,
+        pool_argmax, aux_w, aux_bias, aux_out, ld_aux, aux_argmax, B, H, W, momentum, eps, round_tf32, aux_round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }

@@ -14,6 +14,9 @@ from . import native
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+# training forward: bn1 + ReLU + max pool + aux branch as one kernel (pe_stem_post_train); False = the three separate
+# kernels (kept for the kernel tests and as the reference the fused one is checked against)
+FUSED_STEM_TAIL = [True]
 
 
 def _dev_check(t):
@@ -283,7 +286,8 @@ class TrunkEngine:
                             P(self._bn_views(0)[4]), st)
             if tape is not None:
                 tape.append(("stem", col, y0))
-            a1 = self._bn_train(y0, 0, True, None, tape)
+            fused_tail = FUSED_STEM_TAIL[0] and Ho % 2 == 0 and Wo % 2 == 0
+            a1 = None if fused_tail else self._bn_train(y0, 0, True, None, tape)
         else:
             self.prepare_eval()
             sc, sh = self._bn_views(0)[:2]
@@ -294,16 +298,38 @@ class TrunkEngine:
         Hp, Wp = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
         x = Act(torch.empty(B * Hp * Wp, 64, device=dev, dtype=torch.float32), B, Hp, Wp, 64)
         argmax = torch.empty(B * Hp * Wp * 64, device=dev, dtype=torch.uint8) if tape is not None else None
-        L.pe_maxpool3x3s2_fwd(P(a1.t), P(x.t), P(argmax), B, Ho, Wo, 64, st)
-        if tape is not None:
-            tape.append(("maxpool", a1, x, argmax))
-        if self.aux_conv is not None:
-            aux_am = torch.empty(B * (Ho // 2) * (Wo // 2), device=dev, dtype=torch.uint8) if need_grad else None
-            # aux_round=False: the depth branch multiplies these features next and rounds the product itself
-            L.pe_aux_fwd(P(a1.t), P(self.aux_conv.weight), P(self.aux_conv.bias), P(aux_out), ld_aux, P(aux_am), B,
-                         Ho, Wo, 64, self.round_tf32 if aux_round else 0, st)
-            if head_tape is not None:
-                head_tape.append(("aux", a1, aux_am))
+        aux_am = None
+        if self.aux_conv is not None and need_grad:
+            aux_am = torch.empty(B * (Ho // 2) * (Wo // 2), device=dev, dtype=torch.uint8)
+        # aux_round=False: the depth branch multiplies these features next and rounds the product itself
+        aux_rt = self.round_tf32 if aux_round else 0
+        if a1 is None:
+            # training: bn1 + ReLU + max pool + aux branch in one pass over y0; the normalised activation is never
+            # written (`a1` is a geometry-only handle the gradient slots are keyed by)
+            _, bn = self.convs[0]
+            sc, sh, mean, invstd, stats, _ = self._bn_views(0)
+            ac = self.aux_conv
+            L.pe_stem_post_train(P(y0.t), P(stats), P(bn.weight), P(bn.bias), P(bn.running_mean), P(bn.running_var),
+                                 P(bn.num_batches_tracked), P(sc), P(sh), P(mean), P(invstd), P(x.t), P(argmax),
+                                 P(ac.weight) if ac is not None else None, P(ac.bias) if ac is not None else None,
+                                 P(aux_out) if ac is not None else None, ld_aux, P(aux_am), B, Ho, Wo, 64,
+                                 bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps, self.round_tf32,
+                                 aux_rt, st)
+            a1 = Act(None, B, Ho, Wo, 64)
+            if tape is not None:
+                tape.append(("bn", 0, y0, a1, True, None, None))
+                tape.append(("maxpool", a1, x, argmax))
+            if self.aux_conv is not None and head_tape is not None:
+                head_tape.append(("aux", a1, aux_am, y0))
+        else:
+            L.pe_maxpool3x3s2_fwd(P(a1.t), P(x.t), P(argmax), B, Ho, Wo, 64, st)
+            if tape is not None:
+                tape.append(("maxpool", a1, x, argmax))
+            if self.aux_conv is not None:
+                L.pe_aux_fwd(P(a1.t), P(self.aux_conv.weight), P(self.aux_conv.bias), P(aux_out), ld_aux, P(aux_am),
+                             B, Ho, Wo, 64, aux_rt, st)
+                if head_tape is not None:
+                    head_tape.append(("aux", a1, aux_am, None))
 
         # ---- bottleneck stages ------------------------------------------------------------------
         for blk, ids in self.blocks:
@@ -438,7 +464,7 @@ class TrunkEngine:
             elif kind == "maxpool":
                 _, a1, x, argmax = rec
                 d1, d2 = slots.pop_plain(x, 2)
-                da1 = torch.empty_like(a1.t)
+                da1 = torch.empty(a1.P, a1.C, device=dev, dtype=torch.float32)
                 # the aux branch reads the same activation: its gradient is scattered in the same pass
                 ad, ald, aam = pending_aux if pending_aux is not None else (None, 0, None)
                 L.pe_maxpool3x3s2_bwd(P(d1), P(d2), P(argmax), P(da1), 0, a1.B, a1.H, a1.W, a1.C, P(ad), ald, P(aam),
@@ -446,7 +472,7 @@ class TrunkEngine:
                 pending_aux = None
                 slots.add(a1, da1)
             elif kind == "aux":
-                _, a1, aux_am = rec
+                _, a1, aux_am, y0 = rec
                 # taped after "maxpool", hence visited first in the reversed walk
                 if self.aux_trainable:
                     gw, gb = grad_of(self.aux_conv.weight), grad_of(self.aux_conv.bias)
@@ -454,8 +480,13 @@ class TrunkEngine:
                     gb.zero_()
                     # the 1x1 conv's own gradients (reads a1 at the arg-max pixels only); the scatter into da1 is
                     # fused into the max-pool backward below
-                    L.pe_aux_bwd(P(d_aux), ld_daux, P(aux_am), P(a1.t), P(self.aux_conv.weight), None, 0, P(gw),
-                                 P(gb), a1.B, a1.H, a1.W, a1.C, st)
+                    if y0 is not None:      # fused stem tail: a1 = relu(bn1(y0)) is rebuilt at those pixels
+                        sc, sh = self._bn_views(0)[:2]
+                        L.pe_aux_bwd_params(P(d_aux), ld_daux, P(aux_am), P(y0.t), P(sc), P(sh), self.round_tf32,
+                                            P(gw), P(gb), a1.B, a1.H, a1.W, a1.C, st)
+                    else:
+                        L.pe_aux_bwd(P(d_aux), ld_daux, P(aux_am), P(a1.t), P(self.aux_conv.weight), None, 0, P(gw),
+                                     P(gb), a1.B, a1.H, a1.W, a1.C, st)
                 if frozen:
                     if on_ready is not None and self.aux_trainable:
                         on_ready([self.aux_conv.weight, self.aux_conv.bias])

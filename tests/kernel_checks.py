@@ -369,6 +369,71 @@ def check_pools(B):
     return out
 
 
+def check_stem_tail(B, rt):
+    """pe_stem_post_train (bn1 + ReLU + max pool + aux branch in one pass) against the three separate kernels (bit for
+    bit: same arithmetic) and against torch in float64; pe_aux_bwd_params against pe_aux_bwd on the materialised a1."""
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(500 + B)
+    H = W = 112
+    C = 64
+    y = torch.randn(B, H, W, C, device=DEV, generator=g) * 1.5 + 0.3
+    gamma = torch.rand(C, device=DEV, generator=g) + 0.5
+    beta = torch.randn(C, device=DEV, generator=g) * 0.3
+    w = torch.randn(1, C, 1, 1, device=DEV, generator=g) * 0.2
+    b = torch.randn(1, device=DEV, generator=g)
+    Pn = B * H * W
+    stats = torch.cat([y.double().sum((0, 1, 2)), (y.double() ** 2).sum((0, 1, 2))]).contiguous()
+    ldo = 3136 + 8
+
+    def buffers():
+        return dict(rm=torch.zeros(C, device=DEV), rv=torch.ones(C, device=DEV),
+                    nbt=torch.zeros(1, device=DEV, dtype=torch.int64), sc=torch.empty(C, device=DEV),
+                    sh=torch.empty(C, device=DEV), mean=torch.empty(C, device=DEV), invstd=torch.empty(C, device=DEV),
+                    pool=torch.empty(B, 56, 56, C, device=DEV), am=torch.empty(B, 56, 56, C, device=DEV, dtype=torch.uint8),
+                    aux=torch.zeros(B, ldo, device=DEV), aam=torch.empty(B * 56 * 56, device=DEV, dtype=torch.uint8))
+    f, u = buffers(), buffers()
+    L.pe_stem_post_train(P(y), P(stats), P(gamma), P(beta), P(f["rm"]), P(f["rv"]), P(f["nbt"]), P(f["sc"]), P(f["sh"]),
+                         P(f["mean"]), P(f["invstd"]), P(f["pool"]), P(f["am"]), P(w), P(b), P(f["aux"]), ldo, P(f["aam"]),
+                         B, H, W, C, 0.1, 1e-5, rt, rt, S())
+    a1 = torch.empty_like(y)
+    L.pe_bn_train_apply(P(y), P(stats), P(gamma), P(beta), P(u["rm"]), P(u["rv"]), P(u["nbt"]), P(u["sc"]), P(u["sh"]),
+                        P(u["mean"]), P(u["invstd"]), None, P(a1), None, Pn, C, 0.1, 1e-5, 1, rt, S())
+    L.pe_maxpool3x3s2_fwd(P(a1), P(u["pool"]), P(u["am"]), B, H, W, C, S())
+    L.pe_aux_fwd(P(a1), P(w), P(b), P(u["aux"]), ldo, P(u["aam"]), B, H, W, C, rt, S())
+    out = []
+    tag = "stem tail B%d rt%d " % (B, rt)
+    for k in ("rm", "rv", "sc", "sh", "mean", "invstd", "pool"):
+        out.append((tag + k + " == separate kernels", float((f[k] != u[k]).sum()), 0.0))
+    out.append((tag + "nbt", float(abs(int(f["nbt"]) - 1)), 0.0))
+    out.append((tag + "pool argmax == separate kernels", float((f["am"] != u["am"]).sum()), 0.0))
+    # (the compiler contracts the dot product differently in the two kernels: last-bit differences, which the TF32
+    # rounding of the result can turn into one TF32 ulp = 2^-10 of the value)
+    out.append((tag + "aux vs separate kernels", relerr(f["aux"], u["aux"]), 1e-3 if rt else 1e-6))
+    # the aux arg-max may only differ where two pixels of a window tie to rounding
+    d = f["aam"] != u["aam"]
+    out.append((tag + "aux argmax vs separate kernels", float(d.sum()), 2.0))
+    if not rt:
+        yd = y.double().permute(0, 3, 1, 2)
+        a1d = F.relu(F.batch_norm(yd, None, None, gamma.double(), beta.double(), True, 0.1, 1e-5))
+        out.append((tag + "pool vs torch", relerr(f["pool"], nhwc(F.max_pool2d(a1d, 3, 2, 1))), 1e-5))
+        out.append((tag + "aux vs torch", relerr(f["aux"][:, :3136], F.max_pool2d(F.conv2d(a1d, w.double(), b.double()), 2).flatten(1)), 1e-5))
+    # a no-aux launch leaves the pooled output unchanged
+    f2 = buffers()
+    L.pe_stem_post_train(P(y), P(stats), P(gamma), P(beta), None, None, None, P(f2["sc"]), P(f2["sh"]), P(f2["mean"]),
+                         P(f2["invstd"]), P(f2["pool"]), None, None, None, None, 0, None, B, H, W, C, 0.1, 1e-5, rt, rt,
+                         S())
+    out.append((tag + "pool without aux / argmax / running stats", float((f2["pool"] != f["pool"]).sum()), 0.0))
+    # aux conv gradients from y + scale / shift == from the materialised activation
+    do = torch.zeros(B, ldo, device=DEV)
+    do[:, :3136] = torch.randn(B, 3136, device=DEV, generator=g)
+    dw_a, db_a, dw_b, db_b = (torch.zeros(n, device=DEV) for n in (C, 1, C, 1))
+    L.pe_aux_bwd(P(do), ldo, P(u["aam"]), P(a1), P(w), None, 0, P(dw_a), P(db_a), B, H, W, C, S())
+    L.pe_aux_bwd_params(P(do), ldo, P(u["aam"]), P(y), P(u["sc"]), P(u["sh"]), rt, P(dw_b), P(db_b), B, H, W, C, S())
+    out.append((tag + "aux dw from y", relerr(dw_b, dw_a), 1e-5))
+    out.append((tag + "aux db from y", relerr(db_b, db_a), 1e-5))
+    return out
+
+
 def check_lstm_cell(N, H):
     L = native.lib()
     g = torch.Generator(device=DEV).manual_seed(N + H)
@@ -614,6 +679,8 @@ ALL = [
     lambda: check_bn(98, 2048),
     lambda: check_bn(3000, 128, relu=True, residual=False),
     lambda: check_pools(2),
+    lambda: check_stem_tail(2, 0),
+    lambda: check_stem_tail(3, 1),
     lambda: check_lstm_cell(5, 512),
     lambda: check_loss(37),
     lambda: check_adam(100003),

@@ -279,6 +279,37 @@ def test_streaming_estimator_graph_with_fused_head():
         assert mc.rel(a, b) <= 1e-5, mc.rel(a, b)
 
 
+def test_fused_stem_tail_matches_separate_kernels():
+    """The one-pass stem tail (bn1 + ReLU + max pool + aux branch, pe_stem_post_train; bn1's output never written)
+    gives the same loss, gradients and BN buffers as bn_train_apply + maxpool + aux as three kernels.  Tolerance
+    1e-4: the split-K wgrad accumulates with unordered fp32 atomics, everything else is the same arithmetic."""
+    from models.losses import PoseDistanceLoss
+    from pe_b200 import engine
+    mc.SHALLOW[0] = True
+    img, x0, tgt = po.synthetic_batch("no", 4, seed=11)
+    img, x0, tgt = img.cuda(), x0.cuda(), tgt.cuda()
+    crit = PoseDistanceLoss(distance_metric="l2", alpha=0.5, mode="pose")
+    res = {}
+    for fused in (False, True):
+        engine.FUSED_STEM_TAIL[0] = fused
+        try:
+            model = mc.build_model("no").cuda().train()
+            with torch.no_grad():      # keep the ReLU'd output alive so the loss is finite (quirk Q2)
+                getattr(model, "fc%d" % (model.n_fc - 1)).module.bias.fill_(0.5)
+            loss = crit(model(img, None, x0), tgt)
+            loss.backward()
+            res[fused] = (float(loss), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None},
+                          {n: b.clone() for n, b in model.named_buffers()})
+        finally:
+            engine.FUSED_STEM_TAIL[0] = True
+    assert abs(res[True][0] - res[False][0]) <= 1e-5 * abs(res[False][0])
+    assert res[True][1].keys() == res[False][1].keys()
+    for n, g in res[False][1].items():
+        assert mc.relnorm(res[True][1][n], g) <= 1e-4, (n, mc.relnorm(res[True][1][n], g))
+    for n, b in res[False][2].items():
+        assert mc.relnorm(res[True][2][n].float(), b.float()) <= 1e-6, n
+
+
 def test_frozen_trunk_feature_extraction():
     """feature_extract semantics (util/model_utils.py:110-113): with every trunk parameter frozen except the
     replaced fc, the backward pass skips the convolutions; the head / fc / aux-conv gradients are the same as in
