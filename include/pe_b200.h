@@ -44,9 +44,10 @@ void pe_debug_residual_tma(int on);
 void pe_debug_epilogue_groups(int groups);
 /* debug: haloed-tile path for 3x3 stride-1 forward / dgrad with <= 128 input channels (0 = per-tap boxes) */
 void pe_debug_conv_halo(int on);
-/* debug: 0 = launch the tap-GEMM without the programmatic-dependent-launch attribute (on by default: its prologue
- * overlaps the tail of the previous kernel in the stream; it waits for that kernel before touching global memory) */
-void pe_debug_pdl(int on);
+/* debug: programmatic dependent launch mask -- bit 0: the tap-GEMM launches carry the attribute (default: its
+ * prologue overlaps the tail of the previous kernel; it waits for that kernel before touching global memory),
+ * bit 1: the streaming / elementwise kernels too.  Same as the environment variable PE_B200_PDL.              */
+void pe_debug_pdl(int mask);
 
 /* ---- convolutions: torchvision resnet.py:143-163,266-282 Conv2d calls reached from
  *      models/naive.py:316 and models/time_sensitive.py:185,472 (bias-free, NHWC here) ------------

@@ -41,11 +41,40 @@ const char* get_error();
     } while (0)
 
 int num_sms();
+// programmatic dependent launch: bit 0 = tap-GEMM launches, bit 1 = streaming / elementwise launches carry the
+// attribute (PE_B200_PDL=<mask> or pe_debug_pdl(mask); default in pe_tapgemm.cu)
+bool pdl_enabled(int kind = 1);
 
 #ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute: the grid may be scheduled while the previous kernel
+// of the stream is still draining, so launch latency and ramp-up hide behind that kernel's tail.  Every kernel
+// launched this way calls pdl_sync() before it touches global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled(2) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
+// First statement of a kernel launched with launch_pdl: let the next kernel of the stream be scheduled, then wait
+// until the previous grid has completed and its writes are visible (a no-op without the launch attribute).
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -73,6 +73,7 @@ channel_reduce_kernel(const float* __restrict__ a, const float* __restrict__ a2,
                       const float* __restrict__ invstd, const float* __restrict__ msc,
                       const float* __restrict__ msh, const unsigned* __restrict__ maskbits,
                       double* __restrict__ sums, long long P, int C, int relu) {
+    pdl_sync();
     __shared__ float sm0[EW_THREADS * 4];
     __shared__ float sm1[EW_THREADS * 4];
     constexpr int U = 4;
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                 const float* __restrict__ residual, float* __restrict__ out, long long n4, int G, int relu,
                 int round_out) {
+    pdl_sync();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const int g = (int)(i % G);
@@ -253,6 +255,7 @@ bn_train_apply_kernel(const float* __restrict__ y, const double* __restrict__ st
                       float* __restrict__ shift_out, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                       const float* __restrict__ residual, float* __restrict__ out, unsigned* __restrict__ maskbits,
                       long long P, int C, float momentum, float eps, int relu, int round_out) {
+    pdl_sync();
     extern __shared__ float coef[];  // [2][C]
     float* csc = coef;
     float* csh = coef + C;
@@ -344,6 +347,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ do
                     float* __restrict__ dy, float* __restrict__ dres,
                     int dres_acc, float* __restrict__ dgamma, float* __restrict__ dbeta, int param_acc,
                     long long P, int C, int relu, int round_out) {
+    pdl_sync();
     extern __shared__ float coef[];  // [3][C]
     float* ca = coef;
     float* cb = coef + C;
@@ -434,6 +438,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
 constexpr int PACK_PER_BLOCK = 2048;
 __global__ void __launch_bounds__(EW_THREADS)
 pack_weights_batched_kernel(const long long* __restrict__ table, int n_layers, int round_out) {
+    pdl_sync();
     __shared__ int s_layer;
     if (threadIdx.x == 0) {
         int lo = 0, hi = n_layers - 1;                     // last layer whose first block <= blockIdx.x
@@ -467,6 +472,7 @@ pack_weights_batched_kernel(const long long* __restrict__ table, int n_layers, i
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ tck, float* __restrict__ w, int Cout, int Cin, int RS,
                                     int accumulate) {
+    pdl_sync();
     const long long n = (long long)Cout * Cin * RS;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -486,6 +492,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ tck, float* __rest
 __global__ void __launch_bounds__(EW_THREADS)
 im2col_stem_kernel(const float* __restrict__ img, float* __restrict__ col, int B, int C, int H, int W, int R, int S,
                    int stride, int pad, int Ho, int Wo, int ldc, int round_out) {
+    pdl_sync();
     extern __shared__ float rows_sm[];                // [C*R][SW]
     const int SW = W + 2 * pad;
     const int K = C * R * S;
@@ -522,6 +529,7 @@ im2col_stem_kernel(const float* __restrict__ img, float* __restrict__ col, int B
 
 __global__ void transpose_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows,
                                  int cols, int round_out) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -541,6 +549,7 @@ __global__ void transpose_kernel(const float* __restrict__ src, int lds, float* 
 
 __global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
                                  long long rows, int cols, int round_out) {
+    pdl_sync();
     const long long n = rows * cols;
     const long long gs = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
@@ -555,6 +564,7 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* 
 __global__ void axpby_cols_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
                                   float* __restrict__ out, int ldo, long long rows, int cols, float alpha,
                                   float beta, int round_out) {
+    pdl_sync();
     const long long n = rows * cols;
     const long long gs = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
@@ -568,6 +578,7 @@ __global__ void axpby_cols_kernel(const float* __restrict__ a, int lda, const fl
 
 __global__ void colsum_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int rows, int cols,
                               int accumulate) {
+    pdl_sync();
     // one warp per column chunk of 32; blockDim = (32, 8): 8 row lanes
     __shared__ float sm[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
@@ -584,6 +595,7 @@ __global__ void colsum_kernel(const float* __restrict__ x, int ldx, float* __res
 
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
                                 float* __restrict__ dz, int lddz, long long rows, int cols) {
+    pdl_sync();
     const long long n = rows * cols;
     const long long gs = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
@@ -609,6 +621,7 @@ __global__ void add_i64_kernel(long long* __restrict__ p, long long n, long long
 __global__ void __launch_bounds__(EW_THREADS)
 maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ argmax, int B,
                    int H, int W, int C, int Ho, int Wo) {
+    pdl_sync();
     const int G = C >> 2;
     const long long n = (long long)B * Ho * Wo * G;
     const long long gs = (long long)gridDim.x * blockDim.x;
@@ -652,6 +665,7 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
                    const unsigned char* __restrict__ argmax, float* __restrict__ dx, int accumulate, int B, int H,
                    int W, int C, int Ho, int Wo, const float* __restrict__ aux_dout, int aux_lddo,
                    const unsigned char* __restrict__ aux_argmax, const float* __restrict__ aux_w) {
+    pdl_sync();
     const int G = C >> 2;
     const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;          // 2x2 blocks
     const long long n = (long long)B * Hb * Wb * G;
@@ -726,6 +740,7 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
 
 __global__ void __launch_bounds__(EW_THREADS)
 avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int ldy, int B, int HW, int C, int round_out) {
+    pdl_sync();
     const int G = C >> 2;
     const long long n = (long long)B * G;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -746,6 +761,7 @@ avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int ldy, 
 
 __global__ void __launch_bounds__(EW_THREADS)
 avgpool_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int B, int HW, int C) {
+    pdl_sync();
     const int G = C >> 2;
     const long long n = (long long)B * HW * G;
     const long long gs = (long long)gridDim.x * blockDim.x;
@@ -769,6 +785,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 aux_fwd_kernel(const float* __restrict__ a1, const float* __restrict__ w, const float* __restrict__ bias,
                float* __restrict__ out, int ldo, unsigned char* __restrict__ argmax, int B, int H, int W, int C,
                int round_out) {
+    pdl_sync();
     const int Ho = H >> 1, Wo = W >> 1;
     const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
     const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -822,6 +839,7 @@ aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __
                const float* __restrict__ a1, const float* __restrict__ w, float* __restrict__ da1, int accumulate,
                float* __restrict__ dw, float* __restrict__ db, int B, int H, int W, int C,
                const float* __restrict__ pre_scale, const float* __restrict__ pre_shift, int pre_round) {
+    pdl_sync();
     __shared__ float s_dw[256];
     __shared__ float s_db;
     const int Ho = H >> 1, Wo = W >> 1;
@@ -905,6 +923,7 @@ stem_post_train_kernel(const float* __restrict__ y, const double* __restrict__ s
                        const float* __restrict__ aux_w, const float* __restrict__ aux_bias,
                        float* __restrict__ aux_out, int ld_aux, unsigned char* __restrict__ aux_argmax, int B, int H,
                        int W, float momentum, float eps, int round_out, int aux_round) {
+    pdl_sync();
     constexpr int C = 64;
     __shared__ __align__(16) float csc[C];
     __shared__ __align__(16) float csh[C];
@@ -1118,8 +1137,8 @@ extern "C" {
 int pe_bn_stats(const float* y, long long P, int C, double* stats, void* stream) {
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_stats: unsupported channel count %d", C);
-    channel_reduce_kernel<0><<<reduce_grid(channel_reduce_kernel<0>, P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
+    PE_CHECK_CUDA(launch_pdl(channel_reduce_kernel<0>, reduce_grid(channel_reduce_kernel<0>, P, C), EW_THREADS, 0, (cudaStream_t)stream,
+        y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1138,8 +1157,8 @@ int pe_bn_apply(const float* y, const float* scale, const float* shift, const fl
                 long long P, int C, int relu, int round_tf32, void* stream) {
     PE_REQUIRE(C % 4 == 0, "bn_apply: C %% 4 != 0");
     const long long n4 = P * (C / 4);
-    bn_apply_kernel<<<one_wave_grid(bn_apply_kernel, 0, n4, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        y, scale, shift, residual, out, n4, C / 4, relu, round_tf32);
+    PE_CHECK_CUDA(launch_pdl(bn_apply_kernel, one_wave_grid(bn_apply_kernel, 0, n4, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream,
+        y, scale, shift, residual, out, n4, C / 4, relu, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1154,10 +1173,9 @@ int pe_bn_train_apply(const float* y, const double* stats, const float* gamma, c
     PE_REQUIRE(!maskbits || (reinterpret_cast<uintptr_t>(maskbits) & 15) == 0,
                "bn_train_apply: mask bits need a 16-byte aligned pointer");
     const long long n4 = P * (C / 4);
-    bn_train_apply_kernel<<<one_wave_grid(bn_train_apply_kernel, 2 * C * sizeof(float), n4, EW_THREADS * 4), EW_THREADS,
-                            2 * C * sizeof(float), (cudaStream_t)stream>>>(
+    PE_CHECK_CUDA(launch_pdl(bn_train_apply_kernel, one_wave_grid(bn_train_apply_kernel, 2 * C * sizeof(float), n4, EW_THREADS * 4), EW_THREADS, 2 * C * sizeof(float), (cudaStream_t)stream,
         y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd, residual,
-        out, maskbits, P, C, momentum, eps, relu, round_tf32);
+        out, maskbits, P, C, momentum, eps, relu, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1170,8 +1188,8 @@ int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, co
     PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_reduce: ReLU mask needs `out` or scale/shift");
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_bwd_reduce: unsupported channel count %d", C);
-    channel_reduce_kernel<1><<<reduce_grid(channel_reduce_kernel<1>, P, C), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dout, dout2, out, y, mean, invstd, mask_scale, mask_shift, maskbits, sums, P, C, relu);
+    PE_CHECK_CUDA(launch_pdl(channel_reduce_kernel<1>, reduce_grid(channel_reduce_kernel<1>, P, C), EW_THREADS, 0, (cudaStream_t)stream,
+        dout, dout2, out, y, mean, invstd, mask_scale, mask_shift, maskbits, sums, P, C, relu));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1186,12 +1204,11 @@ int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, con
     PE_REQUIRE(C % 4 == 0 && C <= 4096, "bn_bwd_apply: unsupported channel count %d", C);
     PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_apply: ReLU mask needs `out` or scale/shift");
     const long long n4 = P * (C / 4);
-    bn_bwd_apply_kernel<<<one_wave_grid(bn_bwd_apply_kernel, 3 * C * sizeof(float), n4, EW_THREADS * 4), EW_THREADS,
-                          3 * C * sizeof(float), (cudaStream_t)stream>>>(
+    PE_CHECK_CUDA(launch_pdl(bn_bwd_apply_kernel, one_wave_grid(bn_bwd_apply_kernel, 3 * C * sizeof(float), n4, EW_THREADS * 4), EW_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream,
         dout, dout2, out, y, mean, invstd, gamma, mask_scale, mask_shift, maskbits, sums, dy, dres, dres_accumulate,
         dgamma,
         dbeta, param_accumulate,
-        P, C, relu, round_tf32);
+        P, C, relu, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1208,7 +1225,7 @@ int pe_pack_conv_weight(const float* w_oihw, float* w_tck, float* w_tkc, int Cou
 int pe_pack_conv_weights_batched(const long long* table_dev, int n_layers, int total_blocks, int round_tf32,
                                  void* stream) {
     if (n_layers <= 0 || total_blocks <= 0) return 0;
-    pack_weights_batched_kernel<<<total_blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(table_dev, n_layers, round_tf32);
+    PE_CHECK_CUDA(launch_pdl(pack_weights_batched_kernel, total_blocks, EW_THREADS, 0, (cudaStream_t)stream, table_dev, n_layers, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1218,8 +1235,8 @@ int pe_pack_block_elems(void) { return PACK_PER_BLOCK; }
 int pe_unpack_conv_wgrad(const float* dw_tck, float* dw_oihw, int Cout, int Cin, int R, int S, int accumulate,
                          void* stream) {
     const long long n = (long long)Cout * Cin * R * S;
-    unpack_wgrad_kernel<<<grid_for(n, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dw_tck, dw_oihw, Cout, Cin, R * S, accumulate);
+    PE_CHECK_CUDA(launch_pdl(unpack_wgrad_kernel, grid_for(n, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream,
+        dw_tck, dw_oihw, Cout, Cin, R * S, accumulate));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1238,15 +1255,15 @@ int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W
         configured = smem;
     }
     dim3 block(bx, EW_THREADS / bx);
-    im2col_stem_kernel<<<B * Ho, block, smem, (cudaStream_t)stream>>>(img_nchw, col, B, C, H, W, R, S, stride, pad, Ho,
-                                                                     Wo, ldc, round_tf32);
+    PE_CHECK_CUDA(launch_pdl(im2col_stem_kernel, B * Ho, block, smem, (cudaStream_t)stream, img_nchw, col, B, C, H, W, R, S, stride, pad, Ho,
+                                                                     Wo, ldc, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
 
 int pe_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream) {
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols, round_tf32);
+    PE_CHECK_CUDA(launch_pdl(transpose_kernel, grid, block, 0, (cudaStream_t)stream, src, lds, dst, ldd, rows, cols, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1254,8 +1271,8 @@ int pe_transpose(const float* src, int lds, float* dst, int ldd, int rows, int c
 int pe_copy_cols(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream) {
     const long long n = (long long)rows * cols;
     if (n == 0) return 0;
-    copy_cols_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows,
-                                                                                       cols, round_tf32);
+    PE_CHECK_CUDA(launch_pdl(copy_cols_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, src, lds, dst, ldd, rows,
+                                                                                       cols, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1264,16 +1281,16 @@ int pe_axpby_cols(const float* a, int lda, const float* b, int ldb, float* out, 
                   float alpha, float beta, int round_tf32, void* stream) {
     const long long n = (long long)rows * cols;
     if (n == 0) return 0;
-    axpby_cols_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, out, ldo,
+    PE_CHECK_CUDA(launch_pdl(axpby_cols_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, a, lda, b, ldb, out, ldo,
                                                                                         rows, cols, alpha, beta,
-                                                                                        round_tf32);
+                                                                                        round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
 
 int pe_colsum(const float* x, int ldx, float* out, int rows, int cols, int accumulate, void* stream) {
     dim3 grid((cols + 31) / 32), block(32, 8);
-    colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, out, rows, cols, accumulate);
+    PE_CHECK_CUDA(launch_pdl(colsum_kernel, grid, block, 0, (cudaStream_t)stream, x, ldx, out, rows, cols, accumulate));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1282,8 +1299,8 @@ int pe_relu_bwd(const float* dy, int lddy, const float* y, int ldy, float* dz, i
                 void* stream) {
     const long long n = (long long)rows * cols;
     if (n == 0) return 0;
-    relu_bwd_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, dz, lddz,
-                                                                                      rows, cols);
+    PE_CHECK_CUDA(launch_pdl(relu_bwd_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, dy, lddy, y, ldy, dz, lddz,
+                                                                                      rows, cols));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1306,8 +1323,8 @@ int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, 
     PE_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * Ho * Wo * (C / 4);
-    maxpool_fwd_kernel<<<one_wave_grid(maxpool_fwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(x, y, argmax, B, H, W,
-                                                                                             C, Ho, Wo);
+    PE_CHECK_CUDA(launch_pdl(maxpool_fwd_kernel, one_wave_grid(maxpool_fwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, x, y, argmax, B, H, W,
+                                                                                             C, Ho, Wo));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1320,8 +1337,8 @@ int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* 
                "maxpool_bwd: the aux term needs its arg-max map, weights and even H, W");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
-    maxpool_bwd_kernel<<<one_wave_grid(maxpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dy, dy2, argmax, dx, accumulate, B, H, W, C, Ho, Wo, aux_dout, aux_lddo, aux_argmax, aux_w);
+    PE_CHECK_CUDA(launch_pdl(maxpool_bwd_kernel, one_wave_grid(maxpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream,
+        dy, dy2, argmax, dx, accumulate, B, H, W, C, Ho, Wo, aux_dout, aux_lddo, aux_argmax, aux_w));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1329,8 +1346,8 @@ int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* 
 int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int round_tf32, void* stream) {
     PE_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "avgpool: C, ldy must be multiples of 4");
     const long long n = (long long)B * (C / 4);
-    avgpool_fwd_kernel<<<(unsigned)((n + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        x, y, ldy, B, HW, C, round_tf32);
+    PE_CHECK_CUDA(launch_pdl(avgpool_fwd_kernel, (unsigned)((n + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream,
+        x, y, ldy, B, HW, C, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1338,7 +1355,7 @@ int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int 
 int pe_avgpool_bwd(const float* dy, int lddy, float* dx, int B, int HW, int C, void* stream) {
     PE_REQUIRE(C % 4 == 0 && lddy % 4 == 0, "avgpool: C, lddy must be multiples of 4");
     const long long n = (long long)B * HW * (C / 4);
-    avgpool_bwd_kernel<<<one_wave_grid(avgpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, B, HW, C);
+    PE_CHECK_CUDA(launch_pdl(avgpool_bwd_kernel, one_wave_grid(avgpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, dy, lddy, dx, B, HW, C));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1347,8 +1364,8 @@ int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, i
                int H, int W, int C, int round_tf32, void* stream) {
     PE_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "aux: H, W must be even and C a multiple of 4");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    aux_fwd_kernel<<<one_wave_grid(aux_fwd_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        a1, w, bias, out, ldo, argmax, B, H, W, C, round_tf32);
+    PE_CHECK_CUDA(launch_pdl(aux_fwd_kernel, one_wave_grid(aux_fwd_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0, (cudaStream_t)stream,
+        a1, w, bias, out, ldo, argmax, B, H, W, C, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1357,8 +1374,8 @@ int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const f
                int accumulate, float* dw, float* db, int B, int H, int W, int C, void* stream) {
     PE_REQUIRE(C <= 256 && C % 4 == 0, "aux_bwd: C <= 256, C %% 4 == 0 required");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    aux_bwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dout, lddo, argmax, a1, w, da1, accumulate, dw, db, B, H, W, C, nullptr, nullptr, 0);
+    PE_CHECK_CUDA(launch_pdl(aux_bwd_kernel, grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream,
+        dout, lddo, argmax, a1, w, da1, accumulate, dw, db, B, H, W, C, nullptr, nullptr, 0));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1369,8 +1386,8 @@ int pe_aux_bwd_params(const float* dout, int lddo, const unsigned char* argmax, 
     PE_REQUIRE(C <= 256 && C % 4 == 0, "aux_bwd_params: C <= 256, C %% 4 == 0 required");
     PE_REQUIRE(y && scale && shift && dw, "aux_bwd_params: y, scale, shift and dw are required");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    aux_bwd_kernel<<<grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        dout, lddo, argmax, y, nullptr, nullptr, 0, dw, db, B, H, W, C, scale, shift, round_tf32);
+    PE_CHECK_CUDA(launch_pdl(aux_bwd_kernel, grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream,
+        dout, lddo, argmax, y, nullptr, nullptr, 0, dw, db, B, H, W, C, scale, shift, round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1388,10 +1405,9 @@ int pe_stem_post_train(const float* y, const double* stats, const float* gamma, 
     PE_REQUIRE(!aux_w || (aux_bias && aux_out), "stem_post_train: aux_w needs aux_bias and aux_out");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
     if (nwin == 0) return 0;
-    stem_post_train_kernel<<<one_wave_grid(stem_post_train_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0,
-                             (cudaStream_t)stream>>>(
+    PE_CHECK_CUDA(launch_pdl(stem_post_train_kernel, one_wave_grid(stem_post_train_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0, (cudaStream_t)stream,
         y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd, pool,
-        pool_argmax, aux_w, aux_bias, aux_out, ld_aux, aux_argmax, B, H, W, momentum, eps, round_tf32, aux_round_tf32);
+        pool_argmax, aux_w, aux_bias, aux_out, ld_aux, aux_argmax, B, H, W, momentum, eps, round_tf32, aux_round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }

@@ -742,7 +742,7 @@ void pe_debug_residual_tma(int on) { g_dbg_res_tma = on; }
 
 void pe_debug_epilogue_groups(int groups) { g_dbg_epi_groups = groups; }
 
-void pe_debug_pdl(int on) { pe::g_pdl = on ? 1 : 0; }
+void pe_debug_pdl(int mask) { pe::g_pdl = mask & 3; }
 
 void pe_debug_conv_halo(int on) {
     g_dbg_conv_halo = on & 1;

@@ -16,6 +16,7 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gx, int ldgx, con
                                      const float* __restrict__ c_prev, float* __restrict__ c_out,
                                      float* __restrict__ h_out, int ldh, float* __restrict__ act, int N, int Hd,
                                      int round_out) {
+    pdl_sync();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * Hd) return;
     const int j = idx % Hd, n = idx / Hd;
@@ -47,6 +48,7 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh, int lddh, con
                                      const float* __restrict__ c_prev, const float* __restrict__ c_out,
                                      float* __restrict__ dgates, int lddg, float* __restrict__ dc_prev, int N,
                                      int Hd) {
+    pdl_sync();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * Hd) return;
     const int j = idx % Hd, n = idx / Hd;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(256)
 pose_loss_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ truth, int ldt, long long n,
                  int metric, int mode, float alpha, float epsilon, float scale, float* __restrict__ loss,
                  float* __restrict__ dpred, int lddp, float* __restrict__ val) {
+    pdl_sync();
     __shared__ float red[3][8];
     float acc_loss = 0.f, acc_pos = 0.f, acc_ang = 0.f;
     for (long long r = threadIdx.x; r < n; r += blockDim.x) {
@@ -185,6 +188,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long n, float lr_c, float b1, float b2, float eps, float wd, float inv_bc2_sqrt, float gs) {
+    pdl_sync();
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -208,6 +212,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, long long n, float lr,
            float momentum, float wd, int first, float gs) {
+    pdl_sync();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float gi = g[i] * gs;
@@ -233,9 +238,9 @@ int pe_lstm_cell_fwd(const float* gx, int ldgx, const float* gh, int ldgh, const
                      int round_tf32, void* stream) {
     const int n = N * Hd;
     if (n == 0) return 0;
-    lstm_cell_fwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gx, ldgx, gh, ldgh, b_ih, b_hh, c_prev,
+    PE_CHECK_CUDA(launch_pdl(lstm_cell_fwd_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, gx, ldgx, gh, ldgh, b_ih, b_hh, c_prev,
                                                                             c_out, h_out, ldh, act, N, Hd,
-                                                                            round_tf32);
+                                                                            round_tf32));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -245,8 +250,8 @@ int pe_lstm_cell_bwd(const float* dh, int lddh, const float* dh_rec, const float
                      void* stream) {
     const int n = N * Hd;
     if (n == 0) return 0;
-    lstm_cell_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dh, lddh, dh_rec, dc_next, act, c_prev,
-                                                                            c_out, dgates, lddg, dc_prev, N, Hd);
+    PE_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, dh, lddh, dh_rec, dc_next, act, c_prev,
+                                                                            c_out, dgates, lddg, dc_prev, N, Hd));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -256,8 +261,8 @@ int pe_pose_loss(const float* pred, int ldp, const float* truth, int ldt, long l
                  void* stream) {
     PE_REQUIRE(metric >= 0 && metric <= 3, "pose_loss: metric %d invalid", metric);
     PE_REQUIRE(mode == 0 || mode == 1, "pose_loss: mode %d invalid", mode);
-    pose_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, ldp, truth, ldt, n, metric, mode, alpha, epsilon,
-                                                          scale, loss, dpred, lddp, val);
+    PE_CHECK_CUDA(launch_pdl(pose_loss_kernel, 1, 256, 0, (cudaStream_t)stream, pred, ldp, truth, ldt, n, metric, mode, alpha, epsilon,
+                                                          scale, loss, dpred, lddp, val));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -275,8 +280,8 @@ int pe_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_c, beta1, beta2, eps,
-                                                                    weight_decay, inv_bc2_sqrt, grad_scale);
+    PE_CHECK_CUDA(launch_pdl(adam_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr_c, beta1, beta2, eps,
+                                                                    weight_decay, inv_bc2_sqrt, grad_scale));
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -287,8 +292,8 @@ int pe_sgd_step(float* p, const float* g, float* mom, long long n, float lr, flo
     long long blocks = (n + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    sgd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, mom, n, lr, momentum, weight_decay,
-                                                                   first_step, grad_scale);
+    PE_CHECK_CUDA(launch_pdl(sgd_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, p, g, mom, n, lr, momentum, weight_decay,
+                                                                   first_step, grad_scale));
     PE_LAUNCH_CHECK();
     return 0;
 }

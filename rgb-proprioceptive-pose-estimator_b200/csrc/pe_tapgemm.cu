@@ -830,7 +830,15 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 
 }  // namespace
 
-int g_pdl = 1;      // programmatic dependent launch of the tap-GEMM (pe_debug_pdl)
+int g_pdl = -1;     // programmatic dependent launch (pe_debug_pdl); -1 = not read from the environment yet
+
+bool pdl_enabled(int kind) {
+    if (g_pdl < 0) {
+        const char* e = getenv("PE_B200_PDL");
+        g_pdl = e ? (atoi(e) & 3) : 1;
+    }
+    return (g_pdl & kind) != 0;
+}
 
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream) {
     static bool configured = false;
@@ -839,7 +847,6 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
                                            TG_SMEM_BYTES));
         PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TG_SMEM_BYTES));
-        if (const char* e = getenv("PE_B200_PDL")) g_pdl = atoi(e) != 0;
         configured = true;
     }
     if (p.epi_groups != 4) p.epi_groups = 2;
@@ -866,7 +873,7 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl ? 1 : 0;
+    cfg.numAttrs = pdl_enabled(1) ? 1 : 0;
     if (p.epi_groups == 4)
         PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<4>, maps, p));
     else

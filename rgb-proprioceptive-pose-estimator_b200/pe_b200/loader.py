@@ -22,18 +22,27 @@ class DevicePrefetcher:
         self.k = 0
         self._next = self._issue()
 
+    def _ensure(self, obj, slot, path):
+        """Device buffers of a slot, allocated on the CONSUMER's stream: they come from (and return to) the caching
+        allocator's main pool, so a new prefetcher reuses the previous one's memory instead of paying a cudaMalloc
+        per side stream."""
+        if isinstance(obj, (tuple, list)):
+            for i, o in enumerate(obj):
+                self._ensure(o, slot, path + (i,))
+        elif torch.is_tensor(obj):
+            bufs = self.slots[slot]
+            buf = bufs.get(path)
+            if buf is None or buf.shape != obj.shape or buf.dtype != obj.dtype:
+                bufs[path] = torch.empty(obj.shape, dtype=obj.dtype, device=self.dev)
+
     def _copy(self, obj, slot, path):
         if isinstance(obj, (tuple, list)):
             return type(obj)(self._copy(o, slot, path + (i,)) for i, o in enumerate(obj))
         if not torch.is_tensor(obj):
             return obj
-        bufs = self.slots[slot]
-        key = path
-        buf = bufs.get(key)
-        if buf is None or buf.shape != obj.shape or buf.dtype != obj.dtype:
-            buf = torch.empty(obj.shape, dtype=obj.dtype, device=self.dev)
-            bufs[key] = buf
+        buf = self.slots[slot][path]
         buf.copy_(obj, non_blocking=True)
+        buf.record_stream(self.stream)      # not handed back to the allocator while the copy may still be running
         return buf
 
     def _issue(self):
@@ -46,6 +55,7 @@ class DevicePrefetcher:
         if self.slots[slot] is None:
             self.slots[slot] = {}
         cur = torch.cuda.current_stream(self.dev)
+        self._ensure(batch, slot, ())
         with torch.cuda.stream(self.stream):
             # the buffers of this slot may still be read by the step that used them two batches ago
             self.stream.wait_stream(cur)
