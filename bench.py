@@ -345,7 +345,7 @@ def run_ours(args):
     # times divided into ncu-measured bytes give the achieved HBM rate of the streaming kernels
     prof = {}
     try:
-        pj = json.load(open(os.path.join(ROOT, "profiles", "launches_r01c_train_step_no_b256_summary.json")))
+        pj = json.load(open(os.path.join(ROOT, "profiles", "launches_r01d_train_step_no_b256_summary.json")))
         prof = {k["kernel"]: k for k in pj["kernels"]}
         # tapgemm_kernel<2> / <4> (two / four epilogue groups) are one kernel family
         tg = [k for k in pj["kernels"] if k["kernel"].startswith("tapgemm_kernel")]
@@ -385,7 +385,7 @@ def run_ours(args):
                      "achieved": ach_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                      "frac": ach_tflops / tf32_peak if tf32_peak else None, "traffic": gemm_traffic,
                      "traffic_note": "ncu dram bytes read+written, average per tapgemm launch over one step "
-                                     "(profiles/launches_r01c_train_step_no_b256_summary.json)",
+                                     "(profiles/launches_r01d_train_step_no_b256_summary.json)",
                      "algorithmic_flop_per_step": TRAIN_GFLOP_PER_FRAME[kind] * frames * 1e9,
                      "launches_per_step": gemm_launches,
                      "peak_source": "%s bf16 sustained / 2 (TF32 runs at half the bf16 rate)" % pk["which"],
