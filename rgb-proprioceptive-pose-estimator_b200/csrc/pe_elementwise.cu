@@ -926,7 +926,7 @@ aux_bwd_kernel(const float* __restrict__ dout, int lddo, const unsigned char* __
 // the two arg-max maps, y and scale / shift only (bn_train_apply + maxpool_fwd + aux_fwd would write it once and
 // read it twice: 2.5 GB per 256-frame step).  A half-warp owns one pooled pixel (16 lanes x 4 channels); the
 // arithmetic is that of the three separate kernels, expression for expression.
-__global__ void __launch_bounds__(EW_THREADS)
+__global__ void __launch_bounds__(EW_THREADS, 4)
 stem_post_train_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -982,37 +982,36 @@ stem_post_train_kernel(const float* __restrict__ y, const double* __restrict__ s
         const int wo = (int)(wv % Wo);
         const int ho = (int)((wv / Wo) % Ho);
         const int b = (int)(wv / ((long long)Wo * Ho));
-        float4 v[9];
-        bool in[9];
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int h = 2 * ho - 1 + kh;
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int w = 2 * wo - 1 + kw;
-                in[kh * 3 + kw] = h >= 0 && w >= 0;          // h < H, w < W always hold for even H, W
-                if (in[kh * 3 + kw]) v[kh * 3 + kw] = ld4(y + (((long long)b * H + h) * W + w) * C + 4 * hl);
-            }
-        }
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         uchar4 am = make_uchar4(255, 255, 255, 255);
         float s[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool win_w0 = wo > 0;                           // column 2wo-1 exists (h < H, w < W always hold)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (!in[k]) continue;
-            float4 o;
-            o.x = fmaxf(fmaf(v[k].x, sc.x, sh.x), 0.f);
-            o.y = fmaxf(fmaf(v[k].y, sc.y, sh.y), 0.f);
-            o.z = fmaxf(fmaf(v[k].z, sc.z, sh.z), 0.f);
-            o.w = fmaxf(fmaf(v[k].w, sc.w, sh.w), 0.f);
-            if (round_out) o = round4(o);
-            const unsigned char kk = (unsigned char)k;
-            if (o.x > m.x || am.x == 255) { m.x = o.x; am.x = kk; }
-            if (o.y > m.y || am.y == 255) { m.y = o.y; am.y = kk; }
-            if (o.z > m.z || am.z == 255) { m.z = o.z; am.z = kk; }
-            if (o.w > m.w || am.w == 255) { m.w = o.w; am.w = kk; }
-            if (k == 4 || k == 5 || k == 7 || k == 8)        // the aux window: rows 2ho, 2ho+1 x cols 2wo, 2wo+1
-                s[(k / 3 - 1) * 2 + (k % 3 - 1)] += o.x * w4.x + o.y * w4.y + o.z * w4.z + o.w * w4.w;
+        for (int kh = 0; kh < 3; ++kh) {                      // one window row at a time: three loads in flight
+            const int h = 2 * ho - 1 + kh;
+            if (h < 0) continue;
+            const float* rowp = y + (((long long)b * H + h) * W + 2 * wo - 1) * C + 4 * hl;
+            float4 v[3];
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+                if (kw > 0 || win_w0) v[kw] = ld4(rowp + kw * C);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                if (kw == 0 && !win_w0) continue;
+                float4 o;
+                o.x = fmaxf(fmaf(v[kw].x, sc.x, sh.x), 0.f);
+                o.y = fmaxf(fmaf(v[kw].y, sc.y, sh.y), 0.f);
+                o.z = fmaxf(fmaf(v[kw].z, sc.z, sh.z), 0.f);
+                o.w = fmaxf(fmaf(v[kw].w, sc.w, sh.w), 0.f);
+                if (round_out) o = round4(o);
+                const unsigned char kk = (unsigned char)(kh * 3 + kw);
+                if (o.x > m.x || am.x == 255) { m.x = o.x; am.x = kk; }
+                if (o.y > m.y || am.y == 255) { m.y = o.y; am.y = kk; }
+                if (o.z > m.z || am.z == 255) { m.z = o.z; am.z = kk; }
+                if (o.w > m.w || am.w == 255) { m.w = o.w; am.w = kk; }
+                if (kh >= 1 && kw >= 1)                       // the aux window: rows 2ho, 2ho+1 x cols 2wo, 2wo+1
+                    s[(kh - 1) * 2 + (kw - 1)] += o.x * w4.x + o.y * w4.y + o.z * w4.z + o.w * w4.w;
+            }
         }
         if (valid) {
             st4(pool + win * C + 4 * hl, m);
