@@ -65,6 +65,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// kernel<<<grid, block, smem, stream>>>(args...) through launch_pdl, inside an entry point with a `stream` argument
+#define PE_LAUNCH(kernel, grid, block, smem, ...) \
+    PE_CHECK_CUDA(pe::launch_pdl(kernel, grid, block, smem, (cudaStream_t)stream, __VA_ARGS__))
+
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------

@@ -1149,8 +1149,8 @@ extern "C" {
 int pe_bn_stats(const float* y, long long P, int C, double* stats, void* stream) {
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_stats: unsupported channel count %d", C);
-    PE_CHECK_CUDA(launch_pdl(channel_reduce_kernel<0>, reduce_grid(channel_reduce_kernel<0>, P, C), EW_THREADS, 0, (cudaStream_t)stream,
-        y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0));
+    PE_LAUNCH(channel_reduce_kernel<0>, reduce_grid(channel_reduce_kernel<0>, P, C), EW_THREADS, 0, y, nullptr,
+              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stats, P, C, 0);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1169,8 +1169,8 @@ int pe_bn_apply(const float* y, const float* scale, const float* shift, const fl
                 long long P, int C, int relu, int round_tf32, void* stream) {
     PE_REQUIRE(C % 4 == 0, "bn_apply: C %% 4 != 0");
     const long long n4 = P * (C / 4);
-    PE_CHECK_CUDA(launch_pdl(bn_apply_kernel, one_wave_grid(bn_apply_kernel, 0, n4, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream,
-        y, scale, shift, residual, out, n4, C / 4, relu, round_tf32));
+    PE_LAUNCH(bn_apply_kernel, one_wave_grid(bn_apply_kernel, 0, n4, EW_THREADS * 4), EW_THREADS, 0, y, scale, shift,
+              residual, out, n4, C / 4, relu, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1185,9 +1185,10 @@ int pe_bn_train_apply(const float* y, const double* stats, const float* gamma, c
     PE_REQUIRE(!maskbits || (reinterpret_cast<uintptr_t>(maskbits) & 15) == 0,
                "bn_train_apply: mask bits need a 16-byte aligned pointer");
     const long long n4 = P * (C / 4);
-    PE_CHECK_CUDA(launch_pdl(bn_train_apply_kernel, one_wave_grid(bn_train_apply_kernel, 2 * C * sizeof(float), n4, EW_THREADS * 4), EW_THREADS, 2 * C * sizeof(float), (cudaStream_t)stream,
-        y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd, residual,
-        out, maskbits, P, C, momentum, eps, relu, round_tf32));
+    PE_LAUNCH(bn_train_apply_kernel, one_wave_grid(bn_train_apply_kernel, 2 * C * sizeof(float), n4, EW_THREADS * 4),
+              EW_THREADS, 2 * C * sizeof(float), y, stats, gamma, beta, running_mean, running_var,
+              num_batches_tracked, scale, shift, mean, invstd, residual, out, maskbits, P, C, momentum, eps, relu,
+              round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1200,8 +1201,8 @@ int pe_bn_bwd_reduce(const float* dout, const float* dout2, const float* out, co
     PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_reduce: ReLU mask needs `out` or scale/shift");
     PE_REQUIRE(C % 4 == 0 && ((C / 4) <= EW_THREADS ? EW_THREADS % (C / 4) == 0 : (C / 4) % EW_THREADS == 0),
                "bn_bwd_reduce: unsupported channel count %d", C);
-    PE_CHECK_CUDA(launch_pdl(channel_reduce_kernel<1>, reduce_grid(channel_reduce_kernel<1>, P, C), EW_THREADS, 0, (cudaStream_t)stream,
-        dout, dout2, out, y, mean, invstd, mask_scale, mask_shift, maskbits, sums, P, C, relu));
+    PE_LAUNCH(channel_reduce_kernel<1>, reduce_grid(channel_reduce_kernel<1>, P, C), EW_THREADS, 0, dout, dout2, out,
+              y, mean, invstd, mask_scale, mask_shift, maskbits, sums, P, C, relu);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1216,11 +1217,9 @@ int pe_bn_bwd_apply(const float* dout, const float* dout2, const float* out, con
     PE_REQUIRE(C % 4 == 0 && C <= 4096, "bn_bwd_apply: unsupported channel count %d", C);
     PE_REQUIRE(!relu || out || (mask_scale && mask_shift), "bn_bwd_apply: ReLU mask needs `out` or scale/shift");
     const long long n4 = P * (C / 4);
-    PE_CHECK_CUDA(launch_pdl(bn_bwd_apply_kernel, one_wave_grid(bn_bwd_apply_kernel, 3 * C * sizeof(float), n4, EW_THREADS * 4), EW_THREADS, 3 * C * sizeof(float), (cudaStream_t)stream,
-        dout, dout2, out, y, mean, invstd, gamma, mask_scale, mask_shift, maskbits, sums, dy, dres, dres_accumulate,
-        dgamma,
-        dbeta, param_accumulate,
-        P, C, relu, round_tf32));
+    PE_LAUNCH(bn_bwd_apply_kernel, one_wave_grid(bn_bwd_apply_kernel, 3 * C * sizeof(float), n4, EW_THREADS * 4),
+              EW_THREADS, 3 * C * sizeof(float), dout, dout2, out, y, mean, invstd, gamma, mask_scale, mask_shift,
+              maskbits, sums, dy, dres, dres_accumulate, dgamma, dbeta, param_accumulate, P, C, relu, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1237,7 +1236,7 @@ int pe_pack_conv_weight(const float* w_oihw, float* w_tck, float* w_tkc, int Cou
 int pe_pack_conv_weights_batched(const long long* table_dev, int n_layers, int total_blocks, int round_tf32,
                                  void* stream) {
     if (n_layers <= 0 || total_blocks <= 0) return 0;
-    PE_CHECK_CUDA(launch_pdl(pack_weights_batched_kernel, total_blocks, EW_THREADS, 0, (cudaStream_t)stream, table_dev, n_layers, round_tf32));
+    PE_LAUNCH(pack_weights_batched_kernel, total_blocks, EW_THREADS, 0, table_dev, n_layers, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1247,8 +1246,8 @@ int pe_pack_block_elems(void) { return PACK_PER_BLOCK; }
 int pe_unpack_conv_wgrad(const float* dw_tck, float* dw_oihw, int Cout, int Cin, int R, int S, int accumulate,
                          void* stream) {
     const long long n = (long long)Cout * Cin * R * S;
-    PE_CHECK_CUDA(launch_pdl(unpack_wgrad_kernel, grid_for(n, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream,
-        dw_tck, dw_oihw, Cout, Cin, R * S, accumulate));
+    PE_LAUNCH(unpack_wgrad_kernel, grid_for(n, EW_THREADS * 4), EW_THREADS, 0, dw_tck, dw_oihw, Cout, Cin, R * S,
+              accumulate);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1267,15 +1266,15 @@ int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W
         configured = smem;
     }
     dim3 block(bx, EW_THREADS / bx);
-    PE_CHECK_CUDA(launch_pdl(im2col_stem_kernel, B * Ho, block, smem, (cudaStream_t)stream, img_nchw, col, B, C, H, W, R, S, stride, pad, Ho,
-                                                                     Wo, ldc, round_tf32));
+    PE_LAUNCH(im2col_stem_kernel, B * Ho, block, smem, img_nchw, col, B, C, H, W, R, S, stride, pad, Ho, Wo, ldc,
+              round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
 
 int pe_transpose(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream) {
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    PE_CHECK_CUDA(launch_pdl(transpose_kernel, grid, block, 0, (cudaStream_t)stream, src, lds, dst, ldd, rows, cols, round_tf32));
+    PE_LAUNCH(transpose_kernel, grid, block, 0, src, lds, dst, ldd, rows, cols, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1283,8 +1282,7 @@ int pe_transpose(const float* src, int lds, float* dst, int ldd, int rows, int c
 int pe_copy_cols(const float* src, int lds, float* dst, int ldd, int rows, int cols, int round_tf32, void* stream) {
     const long long n = (long long)rows * cols;
     if (n == 0) return 0;
-    PE_CHECK_CUDA(launch_pdl(copy_cols_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, src, lds, dst, ldd, rows,
-                                                                                       cols, round_tf32));
+    PE_LAUNCH(copy_cols_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, src, lds, dst, ldd, rows, cols, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1293,16 +1291,15 @@ int pe_axpby_cols(const float* a, int lda, const float* b, int ldb, float* out, 
                   float alpha, float beta, int round_tf32, void* stream) {
     const long long n = (long long)rows * cols;
     if (n == 0) return 0;
-    PE_CHECK_CUDA(launch_pdl(axpby_cols_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, a, lda, b, ldb, out, ldo,
-                                                                                        rows, cols, alpha, beta,
-                                                                                        round_tf32));
+    PE_LAUNCH(axpby_cols_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, a, lda, b, ldb, out, ldo, rows, cols, alpha,
+              beta, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
 
 int pe_colsum(const float* x, int ldx, float* out, int rows, int cols, int accumulate, void* stream) {
     dim3 grid((cols + 31) / 32), block(32, 8);
-    PE_CHECK_CUDA(launch_pdl(colsum_kernel, grid, block, 0, (cudaStream_t)stream, x, ldx, out, rows, cols, accumulate));
+    PE_LAUNCH(colsum_kernel, grid, block, 0, x, ldx, out, rows, cols, accumulate);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1311,8 +1308,7 @@ int pe_relu_bwd(const float* dy, int lddy, const float* y, int ldy, float* dz, i
                 void* stream) {
     const long long n = (long long)rows * cols;
     if (n == 0) return 0;
-    PE_CHECK_CUDA(launch_pdl(relu_bwd_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, dy, lddy, y, ldy, dz, lddz,
-                                                                                      rows, cols));
+    PE_LAUNCH(relu_bwd_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, dy, lddy, y, ldy, dz, lddz, rows, cols);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1335,8 +1331,8 @@ int pe_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* argmax, int B, 
     PE_REQUIRE(C % 4 == 0, "maxpool: C %% 4 != 0");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * Ho * Wo * (C / 4);
-    PE_CHECK_CUDA(launch_pdl(maxpool_fwd_kernel, one_wave_grid(maxpool_fwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, x, y, argmax, B, H, W,
-                                                                                             C, Ho, Wo));
+    PE_LAUNCH(maxpool_fwd_kernel, one_wave_grid(maxpool_fwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, x, y, argmax, B,
+              H, W, C, Ho, Wo);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1349,8 +1345,8 @@ int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* 
                "maxpool_bwd: the aux term needs its arg-max map, weights and even H, W");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
-    PE_CHECK_CUDA(launch_pdl(maxpool_bwd_kernel, one_wave_grid(maxpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream,
-        dy, dy2, argmax, dx, accumulate, B, H, W, C, Ho, Wo, aux_dout, aux_lddo, aux_argmax, aux_w));
+    PE_LAUNCH(maxpool_bwd_kernel, one_wave_grid(maxpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, dy, dy2, argmax,
+              dx, accumulate, B, H, W, C, Ho, Wo, aux_dout, aux_lddo, aux_argmax, aux_w);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1358,8 +1354,8 @@ int pe_maxpool3x3s2_bwd(const float* dy, const float* dy2, const unsigned char* 
 int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int round_tf32, void* stream) {
     PE_REQUIRE(C % 4 == 0 && ldy % 4 == 0, "avgpool: C, ldy must be multiples of 4");
     const long long n = (long long)B * (C / 4);
-    PE_CHECK_CUDA(launch_pdl(avgpool_fwd_kernel, (unsigned)((n + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream,
-        x, y, ldy, B, HW, C, round_tf32));
+    PE_LAUNCH(avgpool_fwd_kernel, (unsigned)((n + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, x, y, ldy, B, HW, C,
+              round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1367,7 +1363,8 @@ int pe_avgpool_fwd(const float* x, float* y, int ldy, int B, int HW, int C, int 
 int pe_avgpool_bwd(const float* dy, int lddy, float* dx, int B, int HW, int C, void* stream) {
     PE_REQUIRE(C % 4 == 0 && lddy % 4 == 0, "avgpool: C, lddy must be multiples of 4");
     const long long n = (long long)B * HW * (C / 4);
-    PE_CHECK_CUDA(launch_pdl(avgpool_bwd_kernel, one_wave_grid(avgpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream, dy, lddy, dx, B, HW, C));
+    PE_LAUNCH(avgpool_bwd_kernel, one_wave_grid(avgpool_bwd_kernel, 0, n, EW_THREADS), EW_THREADS, 0, dy, lddy, dx, B,
+              HW, C);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1376,8 +1373,8 @@ int pe_aux_fwd(const float* a1, const float* w, const float* bias, float* out, i
                int H, int W, int C, int round_tf32, void* stream) {
     PE_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "aux: H, W must be even and C a multiple of 4");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    PE_CHECK_CUDA(launch_pdl(aux_fwd_kernel, one_wave_grid(aux_fwd_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0, (cudaStream_t)stream,
-        a1, w, bias, out, ldo, argmax, B, H, W, C, round_tf32));
+    PE_LAUNCH(aux_fwd_kernel, one_wave_grid(aux_fwd_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0, a1, w, bias,
+              out, ldo, argmax, B, H, W, C, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1386,8 +1383,8 @@ int pe_aux_bwd(const float* dout, int lddo, const unsigned char* argmax, const f
                int accumulate, float* dw, float* db, int B, int H, int W, int C, void* stream) {
     PE_REQUIRE(C <= 256 && C % 4 == 0, "aux_bwd: C <= 256, C %% 4 == 0 required");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    PE_CHECK_CUDA(launch_pdl(aux_bwd_kernel, grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream,
-        dout, lddo, argmax, a1, w, da1, accumulate, dw, db, B, H, W, C, nullptr, nullptr, 0));
+    PE_LAUNCH(aux_bwd_kernel, grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, dout, lddo, argmax, a1, w,
+              da1, accumulate, dw, db, B, H, W, C, nullptr, nullptr, 0);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1398,8 +1395,8 @@ int pe_aux_bwd_params(const float* dout, int lddo, const unsigned char* argmax, 
     PE_REQUIRE(C <= 256 && C % 4 == 0, "aux_bwd_params: C <= 256, C %% 4 == 0 required");
     PE_REQUIRE(y && scale && shift && dw, "aux_bwd_params: y, scale, shift and dw are required");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
-    PE_CHECK_CUDA(launch_pdl(aux_bwd_kernel, grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, (cudaStream_t)stream,
-        dout, lddo, argmax, y, nullptr, nullptr, 0, dw, db, B, H, W, C, scale, shift, round_tf32));
+    PE_LAUNCH(aux_bwd_kernel, grid_for(nwin, EW_THREADS / 32 * 2 * 8, 8), EW_THREADS, 0, dout, lddo, argmax, y,
+              nullptr, nullptr, 0, dw, db, B, H, W, C, scale, shift, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -1417,9 +1414,10 @@ int pe_stem_post_train(const float* y, const double* stats, const float* gamma, 
     PE_REQUIRE(!aux_w || (aux_bias && aux_out), "stem_post_train: aux_w needs aux_bias and aux_out");
     const long long nwin = (long long)B * (H / 2) * (W / 2);
     if (nwin == 0) return 0;
-    PE_CHECK_CUDA(launch_pdl(stem_post_train_kernel, one_wave_grid(stem_post_train_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS, 0, (cudaStream_t)stream,
-        y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd, pool,
-        pool_argmax, aux_w, aux_bias, aux_out, ld_aux, aux_argmax, B, H, W, momentum, eps, round_tf32, aux_round_tf32));
+    PE_LAUNCH(stem_post_train_kernel, one_wave_grid(stem_post_train_kernel, 0, nwin, EW_THREADS / 32 * 2), EW_THREADS,
+              0, y, stats, gamma, beta, running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd,
+              pool, pool_argmax, aux_w, aux_bias, aux_out, ld_aux, aux_argmax, B, H, W, momentum, eps, round_tf32,
+              aux_round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }

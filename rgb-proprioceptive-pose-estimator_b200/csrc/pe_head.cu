@@ -238,9 +238,8 @@ int pe_lstm_cell_fwd(const float* gx, int ldgx, const float* gh, int ldgh, const
                      int round_tf32, void* stream) {
     const int n = N * Hd;
     if (n == 0) return 0;
-    PE_CHECK_CUDA(launch_pdl(lstm_cell_fwd_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, gx, ldgx, gh, ldgh, b_ih, b_hh, c_prev,
-                                                                            c_out, h_out, ldh, act, N, Hd,
-                                                                            round_tf32));
+    PE_LAUNCH(lstm_cell_fwd_kernel, (n + 255) / 256, 256, 0, gx, ldgx, gh, ldgh, b_ih, b_hh, c_prev, c_out, h_out,
+              ldh, act, N, Hd, round_tf32);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -250,8 +249,8 @@ int pe_lstm_cell_bwd(const float* dh, int lddh, const float* dh_rec, const float
                      void* stream) {
     const int n = N * Hd;
     if (n == 0) return 0;
-    PE_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, dh, lddh, dh_rec, dc_next, act, c_prev,
-                                                                            c_out, dgates, lddg, dc_prev, N, Hd));
+    PE_LAUNCH(lstm_cell_bwd_kernel, (n + 255) / 256, 256, 0, dh, lddh, dh_rec, dc_next, act, c_prev, c_out, dgates,
+              lddg, dc_prev, N, Hd);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -261,8 +260,8 @@ int pe_pose_loss(const float* pred, int ldp, const float* truth, int ldt, long l
                  void* stream) {
     PE_REQUIRE(metric >= 0 && metric <= 3, "pose_loss: metric %d invalid", metric);
     PE_REQUIRE(mode == 0 || mode == 1, "pose_loss: mode %d invalid", mode);
-    PE_CHECK_CUDA(launch_pdl(pose_loss_kernel, 1, 256, 0, (cudaStream_t)stream, pred, ldp, truth, ldt, n, metric, mode, alpha, epsilon,
-                                                          scale, loss, dpred, lddp, val));
+    PE_LAUNCH(pose_loss_kernel, 1, 256, 0, pred, ldp, truth, ldt, n, metric, mode, alpha, epsilon, scale, loss, dpred,
+              lddp, val);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -280,8 +279,8 @@ int pe_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    PE_CHECK_CUDA(launch_pdl(adam_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr_c, beta1, beta2, eps,
-                                                                    weight_decay, inv_bc2_sqrt, grad_scale));
+    PE_LAUNCH(adam_kernel, (unsigned)blocks, 256, 0, p, g, m, v, n, lr_c, beta1, beta2, eps, weight_decay,
+              inv_bc2_sqrt, grad_scale);
     PE_LAUNCH_CHECK();
     return 0;
 }
@@ -292,8 +291,7 @@ int pe_sgd_step(float* p, const float* g, float* mom, long long n, float lr, flo
     long long blocks = (n + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    PE_CHECK_CUDA(launch_pdl(sgd_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, p, g, mom, n, lr, momentum, weight_decay,
-                                                                   first_step, grad_scale));
+    PE_LAUNCH(sgd_kernel, (unsigned)blocks, 256, 0, p, g, mom, n, lr, momentum, weight_decay, first_step, grad_scale);
     PE_LAUNCH_CHECK();
     return 0;
 }
