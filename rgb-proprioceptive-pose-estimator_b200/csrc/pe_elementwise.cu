@@ -489,7 +489,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ tck, float* __rest
 // One block per output row (b, ho): the R input rows of every channel it needs are staged (zero padded,
 // TF32-rounded) in shared memory, then written out as Wo im2col rows with 128-bit coalesced stores.
 // blockDim = (ldc/4, rows in flight); thread x owns the same four k columns for every row.
-__global__ void __launch_bounds__(EW_THREADS)
+__global__ void __launch_bounds__(EW_THREADS, 6)
 im2col_stem_kernel(const float* __restrict__ img, float* __restrict__ col, int B, int C, int H, int W, int R, int S,
                    int stride, int pad, int Ho, int Wo, int ldc, int round_out) {
     pdl_sync();
@@ -500,22 +500,42 @@ im2col_stem_kernel(const float* __restrict__ img, float* __restrict__ col, int B
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     const float* src = img + (size_t)b * C * H * W;
     const int h0 = ho * stride - pad;
-    // groups of 64 threads walk whole input rows: the (c, r) decomposition and the row pointer are computed once per
-    // row, not per element (the per-element div / mod version was issue-bound: 85 % issue slots busy, 3.4 TB/s)
+    // groups of 64 threads walk whole input rows: (c, r) advance incrementally, the row pointer and the in-range test
+    // are per row, and the body is three plain segments (left pad, 128-bit loads of the row, right pad) -- the
+    // per-element div / mod version was issue-bound (85 % issue slots busy at 3.4 TB/s)
     const int gsz = nthr >= 64 ? 64 : nthr;
     const int grp = tid / gsz, gl = tid - grp * gsz, ngrp = nthr / gsz;
     if (grp < ngrp) {
+        int c = grp / R, r = grp - c * R;
+        const bool vec = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
         for (int cr = grp; cr < C * R; cr += ngrp) {
-            const int r = cr % R, c = cr / R;
             const int h = h0 + r;
-            const bool hin = h >= 0 && h < H;
-            const float* rowp = src + ((size_t)c * H + (hin ? h : 0)) * W;
             float* dstp = rows_sm + cr * SW;
-            for (int x = gl; x < SW; x += gsz) {
-                const int w = x - pad;
-                const float v = (hin && w >= 0 && w < W) ? __ldg(rowp + w) : 0.f;
-                dstp[x] = round_out ? round_tf32(v) : v;
+            if (h < 0 || h >= H) {
+                for (int x = gl; x < SW; x += gsz) dstp[x] = 0.f;
+            } else {
+                const float* rowp = src + ((size_t)c * H + h) * W;
+                for (int x = gl; x < pad; x += gsz) {
+                    dstp[x] = 0.f;
+                    dstp[pad + W + x] = 0.f;
+                }
+                float* body = dstp + pad;
+                if (vec) {
+                    const int W4 = W >> 2;
+                    for (int q = gl; q < W4; q += gsz) {
+                        float4 v = __ldg(reinterpret_cast<const float4*>(rowp) + q);
+                        if (round_out) v = round4(v);
+                        body[4 * q + 0] = v.x; body[4 * q + 1] = v.y; body[4 * q + 2] = v.z; body[4 * q + 3] = v.w;
+                    }
+                } else {
+                    for (int w = gl; w < W; w += gsz) {
+                        const float v = __ldg(rowp + w);
+                        body[w] = round_out ? round_tf32(v) : v;
+                    }
+                }
             }
+            r += ngrp;
+            while (r >= R) { r -= R; ++c; }
         }
     }
     // one extra, all-zero row: the padding columns k >= K read it, so the copy loop below has no predicates
