@@ -82,6 +82,29 @@ def test_bench_gpu_arm_is_independent_of_the_oracle():
     assert not offenders, offenders
 
 
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU port of the reference step, no GPU needed) prints one JSON line with the
+    contract's keys: same metric / unit / config as the GPU arm, `impl`, a `cpu_baseline` describing the run and an
+    `e2e` object that repeats the line's own value with zero copy bytes."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(__file__))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_samples_per_s" and d["unit"] == "samples/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert abs(d["cpu_baseline"]["value"] - d["value"]) <= 1e-9 * d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["unit"] == d["unit"] and abs(d["e2e"]["value"] - d["value"]) <= 1e-9 * d["value"]
+
+
 def test_bench_conv_table_matches_the_trunk():
     """bench.py's analytic per-layer roofline walks the same 53 convolutions as the mirrored trunk
     (util/model_utils.py:10-31) and its flop count agrees with SURVEY 8(d)'s 24.3 GFLOP per training frame."""
