@@ -185,6 +185,18 @@ dim3 reduce_grid(K kernel, long long P, int C) {
     return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
+// Batch mean / invstd of one channel from the fp64 sums: E[x^2] - E[x]^2 in double (cancellation), the reciprocal
+// square root in float -- one IEEE sqrt + divide instead of their ~150-instruction double versions, which every CTA
+// of the apply kernels runs for every channel before it can touch an activation.
+__device__ __forceinline__ void bn_moments(const double* __restrict__ stats, int C, int c, double inv_count,
+                                           float eps, float& mean, float& invstd, double& var) {
+    const double m = stats[c] * inv_count;
+    var = stats[C + c] * inv_count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = 1.f / sqrtf((float)var + eps);
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ scale,
@@ -194,11 +206,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float
     if (c >= C) return;
     float mean, invstd;
     if (stats) {
-        const double m = stats[c] / count;
-        double var = stats[C + c] / count - m * m;
-        if (var < 0.0) var = 0.0;
-        mean = (float)m;
-        invstd = (float)(1.0 / sqrt(var + (double)eps));
+        double var;
+        bn_moments(stats, C, c, 1.0 / count, eps, mean, invstd, var);
         if (running_mean) {
             const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
             running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
@@ -260,12 +269,11 @@ bn_train_apply_kernel(const float* __restrict__ y, const double* __restrict__ st
     float* csc = coef;
     float* csh = coef + C;
     const double count = (double)P;
+    const double inv_count = 1.0 / count;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const double m = stats[c] / count;
-        double var = stats[C + c] / count - m * m;
-        if (var < 0.0) var = 0.0;
-        const float mean = (float)m;
-        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        float mean, invstd;
+        double var;
+        bn_moments(stats, C, c, inv_count, eps, mean, invstd, var);
         const float sc = gamma[c] * invstd;
         const float sh = beta[c] - mean * sc;
         csc[c] = sc;
@@ -961,13 +969,12 @@ stem_post_train_kernel(const float* __restrict__ y, const double* __restrict__ s
     __shared__ __align__(16) float csc[C];
     __shared__ __align__(16) float csh[C];
     const double count = (double)B * H * W;
+    const double inv_count = 1.0 / count;
     if (threadIdx.x < C) {
         const int c = threadIdx.x;
-        const double m = stats[c] / count;
-        double var = stats[C + c] / count - m * m;
-        if (var < 0.0) var = 0.0;
-        const float mean = (float)m;
-        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        float mean, invstd;
+        double var;
+        bn_moments(stats, C, c, inv_count, eps, mean, invstd, var);
         const float sc = gamma[c] * invstd;
         const float sh = beta[c] - mean * sc;
         csc[c] = sc;
