@@ -24,6 +24,10 @@ extern "C" {
 const char* pe_last_error(void);
 int pe_device_error(void);      /* bitmask: 1 conv producer, 2 wgrad producer, 4 MMA issuer, 8 epilogue */
 void pe_device_error_clear(void);
+/* If the sticky flag is set, overwrite buf[0..n) with NaN (asynchronous, graph capturable): a training step's loss
+ * or a rollout step's pose then shows the fault even when the caller never polls pe_device_error().  Guards the
+ * results handed back at util/learn_utils.py:182 (loss.item()) and :448 (pose read-back). */
+int pe_poison_on_error(float* buf, long long n, void* stream);
 int pe_version(void);
 /* debug: override UMMA shared-memory descriptor strides (bytes; <0 restores the default) */
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo);

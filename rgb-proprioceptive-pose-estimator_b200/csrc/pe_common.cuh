@@ -114,12 +114,16 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return done;
 }
-// Bounded wait: returns false after ~2^31 SM cycles (~0.15 s) instead of hanging the GPU.
+// Bounded wait: returns false after PE_WAIT_LIMIT SM cycles (2^30, ~0.55 s at 1.9 GHz: long enough to ride out a
+// time-slice / MPS preemption, short enough that a protocol bug cannot hang the GPU).  A timeout sets the sticky
+// device flag (pe_device_error); pe_poison_on_error turns it into NaNs in the step's result so that a training
+// or rollout loop cannot silently continue on unwritten tiles.
+#define PE_WAIT_LIMIT (1ll << 30)
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (1ll << 28)) return false;
+        if (clock64() - t0 > PE_WAIT_LIMIT) return false;
     }
     return true;
 }
@@ -146,14 +150,14 @@ __device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, in
         const long long t0 = clock64();
         for (;;) {
             if (__all_sync(0xffffffffu, mbar_test_wait(bar, parity))) return true;
-            if (__any_sync(0xffffffffu, clock64() - t0 > (1ll << 28))) return false;
+            if (__any_sync(0xffffffffu, clock64() - t0 > PE_WAIT_LIMIT)) return false;
         }
     }
     if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
     const long long t0 = clock64();
     for (;;) {
         if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
-        if (__any_sync(0xffffffffu, clock64() - t0 > (1ll << 28))) return false;
+        if (__any_sync(0xffffffffu, clock64() - t0 > PE_WAIT_LIMIT)) return false;
     }
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint32_t bar, uint32_t bytes) {

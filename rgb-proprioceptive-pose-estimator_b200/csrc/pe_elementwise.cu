@@ -1149,7 +1149,7 @@ depth_features_bwd_kernel(float* __restrict__ dprod, int ld, const float* __rest
 }
 
 __global__ void preprocess_u8_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int B, int Hs,
-                                     int Ws, int crop, float m0, float m1, float m2, float i0, float i1, float i2) {
+                                     int Ws, int crop, float m0, float m1, float m2, float s0, float s1, float s2) {
     const long long n = (long long)B * crop * crop;
     const long long gs = (long long)gridDim.x * blockDim.x;
     const int oy = (Hs - crop) / 2, ox = (Ws - crop) / 2;
@@ -1160,9 +1160,11 @@ __global__ void preprocess_u8_kernel(const unsigned char* __restrict__ src, floa
         const unsigned char* p = src + (((long long)b * Hs + (y + oy)) * Ws + (x + ox)) * 3;
         const long long plane = (long long)crop * crop;
         float* o = dst + (long long)b * 3 * plane + (long long)y * crop + x;
-        o[0] = ((float)p[0] / 255.f - m0) * i0;
-        o[plane] = ((float)p[1] / 255.f - m1) * i1;
-        o[2 * plane] = ((float)p[2] / 255.f - m2) * i2;
+        // ToTensor's x / 255 followed by Normalize's (x - mean) / std, with true divisions like the reference's
+        // transform (util/data_utils.py:48-54): bit-identical to torchvision on the same uint8 frame
+        o[0] = __fdiv_rn(__fdiv_rn((float)p[0], 255.f) - m0, s0);
+        o[plane] = __fdiv_rn(__fdiv_rn((float)p[1], 255.f) - m1, s1);
+        o[2 * plane] = __fdiv_rn(__fdiv_rn((float)p[2], 255.f) - m2, s2);
     }
 }
 
@@ -1476,7 +1478,7 @@ int pe_preprocess_u8(const unsigned char* src, float* dst, int B, int Hs, int Ws
     PE_REQUIRE(crop <= Hs && crop <= Ws, "preprocess: crop larger than frame");
     const long long n = (long long)B * crop * crop;
     preprocess_u8_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
-        src, dst, B, Hs, Ws, crop, mean3[0], mean3[1], mean3[2], 1.f / std3[0], 1.f / std3[1], 1.f / std3[2]);
+        src, dst, B, Hs, Ws, crop, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
     PE_LAUNCH_CHECK();
     return 0;
 }

@@ -46,6 +46,13 @@ static int ensure_error_flag() {
     return 0;
 }
 
+// Turns a pipeline timeout into something the caller cannot miss without a host synchronisation: when the sticky
+// flag is set, the given result buffer (the step's loss, the rollout step's pose) is overwritten with NaNs.
+__global__ void poison_on_error_kernel(const int* flag, float* buf, long long n) {
+    if (*flag == 0) return;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) buf[i] = __int_as_float(0x7fc00000);
+}
+
 // ---------------------------------------------------------------------------------------------
 // tensor maps
 // ---------------------------------------------------------------------------------------------
@@ -605,6 +612,8 @@ static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, flo
                            int K, const Epilogue& ep, int accumulate_into_y, cudaStream_t stream) {
     if (ensure_error_flag()) return 2;
     PE_REQUIRE(ldx % 4 == 0 && ldw % 4 == 0, "linear: ldx/ldw must be multiples of 4 (got %d, %d)", ldx, ldw);
+    PE_REQUIRE(N <= ldy && K <= ldx && K <= ldw, "linear: N = %d / K = %d exceed the row strides (ldy %d, ldx %d, ldw %d)",
+               N, K, ldy, ldx, ldw);
     TapMaps maps;
     TapParams p;
     init_params(p);
@@ -761,6 +770,14 @@ int pe_device_error(void) {
     int v = 0;
     if (cudaMemcpy(&v, g_error_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return v;
+}
+
+int pe_poison_on_error(float* buf, long long n, void* stream) {
+    if (ensure_error_flag()) return 2;
+    if (n <= 0) return 0;
+    poison_on_error_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(g_error_flag, buf, n);
+    PE_LAUNCH_CHECK();
+    return 0;
 }
 
 void pe_device_error_clear(void) {

@@ -67,8 +67,13 @@ class PoseDistanceLoss(nn.Module):
             prediction = torch.as_tensor(prediction)
         if isinstance(truth, np.ndarray):
             truth = torch.as_tensor(truth)
-        if not prediction.is_cuda:
-            raise native.PeError("PoseDistanceLoss (B200 path) needs CUDA tensors; there is no CPU fallback")
+        host = not prediction.is_cuda
+        if host:
+            # the rollout loop evaluates the metric on host tensors / numpy arrays (util/learn_utils.py:455,492): they
+            # are staged to the current CUDA device -- the arithmetic itself has no CPU implementation here
+            if not torch.cuda.is_available():
+                raise native.PeError("PoseDistanceLoss (B200 path) needs a CUDA device; there is no CPU fallback")
+            prediction = prediction.to(torch.device("cuda", torch.cuda.current_device()), dtype=torch.float32)
         truth = truth.to(prediction.device)
         if prediction.dtype != torch.float32:
             raise native.PeError("prediction must be float32")
@@ -84,7 +89,9 @@ class PoseDistanceLoss(nn.Module):
             L.pe_pose_loss(P(p), p.stride(0), P(t), 7, n, metric, 0, 0.0, float(self.epsilon), 1.0, None, None, 7,
                            P(val), st)
             v = val.cpu().numpy()
+            L.check_device()                  # synchronised by the read-back above: surface pipeline timeouts here
             return np.float32(v[0]), float(v[1])
         mode = 1 if self.mode == "pose" else 0
-        return _PoseLossFn.apply(prediction, truth, metric, mode, float(self.alpha), float(self.epsilon),
+        loss = _PoseLossFn.apply(prediction, truth, metric, mode, float(self.alpha), float(self.epsilon),
                                  float(self.scale_factor))
+        return loss.cpu() if host else loss

@@ -12,8 +12,9 @@ import math
 import torch
 import torch.nn as nn
 
+from pe_b200 import native
 from pe_b200.estimators import NaiveEefCore, NaiveObjectCore
-from pe_b200.functions import run_core
+from pe_b200.functions import run_core, stage_inputs
 from util.model_utils import PassThroughParallel, import_resnet
 
 
@@ -66,6 +67,20 @@ def _inputs(model, img, depth, self_measurement):
     return (img, self_measurement)
 
 
+def _run(model, core_cls, inputs, state=None):
+    """Shared forward of the five mirrors: build the core lazily, stage host tensors to the compute device (and hand
+    the outputs back on the host in that case, as the reference's rollout loop expects), run the kernels."""
+    if model._core is None:
+        object.__setattr__(model, "_core", core_cls(model))
+    inputs, host = stage_inputs(model, inputs)
+    outs = run_core(model._core, inputs, model.training, state,
+                    inference=bool(getattr(model, "rollout", False)) and not model.training)
+    if host:
+        outs = tuple(o.cpu() for o in outs)
+        native.lib().check_device()       # the host copy synchronised anyway: surface a pipeline timeout right here
+    return outs
+
+
 class NaiveEndEffectorStateEstimator(nn.Module):
     """
     One-shot estimator of the other arm's end-effector pose from an image and the active arm's own
@@ -95,9 +110,7 @@ class NaiveEndEffectorStateEstimator(nn.Module):
 
     def forward(self, img, depth, self_measurement):
         """img (N,C,H,W), depth ignored, self_measurement (N,7) -> (pre_out (N,7), post_out (N,7))"""
-        if self._core is None:
-            object.__setattr__(self, "_core", NaiveEefCore(self))
-        pre_out, post_out = run_core(self._core, (img, self_measurement), self.training)
+        pre_out, post_out = _run(self, NaiveEefCore, (img, self_measurement))
         return pre_out, post_out
 
     def reset_initial_state(self, batch_size):
@@ -159,9 +172,7 @@ class NaiveObjectStateEstimator(nn.Module):
 
     def forward(self, img, depth, self_measurement):
         """img (N,C,H,W), depth (N,1,H,W) when use_depth else ignored, self_measurement (N,7) -> pose (N,7)"""
-        if self._core is None:
-            object.__setattr__(self, "_core", NaiveObjectCore(self))
-        return run_core(self._core, _inputs(self, img, depth, self_measurement), self.training)[0]
+        return _run(self, NaiveObjectCore, _inputs(self, img, depth, self_measurement))[0]
 
     def reset_initial_state(self, batch_size):
         pass

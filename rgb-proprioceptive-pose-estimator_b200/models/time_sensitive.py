@@ -10,17 +10,18 @@ starts from zeros otherwise (models/time_sensitive.py:501-507).
 import torch
 import torch.nn as nn
 
-from models.naive import _check_supported, _inputs, _probe_feature_layers
+from models.naive import _check_supported, _inputs, _probe_feature_layers, _run
 from pe_b200.estimators import TDCore, TDOCore, TDOV2Core
-from pe_b200.functions import run_core
+from pe_b200.functions import compute_device
 from util.model_utils import PassThroughParallel, import_resnet
 
 
-def _state_2d(t, like):
+def _state_2d(t, model):
     """(1,N,H) reference-style state tensor -> contiguous (N,H) fp32 on the compute device."""
     if t is None:
         return None
-    return t.detach().reshape(t.shape[-2], t.shape[-1]).to(device=like.device, dtype=torch.float32).contiguous()
+    return t.detach().reshape(t.shape[-2], t.shape[-1]).to(device=compute_device(model),
+                                                            dtype=torch.float32).contiguous()
 
 
 class TemporallyDependentStateEstimator(nn.Module):
@@ -81,13 +82,11 @@ class TemporallyDependentStateEstimator(nn.Module):
 
     def forward(self, img, depth, self_measurement):
         """img (S,N,C,H,W), self_measurement (S,N,7) -> (pre_out (S,N,7), post_out (S,N,7))"""
-        if self._core is None:
-            object.__setattr__(self, "_core", TDCore(self))
         state = None
         if self.rollout:
-            state = ((_state_2d(self.pre_measurement_h, img), _state_2d(self.pre_measurement_c, img)),
-                     (_state_2d(self.post_measurement_h, img), _state_2d(self.post_measurement_c, img)))
-        pre_out, post_out = run_core(self._core, _inputs(self, img, depth, self_measurement), self.training, state)
+            state = ((_state_2d(self.pre_measurement_h, self), _state_2d(self.pre_measurement_c, self)),
+                     (_state_2d(self.post_measurement_h, self), _state_2d(self.post_measurement_c, self)))
+        pre_out, post_out = _run(self, TDCore, _inputs(self, img, depth, self_measurement), state)
         if self.rollout:
             (h1, c1), (h2, c2) = self._core.last_state
             self.pre_measurement_h, self.pre_measurement_c = h1.unsqueeze(0), c1.unsqueeze(0)
@@ -165,12 +164,10 @@ class TemporallyDependentObjectStateEstimator(nn.Module):
 
     def forward(self, img, depth, self_measurement):
         """img (S,N,C,H,W), self_measurement (S,N,7) -> pose (S,N,7)"""
-        if self._core is None:
-            object.__setattr__(self, "_core", TDOCore(self))
         state = None
         if self.rollout:
-            state = (_state_2d(self.rnn_h, img), _state_2d(self.rnn_c, img))
-        out = run_core(self._core, _inputs(self, img, depth, self_measurement), self.training, state)[0]
+            state = (_state_2d(self.rnn_h, self), _state_2d(self.rnn_c, self))
+        out = _run(self, TDOCore, _inputs(self, img, depth, self_measurement), state)[0]
         if self.rollout:
             h, c = self._core.last_state
             self.rnn_h, self.rnn_c = h.unsqueeze(0), c.unsqueeze(0)
@@ -248,13 +245,11 @@ class TemporallyDependentObjectStateEstimatorV2(nn.Module):
 
     def forward(self, img, depth, self_measurement):
         """img (S,N,C,H,W), self_measurement (S,N,7) -> pose (S,N,7)"""
-        if self._core is None:
-            object.__setattr__(self, "_core", TDOV2Core(self))
         state = None
         if self.rollout:
-            state = ((_state_2d(self.img_rnn_h, img), _state_2d(self.img_rnn_c, img)),
-                     (_state_2d(self.proprio_rnn_h, img), _state_2d(self.proprio_rnn_c, img)))
-        out = run_core(self._core, _inputs(self, img, depth, self_measurement), self.training, state)[0]
+            state = ((_state_2d(self.img_rnn_h, self), _state_2d(self.img_rnn_c, self)),
+                     (_state_2d(self.proprio_rnn_h, self), _state_2d(self.proprio_rnn_c, self)))
+        out = _run(self, TDOV2Core, _inputs(self, img, depth, self_measurement), state)[0]
         if self.rollout:
             (h1, c1), (h2, c2) = self._core.last_state
             self.img_rnn_h, self.img_rnn_c = h1.unsqueeze(0), c1.unsqueeze(0)

@@ -100,6 +100,11 @@ class TrunkEngine:
         self._eval_version = None
         self._pack_key = None
         self.round_tf32 = 1
+        # The BN coefficient arenas (scale / shift / mean / invstd) are overwritten by every forward.  Under autograd
+        # torch allows several forwards before a backward (loss(model(a)) + loss(model(b))), so a taped forward keeps
+        # its own copy of the four vectors (26 560 floats each); the fused trainer runs strictly forward -> backward
+        # and switches the copy off.
+        self.snapshot_bn = True
 
     # ------------------------------------------------------------------------------------------
     def _ensure_device(self, dev):
@@ -124,7 +129,9 @@ class TrunkEngine:
                 self.w_tkc.append(torch.empty(r * s, ci, co, **f32))
         fc = self.net.fc
         self.fc_w = torch.empty(fc.out_features, fc.in_features, **f32)
-        self.fc_wt = torch.empty(fc.in_features, fc.out_features, **f32)
+        # transposed shadow for the fc dgrad: rows padded to a multiple of 4 floats (any latent_dim, e.g. the
+        # constructors' default 50, keeps 16-byte aligned rows for TMA); the padding stays zero
+        self.fc_wt = torch.zeros(fc.in_features, (fc.out_features + 3) // 4 * 4, **f32)
         self._packed_version = None
         self._eval_version = None
         self._pack_key = None
@@ -170,14 +177,15 @@ class TrunkEngine:
         L.pe_copy_cols(P(fc.weight), fc.in_features, P(self.fc_w), fc.in_features, fc.out_features, fc.in_features,
                        self.round_tf32, st)
         if need_dgrad:
-            L.pe_transpose(P(fc.weight), fc.in_features, P(self.fc_wt), fc.out_features, fc.out_features,
+            L.pe_transpose(P(fc.weight), fc.in_features, P(self.fc_wt), self.fc_wt.shape[1], fc.out_features,
                            fc.in_features, self.round_tf32, st)
         self._packed_version = ver
 
-    def _bn_views(self, i):
+    def _bn_views(self, i, arena=None):
         C = self.convs[i][1].num_features
         o = self.bn_off[i]
-        return (self.scale[o:o + C], self.shift[o:o + C], self.mean[o:o + C], self.invstd[o:o + C],
+        sc, sh, mean, invstd = arena if arena is not None else (self.scale, self.shift, self.mean, self.invstd)
+        return (sc[o:o + C], sh[o:o + C], mean[o:o + C], invstd[o:o + C],
                 self.stats[2 * o:2 * o + 2 * C], self.sums[2 * o:2 * o + 2 * C])
 
     def prepare_eval(self):
@@ -357,7 +365,10 @@ class TrunkEngine:
         if head_tape is None:
             return None
         head_tape.append(("tail", x, pool))
-        return {"tape": head_tape, "B": B, "frozen": frozen}
+        arena = None
+        if self.snapshot_bn and not frozen:
+            arena = (self.scale.clone(), self.shift.clone(), self.mean.clone(), self.invstd.clone())
+        return {"tape": head_tape, "B": B, "frozen": frozen, "arena": arena}
 
     # ------------------------------------------------------------------------------------------
     def backward(self, ctx, d_feat, ld_dfeat, d_aux, ld_daux, grad_of, on_ready=None):
@@ -368,6 +379,7 @@ class TrunkEngine:
         L, st, P = native.lib(), native.stream_ptr(), native.ptr
         tape = ctx["tape"]
         frozen = ctx.get("frozen", False)
+        arena = ctx.get("arena")
         done_after_conv = {}
         if on_ready is not None:
             for blk, ids in self.blocks:
@@ -385,16 +397,19 @@ class TrunkEngine:
                 fc = self.net.fc
                 nin, nout = fc.in_features, fc.out_features
                 # rounded copy of d_feat so that the TF32 truncation of the MMA operand is unbiased
-                dfr = torch.empty(B, nout, device=dev, dtype=torch.float32)
-                L.pe_copy_cols(P(d_feat), ld_dfeat, P(dfr), nout, B, nout, rt, st)
-                L.pe_linear_wgrad(P(pool), nin, P(dfr), nout, P(grad_of(fc.weight)), nin, B, nout, nin, st)
-                L.pe_colsum(P(dfr), nout, P(grad_of(fc.bias)), B, nout, 0, st)
+                # (row stride padded to a multiple of 4 floats: latent_dim need not be one -- the default is 50)
+                ldf = (nout + 3) // 4 * 4
+                dfr = torch.zeros(B, ldf, device=dev, dtype=torch.float32) if ldf != nout else \
+                    torch.empty(B, ldf, device=dev, dtype=torch.float32)
+                L.pe_copy_cols(P(d_feat), ld_dfeat, P(dfr), ldf, B, nout, rt, st)
+                L.pe_linear_wgrad(P(pool), nin, P(dfr), ldf, P(grad_of(fc.weight)), nin, B, nout, nin, st)
+                L.pe_colsum(P(dfr), ldf, P(grad_of(fc.bias)), B, nout, 0, st)
                 if frozen:
                     if on_ready is not None:
                         on_ready([fc.weight, fc.bias])
                     continue
                 dpool = torch.empty(B, nin, device=dev, dtype=torch.float32)
-                L.pe_linear_fwd(P(dfr), nout, P(self.fc_wt), nout, None, None, P(dpool), nin, B, nin, nout, 0, 0, 0,
+                L.pe_linear_fwd(P(dfr), ldf, P(self.fc_wt), ldf, None, None, P(dpool), nin, B, nin, nout, 0, 0, 0,
                                 None, st)
                 dx = torch.empty_like(x.t)
                 L.pe_avgpool_bwd(P(dpool), nin, P(dx), B, x.H * x.W, x.C, st)
@@ -404,7 +419,7 @@ class TrunkEngine:
             elif kind == "bn":
                 _, i, y, out, relu, residual, maskbits = rec
                 _, bn = self.convs[i]
-                sc, sh, mean, invstd, _, sums = self._bn_views(i)
+                sc, sh, mean, invstd, _, sums = self._bn_views(i, arena)
                 entries = slots.pop(out)
                 dy = torch.empty_like(y.t)
                 if residual is not None and maskbits is not None:
@@ -481,7 +496,7 @@ class TrunkEngine:
                     # the 1x1 conv's own gradients (reads a1 at the arg-max pixels only); the scatter into da1 is
                     # fused into the max-pool backward below
                     if y0 is not None:      # fused stem tail: a1 = relu(bn1(y0)) is rebuilt at those pixels
-                        sc, sh = self._bn_views(0)[:2]
+                        sc, sh = self._bn_views(0, arena)[:2]
                         L.pe_aux_bwd_params(P(d_aux), ld_daux, P(aux_am), P(y0.t), P(sc), P(sh), self.round_tf32,
                                             P(gw), P(gb), a1.B, a1.H, a1.W, a1.C, st)
                     else:

@@ -246,7 +246,8 @@ class NaiveEefCore:
         eng, tctx, hs_pre, hs_post, B = saved
         dev = hs_pre[0].device
         d_post = _pad_grad(douts[1], B, dev, 0)
-        dcat_post = self._mlp_bwd(self.post, hs_post, d_post, B, grad_of, dev, self.latent + 8, self.ld_cat)
+        dcat_post = self._mlp_bwd(self.post, hs_post, d_post, B, grad_of, dev, min(self.latent + 8, self.ld_cat),
+                                  self.ld_cat)
         # gradient reaching pre_out: direct (loss on pre_out) + through measurement_diff
         d_pre = _pad_grad(douts[0], B, dev, 0)
         L.pe_axpby_cols(P(d_pre), OUT_LD, P(dcat_post[:, self.latent:]), self.ld_cat, P(d_pre), OUT_LD, B, 7, 1.0,
@@ -532,7 +533,7 @@ class TDCore:
         dh2 = torch.empty(M, H2, device=dev, dtype=torch.float32)
         self.post_fc.backward(h2, H2, M, d_post, OUT_LD, grad_of, dh2, H2)
         dcat2 = torch.zeros(M, self.ld_cat, device=dev, dtype=torch.float32)
-        self.post_rnn.backward(rctx2, dh2, grad_of, dcat2, self.ld_cat, dx_cols=self.n_feat + 8)
+        self.post_rnn.backward(rctx2, dh2, grad_of, dcat2, self.ld_cat, dx_cols=min(self.n_feat + 8, self.ld_cat))
         d_pre = _pad_grad(douts[0], M, dev, 0)
         L.pe_axpby_cols(P(d_pre), OUT_LD, P(dcat2[:, self.n_feat:]), self.ld_cat, P(d_pre), OUT_LD, M, 7, 1.0, 1.0,
                         1, st)

@@ -41,10 +41,41 @@ class _CoreFunction(torch.autograd.Function):
         return tuple(out)
 
 
-def run_core(core, inputs, training, state=None):
-    """Run an estimator core under autograd.  `inputs` are the data tensors (img, self_measurement)."""
+def compute_device(module):
+    """The CUDA device an estimator computes on.  A model whose parameters still live on the host (the reference's
+    rollout script never calls .cuda(), util/learn_utils.py:322) is moved to the current CUDA device first --
+    nn.Module.to() keeps the Parameter objects, so an optimizer built earlier stays valid, exactly as with the
+    `model.cuda()` inside the reference's train() (util/learn_utils.py:79-80).  No CUDA device -> PeError: there is
+    no CPU implementation of this path."""
+    p = next(module.parameters())
+    if p.is_cuda:
+        return p.device
+    if not torch.cuda.is_available():
+        raise native.PeError("the B200 pose-estimator path needs a CUDA device; there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    module.to(dev)
+    return dev
+
+
+def stage_inputs(module, inputs):
+    """Host tensors are staged to the compute device (the reference's rollout loop feeds CPU tensors and reads the
+    result with .numpy(), util/learn_utils.py:415-455).  Returns (device inputs, whether the caller was on the host)."""
+    host = any(t is not None and torch.is_tensor(t) and not t.is_cuda for t in inputs)
+    dev = compute_device(module)
+    if not host:
+        return inputs, False
+    return tuple(None if t is None else torch.as_tensor(t).to(dev, non_blocking=True) for t in inputs), True
+
+
+def run_core(core, inputs, training, state=None, inference=False):
+    """Run an estimator core under autograd.  `inputs` are the data tensors (img, self_measurement).
+
+    Gradient bookkeeping happens for train-mode forwards only: an eval-mode forward (validation phase,
+    util/learn_utils.py:106,155; rollout, :322-323 -- which the reference runs with autograd accidentally left on,
+    quirk Q9) folds BatchNorm into the convolutions and keeps no tape, so its outputs do not require grad."""
     params = core.params()
-    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    need_grad = (training and not inference and torch.is_grad_enabled()
+                 and any(p.requires_grad for p in params))
     if need_grad:
         outs = _CoreFunction.apply(core, training, True, state, len(inputs), *inputs, *params)
     else:

@@ -33,6 +33,12 @@ class FramePreprocessor:
             raise native.PeError("raw frames must be HWC with 3 channels")
         lead = frames_u8.shape[:-3]
         Hs, Ws = frames_u8.shape[-3], frames_u8.shape[-2]
+        if min(Hs, Ws) != 256:
+            # Resize(256) (shorter side -> 256, bilinear) is the identity only for 256-pixel renders -- robosuite's
+            # default and the only size the reference's scripts produce; anything else would silently diverge from
+            # the reference transform, so it is refused rather than centre-cropped at native resolution
+            raise native.PeError("FramePreprocessor handles renders whose shorter side is 256 pixels (Resize(256) is "
+                                 "then the identity); got %dx%d" % (Hs, Ws))
         B = 1
         for d in lead:
             B *= d

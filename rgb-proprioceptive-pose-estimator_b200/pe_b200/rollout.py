@@ -74,6 +74,10 @@ class StreamingEstimator:
             elif dst is not None and src.data_ptr() != dst.data_ptr():   # the fused head updates the state in place
                 L.pe_copy_cols(P(src), src.stride(0), P(dst), dst.stride(0), dst.shape[0], dst.shape[1], 0, st)
         carry(self.state, new_state)
+        for o in outs:
+            # a pipeline timeout shows up as NaN poses (captured into the graph, so every replay checks)
+            base = o._base if o._base is not None else o
+            L.pe_poison_on_error(P(base), base.numel(), st)
         return outs
 
     def _capture(self):

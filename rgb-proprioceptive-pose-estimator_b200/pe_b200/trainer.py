@@ -35,6 +35,17 @@ def get_core(model):
     return core
 
 
+def engine_of(core, dev):
+    """The TrunkEngine a core drives (created on first use by the core's own accessor)."""
+    if hasattr(core, "_engine"):
+        try:
+            return core._engine()
+        except TypeError:
+            return core._engine(dev)          # TDCore places its unregistered aux conv on the device first
+    net = core.net if hasattr(core, "net") else core.m.feature_net
+    return getattr(net, "module", net).pe_engine()
+
+
 def invalidate_core(core):
     """Drop every packed-weight cache (parameters were updated by a raw kernel, not a torch op)."""
     for v in vars(core).values():
@@ -52,6 +63,8 @@ def invalidate_core(core):
 
 
 class FusedTrainer:
+    POLL_EVERY = 64       # steps between host reads of the device error flag (a 4-byte D2H copy + sync)
+
     def __init__(self, model, distance_metric="l2", alpha=1.0, epsilon=1e-4, scale_factor=1.0, mode="pose",
                  lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, optimizer="adam", momentum=0.0,
                  process_group=None, bucket_mb=32):
@@ -98,6 +111,8 @@ class FusedTrainer:
         nbts = [b for n, b in self.model.named_buffers() if n.endswith("num_batches_tracked")]
         self._flat = True
         invalidate_core(self.core)
+        # strictly forward -> backward here: no per-forward copy of the BN coefficient arenas
+        engine_of(self.core, dev).snapshot_bn = False
         self.touched = set()
         self.reducer = None
         if self.pg is not None:
@@ -165,6 +180,11 @@ class FusedTrainer:
         else:
             core.backward(saved, tuple(douts), self.grad_of)
         self._pending_loss = losses.sum() if len(outs) > 1 else losses
+        # a tcgen05 / TMA pipeline timeout anywhere in this step turns the loss into NaN (asynchronously, on the
+        # device); every POLL_EVERY steps the sticky flag is also read back and raised as an exception
+        L.pe_poison_on_error(P(self._pending_loss), 1, st)
+        if self.t % self.POLL_EVERY == self.POLL_EVERY - 1:
+            L.check_device()
         return self._pending_loss
 
     def apply_update(self):
