@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference modules from /root/reference in the build container.
 
-TEST INFRASTRUCTURE ONLY (used by oracle/make_golden.py and tests/test_oracle_vs_reference.py; the
-reference tree does not exist on the GPU box, so everything here is skipped there).
+TEST / BASELINE INFRASTRUCTURE ONLY (used by oracle/make_golden.py, tests/test_oracle_cpu.py and bench.py's
+reference arm).  In the build container the modules come from /root/reference; on the GPU box from the git-ignored
+copy oracle/_ref that oracle/build_ref.py made (it ships with the gpurun snapshot).
 
 Accommodations:
   1. `robosuite.utils.transform_utils` is stubbed -- imported at models/losses.py:4 but used only in
@@ -17,7 +18,16 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("PE_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """The live tree in the build container (/root/reference or $PE_REFERENCE_ROOT), else the git-ignored copy that
+    oracle/build_ref.py ships to the GPU box (oracle/_ref)."""
+    live = os.environ.get("PE_REFERENCE_ROOT", "/root/reference")
+    if os.path.isdir(os.path.join(live, "models")):
+        return live
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():

@@ -215,6 +215,7 @@ class TrunkEngine:
         stats = self._bn_views(i)[4]
         L.pe_conv2d_fwd(P(x.t), P(self.w_tck[i]), P(y.t), x.B, x.H, x.W, ci, co, r, s, stride, pad, None, None, None,
                         0, 0, P(stats), st)
+        native.account("pe_conv2d_fwd", 4 * (x.P * ci + y.P * co + conv.weight.numel()))
         if tape is not None:
             tape.append(("conv", i, x, y))
         return y
@@ -238,6 +239,8 @@ class TrunkEngine:
                             P(residual.t) if residual is not None else None, P(out.t), P(maskbits), y.P, y.C,
                             bn.momentum if bn.momentum is not None else BN_MOMENTUM, bn.eps, int(relu),
                             self.round_tf32, st)
+        native.account("pe_bn_train_apply", 4 * y.t.numel() * (2 + (residual is not None)) +
+                       (4 * maskbits.numel() if maskbits is not None else 0))
         if tape is not None:
             tape.append(("bn", i, y, out, relu, residual, maskbits))
         return out
@@ -447,6 +450,10 @@ class TrunkEngine:
                 L.pe_bn_bwd_apply(P(d1), P(d2), P(mask_src), P(y.t), P(mean), P(invstd), P(bn.weight), P(sc), P(sh),
                                   P(mb), P(sums), P(dy), P(dres), 0, P(grad_of(bn.weight)), P(grad_of(bn.bias)), 0,
                                   y.P, y.C, relu_k, rt, st)
+                E = 4 * y.t.numel()
+                reads = E * (2 + (d2 is not None) + (mask_src is not None)) + (4 * mb.numel() if mb is not None else 0)
+                native.account("pe_bn_bwd_reduce", reads)
+                native.account("pe_bn_bwd_apply", reads + E * (1 + (dres is not None)))
                 slots.add(y, dy)
                 if residual is not None:
                     if maskbits is not None:
@@ -473,6 +480,10 @@ class TrunkEngine:
                     (res, res_mask), = slots.pop(x)
                 L.pe_conv2d_dgrad(P(dy), P(self.w_tkc[i]), P(dx), x.B, x.H, x.W, ci, co, r, s, stride, pad, P(res),
                                   P(res_mask), st)
+                native.account("pe_conv2d_wgrad", 4 * (x.P * ci + y.P * co + conv.weight.numel()))
+                native.account("pe_conv2d_dgrad", 4 * (x.P * ci * (2 if res is not None else 1) + y.P * co +
+                                                       conv.weight.numel()) +
+                               (4 * res_mask.numel() if res_mask is not None else 0))
                 slots.add(x, dx)
                 if i in done_after_conv:
                     on_ready(done_after_conv[i])

@@ -123,7 +123,7 @@ class _Lib:
 
 
 _lib = None
-_STATE = {"calls": 0, "timing": False, "events": []}
+_STATE = {"calls": 0, "timing": False, "events": [], "bytes": {}}
 
 
 def call_count():
@@ -136,6 +136,18 @@ def enable_timing(on):
     _STATE["timing"] = bool(on)
     if on:
         _STATE["events"] = []
+        _STATE["bytes"] = {}
+
+
+def account(name, nbytes):
+    """Algorithmic bytes (operands read once + results written once, from the call's own shapes) of one C-ABI call;
+    recorded only while enable_timing is on.  bench.py divides them by the live CUDA-event time of the same calls."""
+    if _STATE["timing"]:
+        _STATE["bytes"][name] = _STATE["bytes"].get(name, 0) + int(nbytes)
+
+
+def bytes_summary():
+    return dict(_STATE["bytes"])
 
 
 def timing_summary():

@@ -147,6 +147,13 @@ class FusedTrainer:
             self._flatten()
         model, core = self.model, self.core
         state = None
+        if img.dtype == torch.uint8:
+            # raw renderer frames (..., 256, 256, 3) uint8 HWC: CenterCrop(224) + /255 + Normalize on the device
+            # (util/data_utils.py:48-54) -- the frames cross PCIe at a third of the bytes of preprocessed fp32 tensors
+            if getattr(self, "_pre", None) is None:
+                from .preprocess import FramePreprocessor
+                self._pre = FramePreprocessor(crop=224)
+            img = self._pre(img)
         inputs = (img, self_measurement) if depth is None else (img, self_measurement, depth)
         outs, saved, _ = core.forward(inputs, True, True, state)
         if not isinstance(targets, (tuple, list)):
@@ -193,6 +200,7 @@ class FusedTrainer:
         self.t += 1
         n = self.p_flat.numel()
         if self.optimizer == "adam":
+            native.account("pe_adam_step", 28 * n)          # read p, g, m, v; write p, m, v
             L.pe_adam_step(P(self.p_flat), P(self.g_flat), P(self.m_flat), P(self.v_flat), n, self.lr, self.betas[0],
                            self.betas[1], self.eps, self.wd, self.t, 1.0, st)
         else:

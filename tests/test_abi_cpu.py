@@ -59,7 +59,8 @@ def test_product_never_imports_oracle():
 
 
 def test_bench_gpu_arm_is_independent_of_the_oracle():
-    """bench.py may execute oracle/ only in its cpu_baseline / --impl reference leg (cpu_reference_rate); the GPU
+    """bench.py may execute oracle/ only in its cpu_baseline / --impl reference leg (cpu_reference_rate and its
+    model factory _reference_model); the GPU
     arm builds its models and synthetic data itself and never touches tests/ helpers either."""
     import ast
     path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py")
@@ -73,7 +74,8 @@ def test_bench_gpu_arm_is_independent_of_the_oracle():
             elif isinstance(node, ast.Import):
                 names = [a.name for a in node.names]
             for name in names:
-                if (name.split(".")[0] in ("oracle", "model_checks", "kernel_checks")) and fn.name != "cpu_reference_rate":
+                if (name.split(".")[0] in ("oracle", "model_checks", "kernel_checks")) and \
+                        fn.name not in ("cpu_reference_rate", "_reference_model"):
                     offenders.append((fn.name, name))
     top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
     for node in top:
@@ -99,7 +101,12 @@ def test_bench_reference_arm_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    # "reference" = the reference's own nn.Modules (from /root/reference here, oracle/_ref on the GPU box);
+    # "port" only where neither exists
+    from oracle import ref_shim
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_shim.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["config"]["cpu_batch_frames"] == 8 and d["warmup"] == 1
     assert abs(d["cpu_baseline"]["value"] - d["value"]) <= 1e-9 * d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["unit"] == d["unit"] and abs(d["e2e"]["value"] - d["value"]) <= 1e-9 * d["value"]
