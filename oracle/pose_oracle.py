@@ -17,6 +17,7 @@ against torch 2.11.0 / torchvision 0.26.0 as installed.
 
 Each function cites the reference lines it follows (paths relative to /root/reference).
 """
+import contextlib
 import math
 
 import torch
@@ -24,6 +25,161 @@ import torch.nn.functional as F
 
 # torchvision resnet50: (planes, blocks, stride) per stage -- torchvision/models/resnet.py:266-282
 RESNET50_STAGES = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))
+
+
+# --------------------------------------------------------------------------------------------
+# operand precision
+# --------------------------------------------------------------------------------------------
+# The CUDA path computes every dense contraction with TF32 OPERANDS (10-bit mantissa) and fp32 accumulation, as
+# north_star's "fp32/TF32 tolerance" allows.  Against the plain fp32 restatement below that costs ~4e-3 on the
+# outputs of a 50-layer network -- and far more on its gradients, because a ReLU network's gradient is
+# discontinuous: an activation whose pre-activation moves across zero flips its mask, so a forward perturbation of
+# relative size e changes a fraction ~e of the masks and the gradient by ~sqrt(e) (fp32 vs fp64 on the CPU already
+# differ by 4e-3 in every trunk gradient; measured).  To check the backward LOGIC of the
+# full-depth network to a tight tolerance the oracle can therefore be switched to the same operand precision:
+# inside `tf32_operands()` every conv / linear operand is rounded to TF32 exactly where the CUDA path rounds it
+# (cvt.rna.tf32: weights when they are packed, activations when they are produced, output gradients when BatchNorm /
+# ReLU backward hands them to dgrad and wgrad), everything else (accumulation, BatchNorm, LSTM cell, loss) stays in the
+# working precision -- run it in float64 and what remains between the two is accumulation order.
+_TF32 = [False]
+_FUSED_HEAD_ROWS = 8          # rollout-sized inference (<= 8 rows, no gradients) runs its head in plain fp32 FMA
+
+
+@contextlib.contextmanager
+def tf32_operands(on=True):
+    prev = _TF32[0]
+    _TF32[0] = bool(on)
+    try:
+        yield
+    finally:
+        _TF32[0] = prev
+
+
+def round_tf32(x):
+    """cvt.rna.tf32.f32: round the 24-bit significand to 11 bits, nearest, ties away from zero."""
+    x32 = x.detach().to(torch.float32).contiguous()
+    bits = x32.view(torch.int32)
+    mag = bits & 0x7FFFFFFF
+    rounded = (mag + 0x1000) & 0x7FFFE000
+    out = (rounded | (bits & -0x80000000)).view(torch.float32)
+    out = torch.where(torch.isfinite(x32), out, x32)
+    return out.to(x.dtype)
+
+
+class _RoundSTE(torch.autograd.Function):
+    """Value rounded to TF32; gradient passed through (the CUDA path does not differentiate its roundings)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return round_tf32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _rnd(x):
+    return _RoundSTE.apply(x) if _TF32[0] else x
+
+
+class _ConvTF32(torch.autograd.Function):
+    """conv2d whose three GEMMs see TF32 operands: forward x (already rounded by its producer) * round(w);
+    backward with r = round(dy): dx = r (*) round(w), dw = x (*) r."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding):
+        wr = round_tf32(w)
+        ctx.save_for_backward(x, wr)
+        ctx.cfg = (stride, padding, w.shape)
+        return F.conv2d(x, wr, stride=stride, padding=padding)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wr = ctx.saved_tensors
+        stride, padding, wshape = ctx.cfg
+        r = round_tf32(g)
+        dx = torch.nn.grad.conv2d_input(x.shape, wr, r, stride=stride, padding=padding) if ctx.needs_input_grad[0] else None
+        dw = torch.nn.grad.conv2d_weight(x, wshape, r, stride=stride, padding=padding)
+        return dx, dw, None, None
+
+
+class _LinearTF32(torch.autograd.Function):
+    """linear with TF32 operands: y = x round(w)^T + b; backward with r = round(dy): dx = r round(w), dw = r^T x,
+    db = sum r (the CUDA path takes the bias gradient from the same rounded buffer)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        wr = round_tf32(w)
+        ctx.save_for_backward(x, wr)
+        ctx.has_bias = b is not None
+        y = x.matmul(wr.t())
+        return y + b if b is not None else y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wr = ctx.saved_tensors
+        r = round_tf32(g)
+        dx = r.matmul(wr) if ctx.needs_input_grad[0] else None
+        dw = r.reshape(-1, r.shape[-1]).t().matmul(x.reshape(-1, x.shape[-1]))
+        db = r.reshape(-1, r.shape[-1]).sum(0) if ctx.has_bias else None
+        return dx, dw, db
+
+
+# Teacher forcing of the convolution outputs.  Even at identical operand precision two implementations of a 50-layer
+# ReLU network disagree on ~1e-5 of their activations' signs (accumulation order), and every flipped ReLU mask is an
+# O(1) change of that element's gradient: fp32 vs fp64 accumulation on the CPU, same TF32 operands, already differ by
+# 0.09 (median) in the trunk gradients.  A tight check of the backward pass therefore has to run on the SAME masks:
+# inside `forced_conv_outputs(ys)` every convolution still computes its own output (its relative error against the
+# supplied tensor is recorded -- a per-layer forward check), but the VALUE that flows on is the supplied one while
+# autograd still differentiates the oracle's own op.  With `ys` = the raw conv outputs the CUDA path saved for its
+# backward pass, BatchNorm statistics, ReLU masks and x-hat are then common to both sides and the remaining gradient
+# difference is arithmetic, not chaos.
+_FORCE = [None]
+FORCE_ERRORS = []
+
+
+@contextlib.contextmanager
+def forced_conv_outputs(ys):
+    _FORCE[0] = iter(ys)
+    del FORCE_ERRORS[:]
+    try:
+        yield FORCE_ERRORS
+    finally:
+        _FORCE[0] = None
+
+
+RECORD = [None]          # when a list: every convolution appends its output (self-test of the forcing machinery)
+
+
+def _force(y):
+    if RECORD[0] is not None:
+        RECORD[0].append(y.detach().clone())
+    if _FORCE[0] is None:
+        return y
+    ext = next(_FORCE[0]).to(y.dtype)
+    assert ext.shape == y.shape, (ext.shape, y.shape)
+    FORCE_ERRORS.append(float((y.detach() - ext).abs().max() / ext.abs().max().clamp_min(1e-30)))
+    return y + (ext - y).detach()
+
+
+def _head_ops(fused):
+    """(linear, round) used by a fusion head.  `fused`: the CUDA path runs rollout-sized inference heads (<= 8 rows,
+    no gradients) as ONE fp32-FMA kernel on the un-rounded checkpoint weights (pe_fused_head) -- plain fp32 here too."""
+    if _TF32[0] and not fused:
+        return _linear, _rnd
+    return F.linear, (lambda t: t)
+
+
+def _conv(x, w, stride=1, padding=0):
+    if _TF32[0]:
+        return _force(_ConvTF32.apply(x, w, stride, padding))
+    return _force(F.conv2d(x, w, stride=stride, padding=padding))
+
+
+def _linear(x, w, b=None):
+    if _TF32[0]:
+        return _LinearTF32.apply(x, w, b)
+    return F.linear(x, w, b)
 
 
 # --------------------------------------------------------------------------------------------
@@ -40,16 +196,16 @@ def _bn(x, sd, prefix, training, momentum=0.1, eps=1e-5):
 def _bottleneck(x, sd, prefix, stride, training):
     """torchvision Bottleneck.forward (resnet.py:143-163), stride on conv2 (v1.5)."""
     identity = x
-    out = F.conv2d(x, sd[prefix + "conv1.weight"])
-    out = F.relu(_bn(out, sd, prefix + "bn1.", training))
-    out = F.conv2d(out, sd[prefix + "conv2.weight"], stride=stride, padding=1)
-    out = F.relu(_bn(out, sd, prefix + "bn2.", training))
-    out = F.conv2d(out, sd[prefix + "conv3.weight"])
+    out = _conv(x, sd[prefix + "conv1.weight"])
+    out = _rnd(F.relu(_bn(out, sd, prefix + "bn1.", training)))
+    out = _conv(out, sd[prefix + "conv2.weight"], stride=stride, padding=1)
+    out = _rnd(F.relu(_bn(out, sd, prefix + "bn2.", training)))
+    out = _conv(out, sd[prefix + "conv3.weight"])
     out = _bn(out, sd, prefix + "bn3.", training)
     if prefix + "downsample.0.weight" in sd:
-        identity = F.conv2d(x, sd[prefix + "downsample.0.weight"], stride=stride)
-        identity = _bn(identity, sd, prefix + "downsample.1.", training)
-    return F.relu(out + identity)
+        identity = _conv(x, sd[prefix + "downsample.0.weight"], stride=stride)
+        identity = _rnd(_bn(identity, sd, prefix + "downsample.1.", training))
+    return _rnd(F.relu(out + identity))
 
 
 def resnet50_forward(sd, prefix, img, training):
@@ -58,23 +214,30 @@ def resnet50_forward(sd, prefix, img, training):
 
     The second output is what the reference's bn1 forward hook ends up holding: the hooked tensor
     is overwritten by relu(inplace=True) (models/naive.py:211,282-283)."""
-    x = F.conv2d(img, sd[prefix + "conv1.weight"], stride=2, padding=3)
+    x = _conv(_rnd(img), sd[prefix + "conv1.weight"], stride=2, padding=3)
     x = F.relu(_bn(x, sd, prefix + "bn1.", training))
+    # (TF32-operand mode) training: the fused stem tail never materialises this map -- the max pool and the aux
+    # branch read it un-rounded and round their own outputs; eval: the folded-BN GEMM epilogue rounds it
+    if not training:
+        x = _rnd(x)
     early = x
-    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    x = _rnd(F.max_pool2d(x, kernel_size=3, stride=2, padding=1))
     for li, (_, blocks, stride) in enumerate(RESNET50_STAGES, start=1):
         # block count read from the checkpoint so that shallower Bottleneck stacks (used by the
         # well-conditioned gradient tests) run through the same code; 3/4/6/3 for ResNet-50
         blocks = len({k[len(prefix):].split(".")[1] for k in sd if k.startswith("%slayer%d." % (prefix, li))})
         for b in range(blocks):
             x = _bottleneck(x, sd, "%slayer%d.%d." % (prefix, li, b), stride if b == 0 else 1, training)
-    x = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
-    return F.linear(x, sd[prefix + "fc.weight"], sd[prefix + "fc.bias"]), early
+    x = _rnd(torch.flatten(F.adaptive_avg_pool2d(x, 1), 1))
+    return _rnd(_linear(x, sd[prefix + "fc.weight"], sd[prefix + "fc.bias"])), early
 
 
-def aux_forward(early, w, b):
+def aux_forward(early, w, b, rounded=True):
     """Conv2d(64,1,1) + MaxPool2d(2) + Flatten (models/naive.py:225-229, time_sensitive.py:379-383)."""
-    return torch.flatten(F.max_pool2d(F.conv2d(early, w, b), 2), 1)
+    # fp32 FMA in the CUDA path as well (a 64-term dot product per pixel, no tensor cores); the result is rounded
+    # because it becomes a GEMM operand of the head (with use_depth the product with the depth features is)
+    a = torch.flatten(F.max_pool2d(F.conv2d(early, w, b), 2), 1)
+    return _rnd(a) if rounded else a
 
 
 def depth_forward(depth, weight, bias, n_pool=2):
@@ -86,13 +249,14 @@ def depth_forward(depth, weight, bias, n_pool=2):
     return torch.flatten(F.instance_norm(d, weight=weight, bias=bias, eps=1e-5), 1)
 
 
-def lstm_forward(x, sd, prefix, state=None):
+def lstm_forward(x, sd, prefix, state=None, ops=None):
     """Single-layer nn.LSTM, seq-major input (S, N, F), gates (i, f, g, o)
     (models/time_sensitive.py:126-131,418; torch.nn.LSTM definition)."""
     w_ih, w_hh = sd[prefix + "weight_ih_l0"], sd[prefix + "weight_hh_l0"]
     b_ih, b_hh = sd[prefix + "bias_ih_l0"], sd[prefix + "bias_hh_l0"]
     S, N, _ = x.shape
     H = w_hh.shape[1]
+    lin, rnd = ops if ops is not None else (_linear, _rnd)
     if state is None:
         h = x.new_zeros(N, H)
         c = x.new_zeros(N, H)
@@ -100,10 +264,10 @@ def lstm_forward(x, sd, prefix, state=None):
         h, c = state[0][0], state[1][0]
     outs = []
     for t in range(S):
-        gates = F.linear(x[t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+        gates = lin(x[t], w_ih, b_ih) + lin(h, w_hh, b_hh)
         i, f, g, o = gates.chunk(4, dim=1)
         c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
-        h = torch.sigmoid(o) * torch.tanh(c)
+        h = rnd(torch.sigmoid(o) * torch.tanh(c))
         outs.append(h)
     return torch.stack(outs), (h.unsqueeze(0), c.unsqueeze(0))
 
@@ -115,26 +279,34 @@ def naive_object_forward(sd, img, x0bar, training, n_fc, use_proprio=True, depth
     """NaiveObjectStateEstimator.forward (models/naive.py:298-352); ReLU after EVERY fc incl. the
     last one (quirk Q2, models/naive.py:343-345)."""
     feats, early = resnet50_forward(sd, "feature_net.module.", img, training)
-    aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"])
+    lin, rnd = _head_ops(fused=(not training) and img.shape[0] <= _FUSED_HEAD_ROWS)
+    aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"], rounded=depth is None)
     if depth is not None:      # use_depth: aux features gated by the normalised, pooled depth map (:324-330)
-        aux = aux * depth_forward(depth, sd["depth_nets.0.module.2.weight"], sd["depth_nets.0.module.2.bias"])
+        aux = _rnd(aux * depth_forward(depth, sd["depth_nets.0.module.2.weight"], sd["depth_nets.0.module.2.bias"]))
     out = torch.cat((feats, aux), dim=-1).view(img.shape[0], -1)
     if use_proprio:
-        out = torch.cat((out, x0bar), dim=-1)
+        out = torch.cat((out, rnd(x0bar)), dim=-1)
     for i in range(n_fc):
-        out = F.relu(F.linear(out, sd["fc%d.module.weight" % i], sd["fc%d.module.bias" % i]))
+        out = F.relu(lin(out, sd["fc%d.module.weight" % i], sd["fc%d.module.bias" % i]))
+        if i < n_fc - 1:
+            out = rnd(out)
     return out
 
 
 def naive_eef_forward(sd, img, x0bar, training, n_pre, n_post):
     """NaiveEndEffectorStateEstimator.forward (models/naive.py:68-112): no aux branch."""
     feats, _ = resnet50_forward(sd, "feature_net.", img, training)
+    lin, rnd = _head_ops(fused=(not training) and img.shape[0] <= _FUSED_HEAD_ROWS)
     pre = feats
     for i in range(n_pre):
-        pre = F.relu(F.linear(pre, sd["pre_fc%d.weight" % i], sd["pre_fc%d.bias" % i]))
-    post = torch.cat([feats, pre - x0bar], dim=1)
+        pre = F.relu(lin(pre, sd["pre_fc%d.weight" % i], sd["pre_fc%d.bias" % i]))
+        if i < n_pre - 1:
+            pre = rnd(pre)
+    post = torch.cat([feats, rnd(pre - x0bar)], dim=1)
     for i in range(n_post):
-        post = F.relu(F.linear(post, sd["post_fc%d.weight" % i], sd["post_fc%d.bias" % i]))
+        post = F.relu(lin(post, sd["post_fc%d.weight" % i], sd["post_fc%d.bias" % i]))
+        if i < n_post - 1:
+            post = rnd(post)
     return pre, post
 
 
@@ -144,16 +316,18 @@ def tdo_forward(sd, img, x0bar, training, state=None, use_proprio=True, depth=No
     `state` = (h, c) each (1, N, H) for rollout mode; returns (out, new_state)."""
     S, N = img.shape[0], img.shape[1]
     feats, early = resnet50_forward(sd, "feature_net.module.", img.reshape(S * N, *img.shape[2:]), training)
-    aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"])
+    ops = _head_ops(fused=(not training) and S == 1 and N <= _FUSED_HEAD_ROWS)
+    lin, rnd = ops
+    aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"], rounded=depth is None)
     if depth is not None:
-        aux = aux * depth_forward(depth.reshape(S * N, *depth.shape[2:]), sd["depth_nets.0.module.2.weight"],
-                                  sd["depth_nets.0.module.2.bias"])
+        aux = _rnd(aux * depth_forward(depth.reshape(S * N, *depth.shape[2:]), sd["depth_nets.0.module.2.weight"],
+                                       sd["depth_nets.0.module.2.bias"]))
     f = torch.cat((feats, aux), dim=-1).view(S, N, -1)
     if use_proprio:
-        f = torch.cat((f, x0bar), dim=-1)
-    h, new_state = lstm_forward(f, sd, "rnn.module.", state)
-    out = F.linear(F.linear(h, sd["fc.module.0.weight"], sd["fc.module.0.bias"]),
-                   sd["fc.module.1.weight"], sd["fc.module.1.bias"])
+        f = torch.cat((f, rnd(x0bar)), dim=-1)
+    h, new_state = lstm_forward(f, sd, "rnn.module.", state, ops)
+    out = lin(rnd(lin(h, sd["fc.module.0.weight"], sd["fc.module.0.bias"])),
+              sd["fc.module.1.weight"], sd["fc.module.1.bias"])
     return out, new_state
 
 
@@ -167,10 +341,10 @@ def tdo_v2_forward(sd, img, x0bar, training, state=None):
     aux = aux_forward(early, sd["aux_nets.0.module.0.weight"], sd["aux_nets.0.module.0.bias"])
     f = torch.cat((feats, aux), dim=-1).view(S, N, -1)
     h_img, st_img = lstm_forward(f, sd, "img_rnn.module.", None if state is None else state[0])
-    h_pro, st_pro = lstm_forward(x0bar, sd, "proprio_rnn.module.", None if state is None else state[1])
+    h_pro, st_pro = lstm_forward(_rnd(x0bar), sd, "proprio_rnn.module.", None if state is None else state[1])
     h = torch.cat((h_img, h_pro), dim=-1)
-    out = F.linear(F.linear(h, sd["fc.module.0.weight"], sd["fc.module.0.bias"]),
-                   sd["fc.module.1.weight"], sd["fc.module.1.bias"])
+    out = _linear(_rnd(_linear(h, sd["fc.module.0.weight"], sd["fc.module.0.bias"])),
+                  sd["fc.module.1.weight"], sd["fc.module.1.bias"])
     return out, (st_img, st_pro)
 
 
@@ -181,12 +355,14 @@ def td_forward(sd, img, x0bar, training, aux_w, aux_b, state=None):
     S, N = img.shape[0], img.shape[1]
     feats, early = resnet50_forward(sd, "feature_net.", img.reshape(S * N, *img.shape[2:]), training)
     aux = aux_forward(early, aux_w, aux_b)
+    ops = _head_ops(fused=(not training) and S == 1 and N <= _FUSED_HEAD_ROWS)
+    lin, rnd = ops
     f = torch.cat((feats, aux), dim=-1).view(S, N, -1)
-    h_pre, st_pre = lstm_forward(f, sd, "pre_measurement_rnn.", None if state is None else state[0])
-    pre_out = F.linear(h_pre, sd["pre_measurement_fc.weight"], sd["pre_measurement_fc.bias"])
-    post_in = torch.cat([f, pre_out - x0bar], dim=-1)
-    h_post, st_post = lstm_forward(post_in, sd, "post_measurement_rnn.", None if state is None else state[1])
-    post_out = F.linear(h_post, sd["post_measurement_fc.weight"], sd["post_measurement_fc.bias"])
+    h_pre, st_pre = lstm_forward(f, sd, "pre_measurement_rnn.", None if state is None else state[0], ops)
+    pre_out = lin(h_pre, sd["pre_measurement_fc.weight"], sd["pre_measurement_fc.bias"])
+    post_in = torch.cat([f, rnd(pre_out - x0bar)], dim=-1)
+    h_post, st_post = lstm_forward(post_in, sd, "post_measurement_rnn.", None if state is None else state[1], ops)
+    post_out = lin(h_post, sd["post_measurement_fc.weight"], sd["post_measurement_fc.bias"])
     return pre_out, post_out, (st_pre, st_post)
 
 

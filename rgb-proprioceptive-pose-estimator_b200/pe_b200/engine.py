@@ -17,6 +17,9 @@ BN_MOMENTUM = 0.1
 # training forward: bn1 + ReLU + max pool + aux branch as one kernel (pe_stem_post_train); False = the three separate
 # kernels (kept for the kernel tests and as the reference the fused one is checked against)
 FUSED_STEM_TAIL = [True]
+# test hook: when set to a list, every training-mode convolution appends its raw output (an Act, execution order:
+# stem, then conv1 / conv2 / conv3 / downsample of each block) -- tests/model_checks.py feeds them to the oracle
+CAPTURE_CONV_OUTPUTS = [None]
 
 
 def _dev_check(t):
@@ -216,6 +219,8 @@ class TrunkEngine:
         L.pe_conv2d_fwd(P(x.t), P(self.w_tck[i]), P(y.t), x.B, x.H, x.W, ci, co, r, s, stride, pad, None, None, None,
                         0, 0, P(stats), st)
         native.account("pe_conv2d_fwd", 4 * (x.P * ci + y.P * co + conv.weight.numel()))
+        if CAPTURE_CONV_OUTPUTS[0] is not None:
+            CAPTURE_CONV_OUTPUTS[0].append(y)
         if tape is not None:
             tape.append(("conv", i, x, y))
         return y
@@ -295,6 +300,8 @@ class TrunkEngine:
             self.stats.zero_()
             L.pe_linear_fwd(P(col), 160, P(self.w_tck[0]), 160, None, None, P(y0.t), 64, y0.P, 64, 160, 0, 0, 0,
                             P(self._bn_views(0)[4]), st)
+            if CAPTURE_CONV_OUTPUTS[0] is not None:
+                CAPTURE_CONV_OUTPUTS[0].append(y0)
             if tape is not None:
                 tape.append(("stem", col, y0))
             fused_tail = FUSED_STEM_TAIL[0] and Ho % 2 == 0 and Wo % 2 == 0

@@ -18,6 +18,56 @@ from pe_b200.ddp import shard_range  # noqa: E402
 from pe_b200.trainer import FusedTrainer  # noqa: E402
 
 
+def oracle_check(kind, trainer, model, img, x0, tgt, lk, rank, dev):
+    """SURVEY 8e's multi-GPU oracle: the reference algorithm run ONCE PER SHARD with the gradients summed (BatchNorm
+    statistics stay per GPU, the loss is a sum over samples).  Every rank runs the CPU oracle on its own shard -- at the
+    CUDA path's operand precision and teacher-forced with the conv outputs of this very step, like
+    model_checks.check_forced -- the per-shard reference gradients are summed across ranks, and the result is compared
+    per parameter with the gradient arena the bucketed NCCL all-reduce left behind.  Step 0 reduces in one call,
+    step 1 in backward-ordered buckets overlapped with the backward pass."""
+    from pe_b200 import engine
+    good = True
+    for step in range(2):
+        orc = mc.oracle_for(kind, model)
+        orc.sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in orc.sd.items()}
+        orc.extra = {k: v.double() for k, v in orc.extra.items()}
+        engine.CAPTURE_CONV_OUTPUTS[0] = []
+        try:
+            trainer.forward_backward(img, x0, tgt)
+            acts = engine.CAPTURE_CONV_OUTPUTS[0]
+        finally:
+            engine.CAPTURE_CONV_OUTPUTS[0] = None
+        ys = [t.t.view(t.B, t.H, t.W, t.C).permute(0, 3, 1, 2).double().cpu() for t in acts]
+        del acts
+        with po.tf32_operands(True), po.forced_conv_outputs(ys):
+            _, _, grads_ref = mc.oracle_loss_and_grads(orc, kind, img.double().cpu(), x0.double().cpu(),
+                                                       tgt.double().cpu(), lk)
+        ref = torch.zeros(trainer.g_flat.numel(), device=dev, dtype=torch.float64)
+        named = dict(model.named_parameters())
+        spans = {}
+        for k, g in grads_ref.items():
+            o, n = trainer.param_offsets[id(named[k])]
+            spans[k] = (o, n)
+            if g is not None:
+                ref[o:o + n] = g.reshape(-1).to(dev)
+        dist.all_reduce(ref)                                  # sum of the per-shard oracle gradients
+        errs = []
+        for k, (o, n) in spans.items():
+            if grads_ref[k] is None:
+                continue
+            r = ref[o:o + n]
+            errs.append((float((trainer.g_flat[o:o + n].double() - r).norm() / r.norm().clamp_min(1e-30)), k))
+        errs.sort(reverse=True)
+        buckets = trainer.reducer.launched if trainer.reducer is not None else 0
+        if rank == 0:
+            print("oracle step %d: worst per-parameter gradient error vs the summed per-shard oracle %.3e (%s), median "
+                  "%.3e, %d all-reduce launches" % (step, errs[0][0], errs[0][1], errs[len(errs) // 2][0], buckets),
+                  flush=True)
+        good = good and errs[0][0] <= 1e-2
+        trainer.apply_update()
+    return good
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -41,6 +91,8 @@ def main():
     tb = FusedTrainer(b, lr=1e-4, **lk)
     ok = True
     from pe_b200.trainer import invalidate_core
+    if "--oracle" in sys.argv:
+        ok = oracle_check(kind, ta, a, img, x0, tgt, lk, rank, dev)
     for step in range(3):                       # step 0: single all-reduce; steps 1-2: overlapped buckets
         if step > 0:                            # same parameters everywhere: only the reduction is under test
             for t in (tb, tc):

@@ -31,11 +31,13 @@ CONFIGS = {
 SHALLOW = [False]   # when set, Bottleneck stacks are [1,1,1,1] instead of ResNet-50's [3,4,6,3]
 
 
-def build_model(kind, seed=0):
+def build_model(kind, seed=0, latent=None):
     import models.naive as mn
     import models.time_sensitive as mt
     import util.model_utils as mu
-    cfg = CONFIGS[kind]
+    cfg = dict(CONFIGS[kind])
+    if latent is not None:
+        cfg["latent"] = latent
     mu._RESNET_LAYERS[50] = [1, 1, 1, 1] if SHALLOW[0] else [3, 4, 6, 3]
     torch.manual_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -79,11 +81,11 @@ def relnorm(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def check_train_step(kind, n=2, s=2, seed=1, verbose=False):
+def check_train_step(kind, n=2, s=2, seed=1, verbose=False, latent=None):
     """forward (train mode) + loss + backward vs oracle.  Returns rows (name, err, tol)."""
     from models.losses import PoseDistanceLoss
     cfg = CONFIGS[kind]
-    model = build_model(kind)
+    model = build_model(kind, latent=latent)
     orc = oracle_for(kind, model)
     if kind in ("no", "n"):
         img, x0, tgt = po.synthetic_batch(kind, n, seed=seed)
@@ -169,6 +171,101 @@ def check_train_step(kind, n=2, s=2, seed=1, verbose=False):
     return rows
 
 
+def oracle_loss_and_grads(orc, kind, img, x0, tgt, lk):
+    """(outputs tuple, loss, {name: grad}) of the training objective of util/learn_utils.py:160-172: the object-pose
+    models train on loss(out, obj), the two-headed ones on loss(pre, x0) + loss(post, x1)."""
+    if kind in ("no", "tdo", "tdo_v2"):
+        outs, loss, grads = orc.loss_and_grads(img, x0, tgt, lk)
+        return (outs,), loss, grads
+    for k in orc.param_names:
+        orc.sd[k].requires_grad_(True)
+        orc.sd[k].grad = None
+    pre, post = orc.forward(img, x0, training=True)
+    loss = po.pose_loss(pre, x0, **lk) + po.pose_loss(post, tgt, **lk)
+    loss.backward()
+    grads = {k: orc.sd[k].grad for k in orc.param_names}
+    for k in orc.param_names:
+        orc.sd[k].requires_grad_(False)
+    return (pre.detach(), post.detach()), loss.detach(), grads
+
+
+def check_forced(kind, n=2, s=2, seed=1, verbose=False):
+    """Full-depth training step against the oracle at the SAME operand precision (TF32 operands, float64 accumulation)
+    and on the SAME ReLU masks: the raw convolution outputs the CUDA path saved for its backward pass are teacher-forced
+    into the oracle's forward (oracle/pose_oracle.py: tf32_operands, forced_conv_outputs).  Every convolution is still
+    computed by the oracle and compared (per-layer forward rows); BatchNorm, ReLU, pooling, heads, loss and the whole
+    backward pass are the oracle's own autograd.  Returns rows (name, err, tol)."""
+    from models.losses import PoseDistanceLoss
+    from pe_b200 import engine
+    cfg = CONFIGS[kind]
+    lk = cfg["loss"]
+    model = build_model(kind)
+    with torch.no_grad():      # finite loss for the models that ReLU their output (quirk Q2/Q7)
+        if kind == "no":
+            getattr(model, "fc%d" % (model.n_fc - 1)).module.bias.fill_(0.5)
+        elif kind == "n":
+            getattr(model, "pre_fc%d" % (model.n_pre_hidden - 1)).bias.fill_(0.5)
+            getattr(model, "post_fc%d" % (model.n_post_hidden - 1)).bias.fill_(0.5)
+    orc = oracle_for(kind, model)
+    orc.sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in orc.sd.items()}
+    orc.extra = {k: v.double() for k, v in orc.extra.items()}
+    if kind in ("no", "n"):
+        img, x0, tgt = po.synthetic_batch(kind, n, seed=seed)
+    else:
+        img, x0, tgt = po.synthetic_batch(kind, n, s=s, seed=seed)
+
+    model.cuda().train()
+    crit = PoseDistanceLoss(distance_metric=lk["distance_metric"], alpha=lk["alpha"], mode=lk["mode"])
+    if kind in ("td", "tdo", "tdo_v2"):
+        model.reset_initial_state(n)
+    engine.CAPTURE_CONV_OUTPUTS[0] = []
+    try:
+        out = model(img.cuda(), None, x0.cuda())
+        acts = engine.CAPTURE_CONV_OUTPUTS[0]
+    finally:
+        engine.CAPTURE_CONV_OUTPUTS[0] = None
+    outs = out if isinstance(out, tuple) else (out,)
+    loss = crit(outs[0], tgt.cuda()) if kind in ("no", "tdo", "tdo_v2") else \
+        crit(outs[0], x0.cuda()) + crit(outs[1], tgt.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    ys = [a.t.view(a.B, a.H, a.W, a.C).permute(0, 3, 1, 2).double().cpu() for a in acts]
+    del acts
+
+    t0 = time.time()
+    with po.tf32_operands(True), po.forced_conv_outputs(ys) as ferr:
+        outs_ref, loss_ref, grads_ref = oracle_loss_and_grads(orc, kind, img.double(), x0.double(), tgt.double(), lk)
+        ferr = list(ferr)
+    t_cpu = time.time() - t0
+    tag = "forced %s n%d" % (kind, n) + ("" if kind in ("no", "n") else " s%d" % s)
+    rows = [("%s conv forward, worst of %d layers" % (tag, len(ferr)), max(ferr), 5e-4)]
+    for i, (a, b) in enumerate(zip(outs, outs_ref)):
+        rows.append(("%s out%d" % (tag, i), rel(a, b), 1e-3))
+    rows.append(("%s loss" % tag, rel(loss.reshape(1), loss_ref.reshape(1)), 1e-3))
+    named = dict(model.named_parameters())
+    errs = []
+    for k in orc.param_names:
+        g_ref, g = grads_ref[k], named[k].grad
+        if g_ref is None or g is None:
+            rows.append(("%s grad %s is None" % (tag, k), 0.0 if (g is None) == (g_ref is None) else 1.0, 0.0))
+            continue
+        errs.append((relnorm(g, g_ref), k))
+    errs.sort(reverse=True)
+    for e, k in (errs if verbose else errs[:5]):
+        rows.append(("%s grad %s" % (tag, k), e, 1e-2))
+    rows.append(("%s worst grad over %d parameters" % (tag, len(errs)), errs[0][0], 1e-2))
+    rows.append(("%s median grad" % tag, errs[len(errs) // 2][0], 1e-2))
+    sd = model.state_dict()
+    rows.append(("%s running_mean (max over BNs)" % tag,
+                 max(rel(sd[k], orc.sd[k]) for k in sd if k.endswith("running_mean")), 1e-3))
+    rows.append(("%s running_var (max over BNs)" % tag,
+                 max(rel(sd[k], orc.sd[k]) for k in sd if k.endswith("running_var")), 1e-3))
+    rows.append(("%s num_batches_tracked" % tag,
+                 0.0 if all(int(sd[k]) == int(orc.sd[k]) for k in sd if k.endswith("num_batches_tracked")) else 1.0, 0.0))
+    rows.append(("%s [oracle cpu seconds]" % tag, t_cpu, float("inf")))
+    return rows
+
+
 def check_rollout(kind="tdo", steps=3):
     """Batch-1 streaming inference with carried LSTM state vs oracle."""
     model = build_model(kind)
@@ -232,6 +329,19 @@ def main(argv):
         for name, err, tol in calibrate(argv[0] if argv else "no", n=n):
             print("%-70s %.3e" % (name, err), flush=True)
         return 0
+    if "--forced" in argv:
+        argv = [a for a in argv if a != "--forced"]
+        nb = 2
+        for a in list(argv):
+            if a.startswith("n="):
+                nb = int(a[2:]); argv.remove(a)
+        nfail = 0
+        for kind in [a for a in argv if not a.startswith("-")] or ["no", "tdo", "td", "n", "tdo_v2"]:
+            for name, err, tol in check_forced(kind, n=nb, verbose=("-v" in argv)):
+                ok = err <= tol
+                nfail += (not ok)
+                print("%-4s %-72s err %.3e tol %.1e" % ("ok" if ok else "FAIL", name, err, tol), flush=True)
+        return nfail
     nb = 2
     if "--shallow" in argv:
         SHALLOW[0] = True

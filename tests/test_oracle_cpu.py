@@ -138,3 +138,50 @@ def test_oracle_depth_branch_vs_live_reference(kind):
         want = m(img, depth, x0)
     got = orc.forward(img, x0, training=True, depth=depth)
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_tf32_rounding_matches_cvt_rna():
+    """round_tf32 = cvt.rna.tf32.f32: 10 explicit mantissa bits, round to nearest, ties away from zero."""
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -11 - 2 ** -20, 1.0 + 2 ** -10, -1.0 - 2 ** -11, 3.14159, 0.0])
+    want = torch.tensor([1.0, 1.0 + 2 ** -10, 1.0, 1.0 + 2 ** -10, -1.0 - 2 ** -10, 3.140625, 0.0])
+    assert torch.equal(po.round_tf32(x), want)
+    assert torch.equal(po.round_tf32(x.double()), want.double())
+
+
+def test_teacher_forcing_puts_two_precisions_on_the_same_masks():
+    """The machinery the GPU gradient tests rely on, exercised between two CPU realisations of the oracle (float32
+    and float64 accumulation, both with TF32 operands) on the 4-block trunk: un-forced, their trunk gradients differ
+    by several percent (ReLU masks flip); with the float32 run's conv outputs teacher-forced into the float64 run they
+    agree to well under 1e-2, and every convolution's own output still matches to 5e-4."""
+    import model_checks as mc
+    mc.SHALLOW[0] = True
+    try:
+        model = mc.build_model("tdo")
+    finally:
+        mc.SHALLOW[0] = False
+    img, x0, tgt = po.synthetic_batch("tdo", 2, s=2, seed=1)
+    lk = mc.CONFIGS["tdo"]["loss"]
+
+    def run(dt, force=None, record=False):
+        orc = mc.oracle_for("tdo", model)
+        orc.sd = {k: (v.to(dt) if v.dtype.is_floating_point else v) for k, v in orc.sd.items()}
+        po.RECORD[0] = [] if record else None
+        try:
+            with po.tf32_operands(True):
+                if force is not None:
+                    with po.forced_conv_outputs(force) as errs:
+                        _, _, g = orc.loss_and_grads(img.to(dt), x0.to(dt), tgt.to(dt), lk)
+                        assert len(errs) == 17 and max(errs) <= 5e-4, errs
+                else:
+                    _, _, g = orc.loss_and_grads(img.to(dt), x0.to(dt), tgt.to(dt), lk)
+            return g, po.RECORD[0]
+        finally:
+            po.RECORD[0] = None
+
+    g32, rec = run(torch.float32, record=True)
+    g64_forced, _ = run(torch.float64, force=rec)
+    g64_free, _ = run(torch.float64)
+    forced = max(mc.relnorm(g32[k], g64_forced[k]) for k in g32 if g32[k] is not None)
+    free = max(mc.relnorm(g32[k], g64_free[k]) for k in g32 if g32[k] is not None)
+    assert forced <= 5e-3, forced
+    assert free > 3 * forced, (free, forced)
