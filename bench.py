@@ -647,14 +647,15 @@ def run_ours(args):
     if h.rank == 0:
         if h.world == 1 and not args.no_cpu_baseline:
             try:
+                # the reference's own modules in a CPU-ONLY child process (this bench's reference arm): with a GPU
+                # visible the reference's nn.DataParallel wrappers would scatter to it (models/naive.py:224,253,274)
                 n_cpu = 24
-                rate, sec, fr, which = cpu_reference_rate(args.model, args.cpu_batch, args.seq, n_cpu, 2, args.lr)
-                out["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": os.cpu_count(), "kind": which,
-                                       "sample": "%d-frame batches of the same training step (a bounded sample of the "
-                                                 "%d-frame GPU step), 2 warm-up + %d timed steps, median "
-                                                 "(%.2f s/step, ~%.0f s of CPU work)"
-                                                 % (fr, args.batch * (args.seq if args.model in SEQ_KINDS else 1),
-                                                    n_cpu, sec, (n_cpu + 2) * sec)}
+                child = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--model",
+                                        args.model, "--steps", str(n_cpu), "--warmup", "2", "--cpu-batch",
+                                        str(args.cpu_batch), "--lr", str(args.lr)],
+                                       capture_output=True, text=True, timeout=900)
+                line = [l for l in child.stdout.splitlines() if l.startswith("{")][-1]
+                out["cpu_baseline"] = json.loads(line)["cpu_baseline"]
             except Exception as e:  # the GPU numbers stand on their own
                 out["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(out), flush=True)
@@ -692,6 +693,9 @@ def main():
     if args.batch is None:
         args.batch = {"no": 256, "n": 256, "tdo": 32, "td": 64, "tdo_v2": 32}[args.model]
     if args.impl == "reference":
+        # host cores only: hide the GPUs before torch is imported, otherwise the reference's nn.DataParallel wrappers
+        # (models/naive.py:224,253,274) would move the replicas to cuda:0
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""
         if args.model in SEQ_KINDS and args.cpu_batch == 8:
             args.cpu_batch = 1          # episodes: 1 x S frames per step
         return run_reference(args)

@@ -18,6 +18,9 @@ AUX_DIM = 3136
 OUT_LD = 8          # 7-D poses live in 8-float rows so every row stays 16-byte aligned for TMA
 
 
+# test hook: when set to a list, the naive estimators' MLPs append every layer's (post-ReLU) output buffer, in
+# execution order (tests/model_checks.py teacher-forces them into the oracle next to the conv outputs)
+CAPTURE_HEAD_OUTPUTS = [None]
 FUSED_HEAD = [True]       # rollout-sized inference (<= 8 frames, no gradients) goes through pe_fused_head
 FUSED_HEAD_MAX_ROWS = 8
 
@@ -135,6 +138,8 @@ class NaiveObjectCore:
             # ReLU after every layer including the last one (reference quirk, models/naive.py:343-345)
             op.forward(x, ldx, B, y, y.shape[1], relu=True, round_out=1 if i < len(self.fcs) - 1 else 0)
             hs.append(y)
+            if CAPTURE_HEAD_OUTPUTS[0] is not None:
+                CAPTURE_HEAD_OUTPUTS[0].append(y[:, :op.nout])
             x, ldx = y, y.shape[1]
         return (x[:, :7],), (eng, tctx, hs, B, dctx), None
 
@@ -189,6 +194,8 @@ class NaiveEefCore:
             y = torch.zeros(B, OUT_LD if last else op.ld_out, device=dev, dtype=torch.float32)
             op.forward(x, ldx, B, y, y.shape[1], relu=True, round_out=0 if last else 1)
             hs.append(y)
+            if CAPTURE_HEAD_OUTPUTS[0] is not None:
+                CAPTURE_HEAD_OUTPUTS[0].append(y[:, :op.nout])
             x, ldx = y, y.shape[1]
         return hs
 

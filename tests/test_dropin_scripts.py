@@ -47,8 +47,13 @@ def _compare(res, ref, tol_loss, tol_out):
         elif "running_" in k:
             assert abs(ck[k][1] - sq) <= tol_loss * max(sq, 1e-3), (k, ck[k][1], sq)
         else:
-            # two Adam steps at lr 1e-5 barely move the weights; this pins the layout and the magnitude
-            assert abs(ck[k][1] - sq) <= 1e-3 * max(sq, 1e-6), (k, ck[k][1], sq)
+            # two Adam steps at lr 1e-5 move every weight by at most ~2e-5 (Adam's first steps are +-lr whatever the
+            # gradient's size, so elements whose gradient sign differs between the arms end up 4e-5 apart): this pins
+            # the layout and the magnitude, with that much slack per element
+            numel = 1
+            for d in shape:
+                numel *= d
+            assert abs(ck[k][1] - sq) <= 1e-3 * sq + numel * (4e-5) ** 2 + 2 * 4e-5 * (numel * sq) ** 0.5, (k, ck[k][1], sq)
     if ref["rollout"] is not None:
         r, rr = res["rollout"], ref["rollout"]
         assert len(r["model_outputs"]) == len(rr["model_outputs"]) == 30
