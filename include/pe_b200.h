@@ -33,6 +33,9 @@ int pe_version(void);
 void pe_debug_desc_override(int a_lbo, int a_sbo, int b_lbo, int b_sbo);
 /* debug: tap-GEMM pipeline ablations (1 no TMA store, 2 no staging write, 4 no A loads, 8 no B loads); 0 = normal */
 void pe_debug_flags(int flags);
+/* CTA pairs (tcgen05 cta_group::2, 256-row MMAs over two SMs): 0 automatic (wide tiles of large launches), 1 never,
+ * 2 whenever the launch allows it */
+void pe_debug_cta_group(int mode);
 /* debug: force the smem split of the tap-GEMM (ring stages x 32 KB + nout x 16 KB <= 223 KB); 0 = default */
 void pe_debug_pipeline(int stages, int nout);
 /* debug: cap the tile width (128 or 256 columns) */

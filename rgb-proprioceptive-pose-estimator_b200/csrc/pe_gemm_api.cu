@@ -180,10 +180,22 @@ static int pick_bn(int n_total, long long m_tiles = 1 << 20) {
     return bn;
 }
 
+static int g_dbg_cta_group = 0;       // 0: automatic, 1: never pair CTAs, 2: pair whenever the launch allows it
+// CTA pairs (tcgen05 cta_group::2, M = 256): per MMA a lone CTA reads 128 A rows + bn B rows from shared memory and TMA
+// writes as many -- at bn = 256 that is 24 KB per 128-cycle instruction, 1.5x what the shared-memory port moves, which
+// is where the measured 185 cycles per instruction come from.  In a pair each CTA holds its own A box and HALF of the
+// weight tile: 16 KB per instruction, back under the port's rate, and half the L2 -> SM weight traffic.  Used for
+// the wide tiles when every TPC still gets at least one pair of tiles.
+static bool want_pair(const TapParams& p, long long m_tiles, int n_tiles) {
+    if (p.mode != 0 || p.conv_halo || g_dbg_flags || g_dbg_cta_group == 1 || (p.bn % 32) || m_tiles < 2) return false;
+    if (g_dbg_cta_group == 2) return true;
+    return p.bn == 256 && m_tiles * n_tiles >= 2LL * num_sms();
+}
+
 // Split the 216 KB of dynamic shared memory between the operand ring and the store staging buffers.
 // Long reductions want ring depth, short ones (1x1 convs) are bound by the epilogue's store pipeline.
 static void pick_pipeline(TapParams& p, int ksteps) {
-    p.stage_bytes = TG_A_BYTES + (p.bn > 128 ? 32768 : 16384);
+    p.stage_bytes = TG_A_BYTES + (p.bn / (p.cta_group == 2 ? 2 : 1) > 128 ? 32768 : 16384);
     p.stats_cols = p.stats ? (p.n_total + 31) / 32 * 32 : 0;
     // residual tiles are prefetched by TMA (two 16 KB buffers per epilogue group) when the output goes out by TMA
     p.nres = (p.residual && p.store_mode == TG_STORE_TMA && g_dbg_res_tma) ? 4 : 0;
@@ -330,10 +342,13 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
             for (int pw = 0; pw < 2; ++pw)
                 if (make_nhwc_map(&maps.a[ph * 2 + pw], x, B, H, W, Cin, ph, pw, 2, box)) return 1;
     }
+    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    const int n_tiles = (Cout + p.bn - 1) / p.bn;
+    p.cta_group = want_pair(p, m_tiles, n_tiles) ? 2 : 1;
     {
         const long long dims[4] = {Cin, Cout, (long long)R * S, 1};
         const long long strides[3] = {Cin, (long long)Cin * Cout, (long long)Cin * Cout * R * S};
-        const int bbox[4] = {TG_BK, p.bn, 1, 1};
+        const int bbox[4] = {TG_BK, p.bn / p.cta_group, 1, 1};
         if (make_map(&maps.b[0], w_tck, dims, strides, bbox)) return 1;
     }
     if (make_nhwc_map(&maps.d, y, B, Ho, Wo, Cout, 0, 0, 1, box)) return 1;
@@ -360,7 +375,7 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
     } else {
         pick_pipeline(p, p.n_taps * p.chunks);
     }
-    dim3 grid((Cout + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
+    dim3 grid(n_tiles, (unsigned)((m_tiles + p.cta_group - 1) / p.cta_group), 1);
     return launch_tapgemm(maps, p, grid, stream);
 }
 
@@ -433,9 +448,12 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             const int box[4] = {TG_BK, p.box_w, p.box_h, p.box_n};
             const int hbox[4] = {TG_BK, p.halo_w, p.halo_h, 1};
             if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, halo ? hbox : box)) return 1;
+            const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+            const int n_tiles = (Cin + p.bn - 1) / p.bn;
+            p.cta_group = want_pair(p, m_tiles, n_tiles) ? 2 : 1;
             const long long dims[4] = {Cout, Cin, (long long)R * S, 1};
             const long long strides[3] = {Cout, (long long)Cin * Cout, (long long)Cin * Cout * R * S};
-            const int bbox[4] = {TG_BK, p.bn, 1, 1};
+            const int bbox[4] = {TG_BK, p.bn / p.cta_group, 1, 1};
             if (make_map(&maps.b[0], w_tkc, dims, strides, bbox)) return 1;
             if (make_nhwc_map(&maps.d, dx, B, H, W, Cin, ph, pw, stride, box)) return 1;
             if (residual && make_nhwc_map(&maps.r, residual, B, H, W, Cin, ph, pw, stride, box)) return 1;
@@ -452,7 +470,7 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             } else {
                 pick_pipeline(p, p.n_taps * p.chunks);
             }
-            dim3 grid((Cin + p.bn - 1) / p.bn, p.tiles_w * p.tiles_h * p.tiles_n, 1);
+            dim3 grid(n_tiles, (unsigned)((m_tiles + p.cta_group - 1) / p.cta_group), 1);
             if (launch_tapgemm(maps, p, grid, stream)) return 2;
         }
     return 0;
@@ -634,10 +652,12 @@ static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, flo
         const int box[4] = {TG_BK, TG_BM, 1, 1};
         if (make_map(&maps.a[0], x, dims, strides, box)) return 1;
     }
+    const int n_tiles = (N + p.bn - 1) / p.bn;
+    p.cta_group = want_pair(p, p.tiles_w, n_tiles) ? 2 : 1;
     {
         const long long dims[4] = {K, N, 1, 1};
         const long long strides[3] = {ldw, (long long)ldw * N, (long long)ldw * N};
-        const int box[4] = {TG_BK, p.bn, 1, 1};
+        const int box[4] = {TG_BK, p.bn / p.cta_group, 1, 1};
         if (make_map(&maps.b[0], w, dims, strides, box)) return 1;
     }
     p.n_total = N;
@@ -672,7 +692,7 @@ static int linear_fwd_impl(const float* x, int ldx, const float* w, int ldw, flo
     PE_REQUIRE(!ep.stats || (p.store_mode == TG_STORE_TMA && !(ep.scale || ep.bias || ep.relu || ep.round_out || p.residual)),
                "linear_fwd: statistics need the TMA store path and a raw (un-activated) output");
     pick_pipeline(p, p.chunks);
-    dim3 grid((N + p.bn - 1) / p.bn, p.tiles_w, 1);
+    dim3 grid(n_tiles, (p.tiles_w + p.cta_group - 1) / p.cta_group, 1);
     return launch_tapgemm(maps, p, grid, stream);
 }
 
@@ -752,6 +772,8 @@ void pe_debug_residual_tma(int on) { g_dbg_res_tma = on; }
 void pe_debug_epilogue_groups(int groups) { g_dbg_epi_groups = groups; }
 
 void pe_debug_pdl(int mask) { pe::g_pdl = mask & 3; }
+
+void pe_debug_cta_group(int mode) { g_dbg_cta_group = mode; }
 
 void pe_debug_conv_halo(int on) {
     g_dbg_conv_halo = on & 1;

@@ -96,10 +96,24 @@ __device__ __forceinline__ void issue_halo_stage(uint32_t tmem_d, uint32_t bn, u
     }
 }
 
-template <int G>      // epilogue groups (2 or 4)
+// Work item of this CTA: with CTA pairs the list counts PAIRS of consecutive 128-pixel tiles, CTA rank r owns tile
+// 2 * pair + r (a phantom tile past the end loads zero-filled boxes and stores nothing).
+template <int CG>
+__device__ __forceinline__ Work decode_work_cg(const TapParams& p, int w, uint32_t rank) {
+    Work k = decode_work(p, w);
+    if (CG == 2) k.mt = k.mt * 2 + static_cast<int>(rank);
+    return k;
+}
+
+template <int G, int CG>      // epilogue groups (2 or 4), CTAs per MMA (1, or 2 = tcgen05 cta_group::2 pairs)
 __global__ void __launch_bounds__(64 + 128 * G, 1)
 tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ TapParams p) {
     constexpr int EPI_THREADS = 128 * G;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0u;
+    // persistent walk over the work list: one CTA (or one pair) per list position
+    const int w_first = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int w_step = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_full[TG_STAGES];
     __shared__ __align__(8) uint64_t s_empty[TG_STAGES];
@@ -142,7 +156,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         for (int a = 0; a < 2 * G; ++a) mbar_init(smem_u32(&s_res_full[a]), 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&s_tmem_full[a]), 1);
-            mbar_init(smem_u32(&s_tmem_empty[a]), EPI_THREADS);
+            // pairs: the leader's MMA warp reuses an accumulator once BOTH CTAs' epilogues have drained it
+            mbar_init(smem_u32(&s_tmem_empty[a]), EPI_THREADS * CG);
         }
         fence_mbar_init();
     }
@@ -153,11 +168,17 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         if (p.nres) tma_prefetch_desc(&maps.r);
     }
     if (warp == 1) {
-        tmem_alloc(smem_u32(&s_tmem_base), 2 * TG_MAX_BN);
-        tmem_relinquish();
+        if (CG == 2) {
+            tmem_alloc_pair(smem_u32(&s_tmem_base), 2 * TG_MAX_BN);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(smem_u32(&s_tmem_base), 2 * TG_MAX_BN);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();      // the peer's barriers are initialised before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) touched no
@@ -173,10 +194,40 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         // stage counters and addresses stay in uniform registers and one elected lane issues each TMA.
         uint32_t s = 0, ph = 0, sb = 0, phb = 0;
         bool ok = true;
-        for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
-            const Work wk = decode_work(p, w);
+        for (int w = w_first; w < p.work_total && ok; w += w_step) {
+            const Work wk = decode_work_cg<CG>(p, w, cta_rank);
             const int n_off = wk.nt * p.bn;
-            if (p.mode == 0 && p.conv_halo) {
+            if (CG == 2) {
+                // CTA pair: this CTA's own 128-pixel A box + its half of the weight tile; the bytes of both CTAs are
+                // counted on the leader's barrier, which the leader arms for the pair
+                const TileOrigin o = tile_origin(p, wk.mt);
+                const int bhalf = p.bn >> 1;
+                const uint32_t nbytes = static_cast<uint32_t>(p.m_rows + bhalf) * 128u;
+                const int n_mine = n_off + static_cast<int>(cta_rank) * bhalf;
+                int tap = wk.k_begin / p.chunks;
+                int ch = wk.k_begin - tap * p.chunks;
+                for (int j = 0; j < wk.nk; ++j) {
+                    if (!mbar_wait_warp(smem_u32(&s_empty[s]), ph ^ 1, spin)) {
+                        atomicOr(p.error_flag, 1);
+                        ok = false;
+                        break;
+                    }
+                    const uint32_t full = smem_u32(&s_full[s]);
+                    const uint32_t sa = smem_base + s * p.stage_bytes;
+                    if (leader) mbar_arrive_expect_tx_elect(full, 2u * nbytes);
+                    tma_load_4d_pair_elect(sa, &maps.a[p.tap_map[tap]], full, ch * TG_BK, o.w0 + p.tap_dw[tap],
+                                           o.h0 + p.tap_dh[tap], o.n0);
+                    tma_load_4d_pair_elect(sa + TG_A_BYTES, &maps.b[0], full, ch * TG_BK, n_mine, p.tap_b[tap], 0);
+                    if (++ch == p.chunks) {
+                        ch = 0;
+                        ++tap;
+                    }
+                    if (++s == static_cast<uint32_t>(p.stages)) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            } else if (p.mode == 0 && p.conv_halo) {
                 // haloed stride-1 conv: one haloed A tile per channel chunk, then one weight tile per tap
                 const TileOrigin o = tile_origin(p, wk.mt);
                 const uint32_t a_bytes = static_cast<uint32_t>(p.halo_w * p.halo_h) * 128u;
@@ -333,7 +384,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     } else if (warp == 1) {
         // =============================== MMA issuer ==========================================
         // Convergent warp, uniform descriptors, one elected lane per tcgen05.mma / tcgen05.commit.
-        const uint32_t idesc = make_idesc_tf32(TG_BM, p.bn, p.mode != 0, p.mode != 0);
+        const uint32_t idesc = make_idesc_tf32(TG_BM * CG, p.bn, p.mode != 0, p.mode != 0);
         // K-major: LBO unused (16 B), SBO = 8 rows * 128 B.  MN-major: LBO = one 32-wide
         // atom column (32 k-rows * 128 B), SBO = 4 k-rows * 128 B (128B_BASE32B atoms).
         const uint32_t a_lbo = p.dbg_a_lbo >= 0 ? p.dbg_a_lbo : (p.mode ? 4096 : 16);
@@ -350,8 +401,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         const uint32_t kstep16 = (p.mode ? 1024u : 32u) >> 4;  // 8 tf32 along K, in 16-byte units
         uint32_t s = 0, ph = 0, sb = 0, phb = 0, tile_i = 0;   // tile_i counts tiles that really use an accumulator
         bool ok = true;
-        for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
-            const Work wk = decode_work(p, w);
+        // pairs: only the leader CTA issues; its MMAs read both CTAs' stages and write both CTAs' accumulators
+        for (int w = w_first; w < p.work_total && ok && (CG == 1 || leader); w += w_step) {
+            const Work wk = decode_work_cg<CG>(p, w, cta_rank);
             if (wk.nk == 0) continue;
             // mode 2 owns all 512 TMEM columns as ONE set of per-tap accumulators
             const uint32_t acc = p.mode == 2 ? 0u : (tile_i & 1);
@@ -472,17 +524,24 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                 const uint32_t a_lo = a_lo00 + sa16;
                 const uint32_t b_lo = b_lo00 + sa16 + (static_cast<uint32_t>(TG_A_BYTES) >> 4);
 #pragma unroll
-                for (int kk = 0; kk < TG_BK / 8; ++kk)
-                    tc_mma_tf32_elect(tmem_d, (static_cast<uint64_t>(a_hi0) << 32) | (a_lo + kk * kstep16),
-                                      (static_cast<uint64_t>(b_hi0) << 32) | (b_lo + kk * kstep16), idesc,
-                                      (j > 0 || kk > 0) ? 1u : 0u);
-                tc_commit_elect(smem_u32(&s_empty[s]));  // frees the stage when these MMAs retire
+                for (int kk = 0; kk < TG_BK / 8; ++kk) {
+                    const uint64_t ad = (static_cast<uint64_t>(a_hi0) << 32) | (a_lo + kk * kstep16);
+                    const uint64_t bd = (static_cast<uint64_t>(b_hi0) << 32) | (b_lo + kk * kstep16);
+                    if (CG == 2) tc_mma_tf32_pair_elect(tmem_d, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                    else tc_mma_tf32_elect(tmem_d, ad, bd, idesc, (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                // frees the stage (in both CTAs of a pair) when these MMAs retire
+                if (CG == 2) tc_commit_pair_elect(smem_u32(&s_empty[s]));
+                else tc_commit_elect(smem_u32(&s_empty[s]));
                 if (++s == static_cast<uint32_t>(p.stages)) {
                     s = 0;
                     ph ^= 1;
                 }
             }
-            if (ok) tc_commit_elect(smem_u32(&s_tmem_full[acc]));
+            if (ok) {
+                if (CG == 2) tc_commit_pair_elect(smem_u32(&s_tmem_full[acc]));
+                else tc_commit_elect(smem_u32(&s_tmem_full[acc]));
+            }
         }
         __syncwarp();
     } else {
@@ -509,10 +568,10 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         const int res_chunks = (p.bn + 31) >> 5;
         const uint32_t my_res = res_base + grp * 2 * TG_A_BYTES;
         uint32_t rq = 0;                      // residual chunks consumed by this group
-        int pw = blockIdx.x, pc = grp;        // next chunk to prefetch (work item, chunk)
+        int pw = w_first, pc = grp;           // next chunk to prefetch (work item, chunk)
         auto res_issue = [&](uint32_t buf) {  // called by one thread
             if (pw >= p.work_total || pc >= res_chunks) return;
-            const Work w2 = decode_work(p, pw);
+            const Work w2 = decode_work_cg<CG>(p, pw, cta_rank);
             const TileOrigin o2 = tile_origin(p, w2.mt);
             const uint32_t bar = smem_u32(&s_res_full[grp * 2 + buf]);
             mbar_arrive_expect_tx(bar, static_cast<uint32_t>(p.m_rows) * 128u);
@@ -520,7 +579,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             pc += G;
             if (pc >= res_chunks) {
                 pc = grp;
-                pw += gridDim.x;
+                pw += w_step;
             }
         };
         if (res_tma && et == 0) {
@@ -531,8 +590,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             for (int cidx = eall; cidx < 2 * p.stats_cols; cidx += EPI_THREADS) s_sum[cidx] = 0.f;
             asm volatile("bar.sync %0, %1;" ::"n"(BAR_ALL), "n"(EPI_THREADS) : "memory");
         }
-        for (int w = blockIdx.x; w < p.work_total && ok; w += gridDim.x) {
-            const Work wk = decode_work(p, w);
+        for (int w = w_first; w < p.work_total && ok; w += w_step) {
+            const Work wk = decode_work_cg<CG>(p, w, cta_rank);
             const int n_off = wk.nt * p.bn;
             const uint32_t acc = p.mode == 2 ? 0u : (tile_i & 1);
             const uint32_t aph = p.mode == 2 ? (tile_i & 1) : ((tile_i >> 1) & 1);
@@ -596,14 +655,18 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             float* const out_row0 = out_row;
             int last_c = -1;                       // last chunk this group reads from TMEM
             for (int c = grp; c < nchunks; c += G) last_c = c;
-            if (last_c < 0 && wk.nk > 0) mbar_arrive(smem_u32(&s_tmem_empty[acc]));
+            if (last_c < 0 && wk.nk > 0) {
+                if (CG == 2) mbar_arrive_leader(smem_u32(&s_tmem_empty[acc]));
+                else mbar_arrive(smem_u32(&s_tmem_empty[acc]));
+            }
             for (int c = grp; c < nchunks; c += G) {
                 float v[32];
                 if (wk.nk > 0) {
                     tmem_ld_32x32(tmem_base + acc * TG_MAX_BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-                    if (c == last_c) {   // this thread is done with the accumulator: hand it back
+                    if (c == last_c) {   // this thread is done with the accumulator: hand it back (to the leader's MMA warp)
                         tc_fence_before();
-                        mbar_arrive(smem_u32(&s_tmem_empty[acc]));
+                        if (CG == 2) mbar_arrive_leader(smem_u32(&s_tmem_empty[acc]));
+                        else mbar_arrive(smem_u32(&s_tmem_empty[acc]));
                     }
                 } else {
 #pragma unroll
@@ -822,9 +885,11 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();      // nothing of the pair is in flight any more: barriers, stages, accumulators
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * TG_MAX_BN);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, 2 * TG_MAX_BN);
+        else tmem_dealloc(tmem_base, 2 * TG_MAX_BN);
     }
 }
 
@@ -843,13 +908,20 @@ bool pdl_enabled(int kind) {
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TG_SMEM_BYTES));
-        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TG_SMEM_BYTES));
+        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TG_SMEM_BYTES));
+        PE_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            TG_SMEM_BYTES));
         configured = true;
     }
     if (p.epi_groups != 4) p.epi_groups = 2;
+    if (p.cta_group != 2) p.cta_group = 1;
+    PE_REQUIRE(p.cta_group == 1 || (p.mode == 0 && !p.conv_halo && p.ksplit == 1 && p.bn % 32 == 0),
+               "tap-GEMM: CTA pairs are implemented for the plain conv / GEMM mode only");
     {
         // the carve-up of dynamic shared memory must fit: ring + weight ring + store staging + residual tiles +
         // statistics scratch (a violation here would be an out-of-bounds shared-memory access on the device)
@@ -862,22 +934,38 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
     p.work_n = work.x;
     p.work_m = work.y;
     p.work_total = static_cast<int>(work.x * work.y * work.z);
-    int grid = p.work_total < num_sms() ? p.work_total : num_sms();
+    // one CTA per SM, or one CTA pair per TPC (the work list then counts pairs of tiles)
+    const int slots = p.cta_group == 2 ? num_sms() / 2 : num_sms();
+    int grid = p.work_total < slots ? p.work_total : slots;
     if (grid < 1) return 0;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.gridDim = dim3(grid * p.cta_group, 1, 1);
     cfg.blockDim = dim3(64 + 128 * p.epi_groups, 1, 1);
     cfg.dynamicSmemBytes = TG_SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.cta_group == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled(1)) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled(1) ? 1 : 0;
-    if (p.epi_groups == 4)
-        PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<4>, maps, p));
-    else
-        PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, maps, p));
+    cfg.numAttrs = na;
+    if (p.cta_group == 2) {
+        if (p.epi_groups == 4) PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<4, 2>, maps, p));
+        else PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<2, 2>, maps, p));
+    } else {
+        if (p.epi_groups == 4) PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<4, 1>, maps, p));
+        else PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tapgemm_kernel<2, 1>, maps, p));
+    }
     PE_LAUNCH_CHECK();
     return 0;
 }

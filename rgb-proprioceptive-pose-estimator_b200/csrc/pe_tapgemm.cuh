@@ -90,6 +90,10 @@ struct TapParams {
     int b_stages, b_bytes;    // B ring: stages and bytes per stage (b_taps * bn * 128)
     int b_taps;               // filter taps per B stage (one TMA box {32, bn, b_taps}); divides n_taps
     int b_ring_bytes;         // b_stages * b_bytes (0 when conv_halo == 0): offset of the store staging after the A ring
+    // CTA pairs (mode 0 without conv_halo): cta_group = 2 runs the work list on clusters of two CTAs; a pair owns two
+    // consecutive 128-pixel tiles (work_m counts PAIRS), each CTA loads its own A box and HALF of the B tile
+    // (bn / 2 weight rows), the leader issues tcgen05.mma.cta_group::2 with M = 256 for both.
+    int cta_group;
 };
 
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream);

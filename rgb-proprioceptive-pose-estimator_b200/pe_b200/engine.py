@@ -18,7 +18,7 @@ BN_MOMENTUM = 0.1
 # kernels (kept for the kernel tests and as the reference the fused one is checked against)
 FUSED_STEM_TAIL = [True]
 # test hook: when set to a list, every training-mode convolution appends its raw output (an Act, execution order:
-# stem, then conv1 / conv2 / conv3 / downsample of each block) -- tests/model_checks.py feeds them to the oracle
+# stem, then conv1 / conv2 / conv3 / downsample of each block) -- read by the parity tests (tests/model_checks.py)
 CAPTURE_CONV_OUTPUTS = [None]
 
 

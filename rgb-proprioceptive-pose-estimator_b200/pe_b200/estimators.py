@@ -19,7 +19,7 @@ OUT_LD = 8          # 7-D poses live in 8-float rows so every row stays 16-byte 
 
 
 # test hook: when set to a list, the naive estimators' MLPs append every layer's (post-ReLU) output buffer, in
-# execution order (tests/model_checks.py teacher-forces them into the oracle next to the conv outputs)
+# execution order (read by the parity tests, tests/model_checks.py)
 CAPTURE_HEAD_OUTPUTS = [None]
 FUSED_HEAD = [True]       # rollout-sized inference (<= 8 frames, no gradients) goes through pe_fused_head
 FUSED_HEAD_MAX_ROWS = 8

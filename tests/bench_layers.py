@@ -50,7 +50,11 @@ def main():
         flop = 2.0 * B * Ho * Ho * co * ci * k * k / TF32 * 1e6
         cols = []
         for f in flags:
-            if f == 4000:
+            if f == 5001:
+                L.pe_debug_cta_group(1)
+            elif f == 5002:
+                L.pe_debug_cta_group(2)
+            elif f == 4000:
                 L.pe_debug_epilogue_groups(4)
             elif f == 2002:
                 L.pe_debug_epilogue_groups(2)
@@ -82,6 +86,7 @@ def main():
             L.pe_debug_flags(0)
             L.pe_debug_wgrad_halo(1)
             L.pe_debug_epilogue_groups(0)
+            L.pe_debug_cta_group(0)
         L.pe_debug_flags(0)
         L.pe_debug_pipeline(0, 0)
         L.pe_debug_max_bn(256)

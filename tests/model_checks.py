@@ -168,6 +168,16 @@ def check_train_step(kind, n=2, s=2, seed=1, verbose=False, latent=None):
     ref_e = ref_e if isinstance(ref_e, tuple) else (ref_e,)
     for i, (a, b) in enumerate(zip(oe, ref_e)):
         rows.append(("%s eval out%d" % (tag, i), rel(a, b), 2e-3))
+    # the same eval forward against the oracle at the CUDA path's operand precision (TF32 operands, float64
+    # accumulation), on the running statistics the CUDA model now holds: what is left is accumulation order
+    orc2 = oracle_for(kind, model)
+    orc2.sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in orc2.sd.items()}
+    orc2.extra = {k: v.double() for k, v in orc2.extra.items()}
+    with po.tf32_operands(True), torch.no_grad():
+        ref_t = orc2.forward(img.double(), x0.double(), training=False)
+    ref_t = ref_t if isinstance(ref_t, tuple) else (ref_t,)
+    for i, (a, b) in enumerate(zip(oe, ref_t)):
+        rows.append(("%s eval out%d [tf32-operand oracle]" % (tag, i), rel(a, b), 1e-3))
     return rows
 
 
@@ -242,9 +252,15 @@ def check_forced(kind, n=2, s=2, seed=1, verbose=False):
         ferr = list(ferr)
     t_cpu = time.time() - t0
     tag = "forced %s n%d" % (kind, n) + ("" if kind in ("no", "n") else " s%d" % s)
-    rows = [("%s conv / dense forward, worst of %d layers" % (tag, len(ferr)), max(ferr), 5e-4)]
-    for i, (a, b) in enumerate(zip(outs, outs_ref)):
-        rows.append(("%s out%d" % (tag, i), rel(a, b), 1e-3))
+    n_conv = len(ys)
+    rows = [("%s conv forward, worst of %d layers" % (tag, n_conv), max(ferr[:n_conv]), 5e-4)]
+    if len(ferr) > n_conv:
+        # the naive heads' layer outputs (incl. the final pose) are forced too: each layer's own result is the check
+        rows.append(("%s head layers forward (incl. output), worst of %d" % (tag, len(ferr) - n_conv),
+                     max(ferr[n_conv:]), 1e-3))
+    else:
+        for i, (a, b) in enumerate(zip(outs, outs_ref)):
+            rows.append(("%s out%d" % (tag, i), rel(a, b), 1e-3))
     rows.append(("%s loss" % tag, rel(loss.reshape(1), loss_ref.reshape(1)), 1e-3))
     named = dict(model.named_parameters())
     errs = []
@@ -284,22 +300,35 @@ def check_forced(kind, n=2, s=2, seed=1, verbose=False):
 
 
 def check_rollout(kind="tdo", steps=3):
-    """Batch-1 streaming inference with carried LSTM state vs oracle."""
+    """Batch-1 streaming inference with carried LSTM state vs the plain fp32 oracle and vs the oracle at the CUDA
+    path's operand precision (TF32 trunk operands, fp32 fused head; float64 accumulation)."""
     model = build_model(kind)
     orc = oracle_for(kind, model)
+    orc_t = oracle_for(kind, model)
+    orc_t.sd = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in orc_t.sd.items()}
+    orc_t.extra = {k: v.double() for k, v in orc_t.extra.items()}
     model.cuda().eval()
     model.rollout = True
     model.reset_initial_state(1)
     orc.reset_state(1)
+    orc_t.reset_state(1)
+    if orc_t.state is not None:
+        def dbl(t):
+            return tuple(dbl(u) for u in t) if isinstance(t, tuple) else t.double()
+        orc_t.state = dbl(orc_t.state)
     rows = []
     for t in range(steps):
         img, x0, _ = po.synthetic_batch(kind, 1, s=1, seed=10 + t)
         with torch.no_grad():
             o = model(img.cuda(), None, x0.cuda())
-        r = orc.forward(img, x0, training=False, rollout=True)
+            r = orc.forward(img, x0, training=False, rollout=True)
+            with po.tf32_operands(True):
+                rt = orc_t.forward(img.double(), x0.double(), training=False, rollout=True)
         o = o if isinstance(o, tuple) else (o,)
         r = r if isinstance(r, tuple) else (r,)
+        rt = rt if isinstance(rt, tuple) else (rt,)
         rows.append(("%s rollout step %d" % (kind, t), max(rel(a, b) for a, b in zip(o, r)), 2e-3))
+        rows.append(("%s rollout step %d [tf32-operand oracle]" % (kind, t), max(rel(a, b) for a, b in zip(o, rt)), 1e-3))
     return rows
 
 
