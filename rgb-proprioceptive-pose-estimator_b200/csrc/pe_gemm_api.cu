@@ -185,11 +185,12 @@ static int g_dbg_cta_group = 0;       // 0: automatic, 1: never pair CTAs, 2: pa
 // writes as many -- at bn = 256 that is 24 KB per 128-cycle instruction, 1.5x what the shared-memory port moves, which
 // is where the measured 185 cycles per instruction come from.  In a pair each CTA holds its own A box and HALF of the
 // weight tile: 16 KB per instruction, back under the port's rate, and half the L2 -> SM weight traffic.  Used for
-// the wide tiles when every TPC still gets at least one pair of tiles.
+// the wide tiles when the launch has at least one tile per SM (measured on B200, 256 frames: 14x14 256->1024 forward
+// 97 -> 69 us, 7x7 512->2048 81 -> 58 us, 3x3 256->256 @14 91 -> 82 us = 720 TFLOP/s; no gain at 128 or 64 columns).
 static bool want_pair(const TapParams& p, long long m_tiles, int n_tiles) {
     if (p.mode != 0 || p.conv_halo || g_dbg_flags || g_dbg_cta_group == 1 || (p.bn % 32) || m_tiles < 2) return false;
     if (g_dbg_cta_group == 2) return true;
-    return p.bn == 256 && m_tiles * n_tiles >= 2LL * num_sms();
+    return p.bn == 256 && m_tiles * n_tiles >= (long long)num_sms();
 }
 
 // Split the 216 KB of dynamic shared memory between the operand ring and the store staging buffers.

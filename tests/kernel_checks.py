@@ -528,6 +528,16 @@ def check_adam(n):
         opt2.step()
         L.pe_sgd_step(P(ps), P(grad), P(buf), n, 0.1, 0.9, 0.0, int(step == 0), 1.0, S())
     out.append(("sgd 3 steps n%d" % n, relerr(ps, ref_s.detach()), 1e-6))
+    # plain SGD with weight decay (no momentum buffer): the 12-bytes-per-parameter variant of the same kernel
+    ref_w = torch.nn.Parameter(p0.clone())
+    opt3 = torch.optim.SGD([ref_w], lr=0.05, weight_decay=1e-2)
+    pw = p0.clone()
+    for step in range(2):
+        grad = torch.randn(n, device=DEV, generator=g)
+        ref_w.grad = grad.clone()
+        opt3.step()
+        L.pe_sgd_step(P(pw), P(grad), None, n, 0.05, 0.0, 1e-2, int(step == 0), 1.0, S())
+    out.append(("sgd (no momentum, weight decay) n%d" % n, relerr(pw, ref_w.detach()), 1e-6))
     return out
 
 
