@@ -203,6 +203,20 @@ int pe_lstm_cell_bwd(const float* dh, int lddh, const float* dh_rec, const float
                      const float* c_prev, const float* c_out, float* dgates, int lddg, float* dc_prev, int N,
                      int Hd, void* stream);
 
+/* ---- persistent LSTM recurrence: ONE launch for all S timesteps (models/time_sensitive.py:501-510 nn.LSTM call;
+ *      gates i,f,g,o).  gx = x W_ih^T for all S*N rows (pe_linear_fwd, no bias); W_hh stays in the checkpoint layout
+ *      [4H, H] (fp32, un-rounded) and is sliced across the grid, resident in shared memory for the whole sequence; one
+ *      grid-wide barrier per timestep (cooperative launch), LSTM cell fused behind the recurrent dot products.
+ *      h0 / c0: carried state [N, H] or NULL (zeros).  act: activated gates [S*N, 4H] for the backward pass or NULL.
+ *      Backward (h0 = NULL sequences): dgates [S*N, 4H] (TF32-rounded when round_tf32) from dh_all [S*N, H]; the weight
+ *      and input gradients then follow as plain GEMMs on dgates. ------------------------------------------------- */
+int pe_lstm_seq_supported(int N, int Hd, int backward);      /* 1 if the shape fits (grid <= SMs, smem <= 200 KB) */
+int pe_lstm_seq_fwd(const float* gx, const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
+                    const float* c0, float* h_all, float* c_all, float* act, int S, int N, int Hd, int round_tf32,
+                    void* stream);
+int pe_lstm_seq_bwd(const float* dh_all, const float* w_hh, const float* act, const float* c_all, const float* c0,
+                    float* dgates, int S, int N, int Hd, int round_tf32, void* stream);
+
 /* ---- fused fusion-head step for rollout inference (<= 8 frames): replaces, in ONE launch, the torch.cat of
  *      image / aux features with the proprioceptive vector, the first dense layer or LSTM gate projection, the
  *      LSTM cell and the remaining small layers (models/naive.py:333-345, :92-104; models/time_sensitive.py:

@@ -196,6 +196,24 @@ def _head_ops(fused):
     return F.linear, (lambda t: t)
 
 
+class _RecurrentFP32(torch.autograd.Function):
+    """h W_hh^T + b of a SEQUENCE's recurrence as the persistent LSTM kernel computes it: fp32 FMA on the un-rounded
+    checkpoint weights (h itself was rounded where it was produced); backward on the TF32-rounded gate gradient the
+    kernel writes out, r = round(dg):  dh = r W_hh (un-rounded weights),  dW_hh = r^T h and db = sum r (tensor-core
+    GEMM / column sum over the same rounded buffer)."""
+
+    @staticmethod
+    def forward(ctx, h, w, b):
+        ctx.save_for_backward(h, w)
+        return h.matmul(w.t()) + b
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.saved_tensors
+        r = round_tf32(g)
+        return r.matmul(w), r.t().matmul(h), r.sum(0)
+
+
 def _conv(x, w, stride=1, padding=0):
     if _TF32[0]:
         return _force(_ConvTF32.apply(x, w, stride, padding))
@@ -283,6 +301,9 @@ def lstm_forward(x, sd, prefix, state=None, ops=None):
     S, N, _ = x.shape
     H = w_hh.shape[1]
     lin, rnd = ops if ops is not None else (_linear, _rnd)
+    # sequences run their recurrence in the persistent kernel (fp32 recurrent product); single steps outside the fused
+    # head keep the TF32 recurrent GEMM
+    rec = _RecurrentFP32.apply if (lin is _linear and _TF32[0] and S > 1) else lin
     if state is None:
         h = x.new_zeros(N, H)
         c = x.new_zeros(N, H)
@@ -290,7 +311,7 @@ def lstm_forward(x, sd, prefix, state=None, ops=None):
         h, c = state[0][0], state[1][0]
     outs = []
     for t in range(S):
-        gates = lin(x[t], w_ih, b_ih) + lin(h, w_hh, b_hh)
+        gates = lin(x[t], w_ih, b_ih) + rec(h, w_hh, b_hh)
         i, f, g, o = gates.chunk(4, dim=1)
         c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
         h = rnd(torch.sigmoid(o) * torch.tanh(c))

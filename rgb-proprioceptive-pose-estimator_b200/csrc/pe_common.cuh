@@ -41,6 +41,10 @@ const char* get_error();
     } while (0)
 
 int num_sms();
+// the sticky device-side error flag (one int, allocated on first use; nullptr if that fails): bits 1-32 tap-GEMM
+// pipeline timeouts, 64 grid-barrier timeout of the persistent LSTM kernels
+int* device_error_flag();
+void lstm_seq_reset();      // re-arm the LSTM kernels' grid barrier (after a reported timeout)
 // programmatic dependent launch: bit 0 = tap-GEMM launches, bit 1 = streaming / elementwise launches carry the
 // attribute (PE_B200_PDL=<mask> or pe_debug_pdl(mask); default in pe_tapgemm.cu)
 bool pdl_enabled(int kind = 1);

@@ -46,6 +46,8 @@ static int ensure_error_flag() {
     return 0;
 }
 
+int* device_error_flag() { return ensure_error_flag() ? nullptr : g_error_flag; }
+
 // Turns a pipeline timeout into something the caller cannot miss without a host synchronisation: when the sticky
 // flag is set, the given result buffer (the step's loss, the rollout step's pose) is overwritten with NaNs.
 __global__ void poison_on_error_kernel(const int* flag, float* buf, long long n) {
@@ -805,6 +807,7 @@ int pe_poison_on_error(float* buf, long long n, void* stream) {
 
 void pe_device_error_clear(void) {
     if (g_error_flag) cudaMemset(g_error_flag, 0, sizeof(int));
+    pe::lstm_seq_reset();
 }
 
 int pe_conv2d_fwd(const float* x, const float* w_tck, float* y, int B, int H, int W, int Cin, int Cout, int R,

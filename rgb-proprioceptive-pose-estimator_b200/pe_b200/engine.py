@@ -660,9 +660,15 @@ class LinearOp:
                             None, st)
 
 
+PERSISTENT_LSTM = [True]      # sequences (S > 1): the whole recurrence in one persistent launch (pe_lstm_seq_*)
+
+
 class LSTMOp:
-    """Single-layer seq-major nn.LSTM (gates i,f,g,o): one big input-projection GEMM, then per-step
-    recurrent GEMM + fused cell kernel; BPTT in reverse with the mirrored kernels."""
+    """Single-layer seq-major nn.LSTM (gates i,f,g,o): one big input-projection GEMM, then the recurrence.  For
+    sequences the recurrence is ONE persistent launch forward and one backward (W_hh sliced across the grid and
+    resident in shared memory, a grid barrier per timestep, cell fused; fp32 on the un-rounded W_hh); single steps
+    (streaming rollout beyond the fused head's 8 rows) and carried-state backward keep the per-step recurrent GEMM +
+    cell kernel pair."""
 
     def __init__(self, lstm, ld_in):
         self.lstm = lstm
@@ -704,6 +710,12 @@ class LSTMOp:
         h_all = torch.empty(S * N, H, device=dev, dtype=torch.float32)
         c_all = torch.empty(S * N, H, device=dev, dtype=torch.float32)
         act = torch.empty(S * N, G, device=dev, dtype=torch.float32) if need_grad else None
+        if PERSISTENT_LSTM[0] and S > 1 and L.pe_lstm_seq_supported(N, H, 0):
+            _dev_check(lstm.weight_hh_l0)
+            L.pe_lstm_seq_fwd(P(gx), P(lstm.weight_hh_l0), P(lstm.bias_ih_l0), P(lstm.bias_hh_l0), P(h0), P(c0),
+                              P(h_all), P(c_all), P(act), S, N, H, 1, st)
+            ctx = dict(x=x, S=S, N=N, h_all=h_all, c_all=c_all, act=act, h0=h0, c0=c0) if need_grad else None
+            return h_all, h_all[(S - 1) * N:], c_all[(S - 1) * N:], ctx
         gh = torch.empty(N, G, device=dev, dtype=torch.float32)
         h_prev, c_prev = h0, c0
         for t in range(S):
@@ -730,22 +742,27 @@ class LSTMOp:
         dev = dh_all.device
         h_all, c_all, act = ctx["h_all"], ctx["c_all"], ctx["act"]
         dg = torch.empty(S * N, G, device=dev, dtype=torch.float32)
-        dh_rec = None
-        dc = None
-        dhr_buf = torch.empty(N, H, device=dev, dtype=torch.float32)
-        dc_bufs = [torch.empty(N, H, device=dev, dtype=torch.float32) for _ in range(2)]
-        for t in range(S - 1, -1, -1):
-            c_prev = c_all[(t - 1) * N:] if t > 0 else ctx["c0"]
-            dc_new = dc_bufs[t & 1]
-            L.pe_lstm_cell_bwd(P(dh_all[t * N:]), H, P(dh_rec), P(dc), P(act[t * N:]), P(c_prev), P(c_all[t * N:]),
-                               P(dg[t * N:]), G, P(dc_new), N, H, st)
-            dc = dc_new
-            if t > 0 or ctx["h0"] is not None:
-                L.pe_linear_fwd(P(dg[t * N:]), G, P(self.w_hh_t), G, None, None, P(dhr_buf), H, N, H, G, 0, 0, 0,
-                                None, st)
-                dh_rec = dhr_buf
-        # round dg once for the three big GEMMs that consume it as a TF32 operand
-        L.pe_copy_cols(P(dg), G, P(dg), G, S * N, G, 1, st)
+        if (PERSISTENT_LSTM[0] and S > 1 and ctx["h0"] is None and dh_all.stride(0) == H and
+                L.pe_lstm_seq_supported(N, H, 1)):
+            # whole BPTT recurrence in one launch; dg comes out TF32-rounded for the GEMMs below
+            L.pe_lstm_seq_bwd(P(dh_all), P(lstm.weight_hh_l0), P(act), P(c_all), P(ctx["c0"]), P(dg), S, N, H, 1, st)
+        else:
+            dh_rec = None
+            dc = None
+            dhr_buf = torch.empty(N, H, device=dev, dtype=torch.float32)
+            dc_bufs = [torch.empty(N, H, device=dev, dtype=torch.float32) for _ in range(2)]
+            for t in range(S - 1, -1, -1):
+                c_prev = c_all[(t - 1) * N:] if t > 0 else ctx["c0"]
+                dc_new = dc_bufs[t & 1]
+                L.pe_lstm_cell_bwd(P(dh_all[t * N:]), H, P(dh_rec), P(dc), P(act[t * N:]), P(c_prev),
+                                   P(c_all[t * N:]), P(dg[t * N:]), G, P(dc_new), N, H, st)
+                dc = dc_new
+                if t > 0 or ctx["h0"] is not None:
+                    L.pe_linear_fwd(P(dg[t * N:]), G, P(self.w_hh_t), G, None, None, P(dhr_buf), H, N, H, G, 0, 0, 0,
+                                    None, st)
+                    dh_rec = dhr_buf
+            # round dg once for the three big GEMMs that consume it as a TF32 operand
+            L.pe_copy_cols(P(dg), G, P(dg), G, S * N, G, 1, st)
         L.pe_linear_wgrad(P(ctx["x"]), self.ld_in, P(dg), G, P(grad_of(lstm.weight_ih_l0)), self.nin, S * N, G,
                           self.nin, st)
         g_hh = grad_of(lstm.weight_hh_l0)

@@ -16,7 +16,7 @@ _REPO_ROOT = os.path.dirname(_PKG_ROOT)
 HEADER = os.path.join(_REPO_ROOT, "include", "pe_b200.h")
 CSRC = os.path.join(_PKG_ROOT, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpe_b200.so")
-SOURCES = ["pe_tapgemm.cu", "pe_gemm_api.cu", "pe_elementwise.cu", "pe_head.cu", "pe_fused_head.cu"]
+SOURCES = ["pe_tapgemm.cu", "pe_gemm_api.cu", "pe_elementwise.cu", "pe_head.cu", "pe_fused_head.cu", "pe_lstm_seq.cu"]
 
 _CTYPE = {
     "int": ctypes.c_int,
@@ -68,7 +68,8 @@ def build(force=False, verbose=False):
 
 
 # entry points whose int return value is a VALUE, not a status code
-_VALUE_RETURNING = ("pe_version", "pe_device_error", "pe_pack_block_elems", "pe_head_desc_size")
+_VALUE_RETURNING = ("pe_version", "pe_device_error", "pe_pack_block_elems", "pe_head_desc_size",
+                    "pe_lstm_seq_supported")
 
 
 class PeError(RuntimeError):
