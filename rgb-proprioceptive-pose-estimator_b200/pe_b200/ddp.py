@@ -19,12 +19,16 @@ class BucketedAllReduce:
     """All-reduce(sum) of a flat gradient arena in buckets that are launched as soon as a contiguous
     tail of the arena is final (backward produces gradients from the end of the arena to its start)."""
 
-    def __init__(self, flat, bucket_elems, group=None, async_op=True, stream=None):
+    def __init__(self, flat, bucket_elems, group=None, async_op=True, stream=None, after=None):
+        """after(lo, hi): optional callback enqueued on `stream` right behind each bucket's all-reduce (the fused
+        trainer applies the optimizer update of that arena range there, so the update of the early buckets overlaps
+        the rest of the backward pass and only the last, small bucket's reduce + update is exposed)."""
         self.flat = flat
         self.bucket = int(bucket_elems)
         self.group = group
         self.async_op = async_op
         self.stream = stream
+        self.after = after
         self.reset()
 
     def reset(self):
@@ -43,6 +47,9 @@ class BucketedAllReduce:
             self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
                 w = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                if self.after is not None:
+                    w.wait()                  # stream-level dependency on the collective, the host does not block
+                    self.after(lo, hi)
             self.works.append(w)
         else:
             w = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=self.async_op)

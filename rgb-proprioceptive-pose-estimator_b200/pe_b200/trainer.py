@@ -67,7 +67,7 @@ class FusedTrainer:
 
     def __init__(self, model, distance_metric="l2", alpha=1.0, epsilon=1e-4, scale_factor=1.0, mode="pose",
                  lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, optimizer="adam", momentum=0.0,
-                 process_group=None, bucket_mb=32):
+                 process_group=None, bucket_mb=8):
         if mode not in ("pose", "position"):
             raise ValueError("training loss mode must be 'pose' or 'position'")
         self.model = model
@@ -120,7 +120,9 @@ class FusedTrainer:
             from .ddp import BucketedAllReduce
             if dist.get_world_size(self.pg) > 1:
                 self.comm_stream = torch.cuda.Stream(device=dev)
-                self.reducer = BucketedAllReduce(gf, self.bucket_bytes // 4, group=self.pg, stream=self.comm_stream)
+                self.reducer = BucketedAllReduce(gf, self.bucket_bytes // 4, group=self.pg, stream=self.comm_stream,
+                                                 after=self._bucket_update)
+        self._fused_update = False
 
     def grad_of(self, p):
         self.touched.add(id(p))
@@ -135,10 +137,34 @@ class FusedTrainer:
     def step(self, img, self_measurement, targets, depth=None):
         """One optimisation step.  `targets`: a tensor (object-pose models) or a (x0, x1) pair for the
         two-headed models, matching util/learn_utils.py:160-172.  Returns the loss as a 1-element device
-        tensor (sum over the local samples)."""
-        loss = self.forward_backward(img, self_measurement, targets, depth)
-        self.apply_update()
+        tensor (sum over the local samples).
+
+        Multi-GPU: from the second step on, every all-reduce bucket is followed on the communication stream by the
+        optimizer update of exactly that arena range, so reducing and updating the head / layer4 / layer3 buckets
+        overlaps the backward pass of the earlier layers; only the last (stem-side, <= bucket_mb) bucket is exposed."""
+        self._fused_update = self.reducer is not None and self.t > 0
+        try:
+            loss = self.forward_backward(img, self_measurement, targets, depth)
+        finally:
+            fused, self._fused_update = self._fused_update, False
+        self.apply_update(already_applied=fused)
         return loss
+
+    def _bucket_update(self, lo, hi):
+        """Runs on the communication stream behind the all-reduce of g_flat[lo:hi] (BucketedAllReduce.after)."""
+        if self._fused_update and hi > lo:
+            self._update_range(lo, hi, self.t + 1)
+
+    def _update_range(self, lo, hi, t):
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        n = hi - lo
+        if self.optimizer == "adam":
+            native.account("pe_adam_step", 28 * n)          # read p, g, m, v; write p, m, v
+            L.pe_adam_step(P(self.p_flat[lo:]), P(self.g_flat[lo:]), P(self.m_flat[lo:]), P(self.v_flat[lo:]), n,
+                           self.lr, self.betas[0], self.betas[1], self.eps, self.wd, t, 1.0, st)
+        else:
+            L.pe_sgd_step(P(self.p_flat[lo:]), P(self.g_flat[lo:]), P(self.m_flat[lo:]) if self.momentum else None, n,
+                          self.lr, self.momentum, self.wd, int(t == 1), 1.0, st)
 
     def forward_backward(self, img, self_measurement, targets, depth=None):
         """forward + loss + backward (+ gradient all-reduce): leaves the summed gradient in self.g_flat."""
@@ -194,16 +220,9 @@ class FusedTrainer:
             L.check_device()
         return self._pending_loss
 
-    def apply_update(self):
-        L, st, P = native.lib(), native.stream_ptr(), native.ptr
-        core = self.core
+    def apply_update(self, already_applied=False):
+        """Optimizer update over the whole arena (one streaming kernel), unless the buckets already carried it."""
         self.t += 1
-        n = self.p_flat.numel()
-        if self.optimizer == "adam":
-            native.account("pe_adam_step", 28 * n)          # read p, g, m, v; write p, m, v
-            L.pe_adam_step(P(self.p_flat), P(self.g_flat), P(self.m_flat), P(self.v_flat), n, self.lr, self.betas[0],
-                           self.betas[1], self.eps, self.wd, self.t, 1.0, st)
-        else:
-            L.pe_sgd_step(P(self.p_flat), P(self.g_flat), P(self.m_flat) if self.momentum else None, n, self.lr,
-                          self.momentum, self.wd, int(self.t == 1), 1.0, st)
-        invalidate_core(core)
+        if not already_applied:
+            self._update_range(0, self.p_flat.numel(), self.t)
+        invalidate_core(self.core)

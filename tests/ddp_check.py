@@ -120,6 +120,31 @@ def main():
                   "buckets %d, param diff %.2e, ranks identical %s" % (step, err, noise, buckets, perr, same),
                   flush=True)
         ok = ok and err < max(1e-4, 10 * noise) and same
+    if "--step" in sys.argv:
+        # FusedTrainer.step(): every all-reduce bucket is followed by the optimizer update of its arena range on the
+        # communication stream.  Against the same steps done as forward_backward -> plain all-reduce -> one update:
+        # identical parameters on every rank, and equal to the plain path up to the atomic summation order of the
+        # split-K wgrad (Adam moves a weight by ~lr per step whatever the gradient's size: a few lr of slack)
+        lr = 1e-4
+        for t in (tb,):
+            t.p_flat.copy_(ta.p_flat)
+            t.m_flat.copy_(ta.m_flat)
+            t.v_flat.copy_(ta.v_flat)
+            t.t = ta.t
+            invalidate_core(t.core)
+        for step in range(3):
+            ta.step(img, x0, tgt)
+            tb.forward_backward(img, x0, tgt)
+            dist.all_reduce(tb.g_flat)
+            tb.apply_update()
+            ref = ta.p_flat.clone()
+            dist.broadcast(ref, 0)
+            same = bool(torch.equal(ref, ta.p_flat))
+            perr = float((ta.p_flat - tb.p_flat).abs().max())
+            if rank == 0:
+                print("fused step %d: ranks identical %s, max parameter difference to the plain path %.2e (lr %.0e), "
+                      "%d all-reduce launches" % (step, same, perr, lr, ta.reducer.launched), flush=True)
+            ok = ok and same and perr <= 20 * lr
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1

@@ -465,32 +465,32 @@ def check_lstm_cell(N, H):
     return out
 
 
-def check_lstm_seq(S, N, H, with_state=False):
+def check_lstm_seq(T, N, H, with_state=False):
     """Persistent LSTM recurrence (pe_lstm_seq_fwd / _bwd: one launch for all S steps) against the fp64 recurrence
     h_t, c_t = cell(gx_t + h_{t-1} W_hh^T + b) and its autograd: hidden / cell states, and the gate pre-activation
     gradients (= d loss / d gx) for a random upstream gradient on every hidden output."""
     L = native.lib()
-    g = torch.Generator(device=DEV).manual_seed(S * 1000 + N * 10 + H)
-    gx = torch.randn(S * N, 4 * H, device=DEV, generator=g)
+    g = torch.Generator(device=DEV).manual_seed(T * 1000 + N * 10 + H)
+    gx = torch.randn(T * N, 4 * H, device=DEV, generator=g)
     w = torch.randn(4 * H, H, device=DEV, generator=g) / H ** 0.5
     b_ih = torch.randn(4 * H, device=DEV, generator=g) * 0.1
     b_hh = torch.randn(4 * H, device=DEV, generator=g) * 0.1
     h0 = torch.randn(N, H, device=DEV, generator=g) * 0.5 if with_state else None
     c0 = torch.randn(N, H, device=DEV, generator=g) * 0.5 if with_state else None
-    dh = torch.randn(S * N, H, device=DEV, generator=g)
-    tag = "S%d N%d H%d%s" % (S, N, H, " +state" if with_state else "")
+    dh = torch.randn(T * N, H, device=DEV, generator=g)
+    tag = "S%d N%d H%d%s" % (T, N, H, " +state" if with_state else "")
     if not L.pe_lstm_seq_supported(N, H, 1):
         return [("lstm_seq %s unsupported" % tag, 1.0, 0.0)]
-    h_all = torch.full((S * N, H), float("nan"), device=DEV)
-    c_all = torch.full((S * N, H), float("nan"), device=DEV)
-    act = torch.full((S * N, 4 * H), float("nan"), device=DEV)
-    L.pe_lstm_seq_fwd(P(gx), P(w), P(b_ih), P(b_hh), P(h0), P(c0), P(h_all), P(c_all), P(act), S, N, H, 0, S())
+    h_all = torch.full((T * N, H), float("nan"), device=DEV)
+    c_all = torch.full((T * N, H), float("nan"), device=DEV)
+    act = torch.full((T * N, 4 * H), float("nan"), device=DEV)
+    L.pe_lstm_seq_fwd(P(gx), P(w), P(b_ih), P(b_hh), P(h0), P(c0), P(h_all), P(c_all), P(act), T, N, H, 0, S())
     gxd = gx.double().requires_grad_(True)
     wd = w.double()
     h = h0.double() if with_state else torch.zeros(N, H, device=DEV, dtype=torch.float64)
     c = c0.double() if with_state else torch.zeros(N, H, device=DEV, dtype=torch.float64)
     hs, cs = [], []
-    for t in range(S):
+    for t in range(T):
         gates = gxd[t * N:(t + 1) * N] + h @ wd.t() + b_ih.double() + b_hh.double()
         i, f, gg, o = gates.chunk(4, dim=1)
         c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
@@ -501,8 +501,8 @@ def check_lstm_seq(S, N, H, with_state=False):
     out = [("lstm_seq fwd h " + tag, relerr(h_all, h_ref.detach()), 1e-5),
            ("lstm_seq fwd c " + tag, relerr(c_all, c_ref.detach()), 1e-5)]
     if not with_state:
-        dg = torch.full((S * N, 4 * H), float("nan"), device=DEV)
-        L.pe_lstm_seq_bwd(P(dh), P(w), P(act), P(c_all), None, P(dg), S, N, H, 0, S())
+        dg = torch.full((T * N, 4 * H), float("nan"), device=DEV)
+        L.pe_lstm_seq_bwd(P(dh), P(w), P(act), P(c_all), None, P(dg), T, N, H, 0, S())
         (h_ref * dh.double()).sum().backward()
         out.append(("lstm_seq bwd dgates " + tag, relerr(dg, gxd.grad), 1e-5))
     return out

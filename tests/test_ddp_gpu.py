@@ -25,3 +25,13 @@ def test_two_gpu_gradients_equal_summed_per_shard_oracle():
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "oracle step 1" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_bucketed_update_matches_plain_path():
+    """Overlapped reduce + per-bucket optimizer update (FusedTrainer.step) == plain all-reduce + one update."""
+    r = _torchrun(["tdo", "--step"])
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "fused step 2" in r.stdout
