@@ -21,7 +21,7 @@ namespace {
 
 constexpr int LS_THREADS = 256;
 constexpr int LS_ROWS = 32;          // rows of h_{t-1} staged per forward chunk
-constexpr int LS_BROWS = 8;          // rows of dgates_t staged per backward chunk (one warp per row)
+constexpr int LS_BROWS = 16;         // rows of dgates_t staged per backward chunk (each of the 8 warps takes two)
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -76,6 +76,26 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks, in
     return s_ok != 0;
 }
 
+// Contiguous rows global (L2) -> shared memory, n4 float4s, with four independent loads in flight per thread (a plain
+// load-store loop serialises on the L2 latency: 16 round trips per chunk).
+__device__ __forceinline__ void stage_rows(float* dst, const float* src, int n4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int base = threadIdx.x; base < n4; base += 4 * LS_THREADS) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * LS_THREADS;
+            if (idx < n4) v[u] = __ldcg(s4 + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * LS_THREADS;
+            if (idx < n4) d4[idx] = v[u];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
@@ -109,12 +129,8 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const LstmS
         for (int r0 = 0; r0 < p.N; r0 += LS_ROWS) {
             const int nr = min(LS_ROWS, p.N - r0);
             if (h_prev) {
-                for (int idx = threadIdx.x; idx < nr * (H / 4); idx += LS_THREADS) {
-                    const int r = idx / (H / 4), k4 = idx % (H / 4);
-                    // written by other CTAs during the previous timestep: read through L2
-                    *reinterpret_cast<float4*>(s_h + r * H + 4 * k4) =
-                        __ldcg(reinterpret_cast<const float4*>(h_prev + (long long)(r0 + r) * H) + k4);
-                }
+                // written by other CTAs during the previous timestep: read through L2, four loads in flight per thread
+                stage_rows(s_h, h_prev + (long long)r0 * H, nr * (H / 4));
                 __syncthreads();
                 if (slot < nslots) {
                     for (int r = slot; r < nr; r += 2 * nslots) {
@@ -233,17 +249,13 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const LstmS
         const float* dgt = p.dg + (long long)t * p.N * G;
         for (int n0 = 0; n0 < p.N; n0 += LS_BROWS) {
             const int nr = min(LS_BROWS, p.N - n0);
-            for (int idx = threadIdx.x; idx < nr * (G / 4); idx += LS_THREADS) {
-                const int r = idx / (G / 4), k4 = idx % (G / 4);
-                *reinterpret_cast<float4*>(s_dg + r * G + 4 * k4) =
-                    __ldcg(reinterpret_cast<const float4*>(dgt + (long long)(n0 + r) * G) + k4);
-            }
+            stage_rows(s_dg, dgt + (long long)n0 * G, nr * (G / 4));
             __syncthreads();
-            if (warp < nr) {                           // one warp per staged row, lanes split the 4H reduction
+            for (int rw = warp; rw < nr; rw += LS_THREADS / 32) {      // a warp per staged row, lanes split the 4H sum
                 float acc[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-                const float* dr = s_dg + warp * G;
+                const float* dr = s_dg + rw * G;
                 for (int r = lane; r < G; r += 32) {
                     const float d = dr[r];
                     const float* w = s_wt + r * U;
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const LstmS
                 for (int u = 0; u < 8; ++u) {
                     if (u < U) {
                         const float v = warp_sum(acc[u]);
-                        if (lane == 0) s_dhr[(n0 + warp) * U + u] = v;
+                        if (lane == 0) s_dhr[(n0 + rw) * U + u] = v;
                     }
                 }
             }

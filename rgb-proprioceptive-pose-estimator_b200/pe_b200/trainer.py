@@ -81,6 +81,8 @@ class FusedTrainer:
         self.t = 0
         self._flat = None
         self.comm_stream = None
+        self.reducer = None
+        self._fused_update = False
 
     # ------------------------------------------------------------------------------------------
     def _flatten(self):
@@ -142,6 +144,8 @@ class FusedTrainer:
         Multi-GPU: from the second step on, every all-reduce bucket is followed on the communication stream by the
         optimizer update of exactly that arena range, so reducing and updating the head / layer4 / layer3 buckets
         overlaps the backward pass of the earlier layers; only the last (stem-side, <= bucket_mb) bucket is exposed."""
+        if self._flat is None:
+            self._flatten()
         self._fused_update = self.reducer is not None and self.t > 0
         try:
             loss = self.forward_backward(img, self_measurement, targets, depth)

@@ -93,6 +93,9 @@ def main():
     from pe_b200.trainer import invalidate_core
     if "--oracle" in sys.argv:
         ok = oracle_check(kind, ta, a, img, x0, tgt, lk, rank, dev)
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0 if ok else 1
     for step in range(3):                       # step 0: single all-reduce; steps 1-2: overlapped buckets
         if step > 0:                            # same parameters everywhere: only the reduction is under test
             for t in (tb, tc):
