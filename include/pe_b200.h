@@ -36,6 +36,10 @@ void pe_debug_flags(int flags);
 /* CTA pairs (tcgen05 cta_group::2, 256-row MMAs over two SMs): 0 automatic (wide tiles of large launches), 1 never,
  * 2 whenever the launch allows it */
 void pe_debug_cta_group(int mode);
+/* Number of SMs the persistent tap-GEMM grids leave unused (0 = none).  The data-parallel trainer sets it during the
+ * backward pass, while NCCL gradient all-reduce kernels share the GPU: a one-CTA-per-SM grid that needs every SM
+ * would wait for the collective's CTAs and finish with a straggler wave. */
+void pe_set_sm_reserve(int sms);
 /* debug: force the smem split of the tap-GEMM (ring stages x 32 KB + nout x 16 KB <= 223 KB); 0 = default */
 void pe_debug_pipeline(int stages, int nout);
 /* debug: cap the tile width (128 or 256 columns) */

@@ -13,6 +13,7 @@
 namespace pe {
 
 extern int g_pdl;      // pe_tapgemm.cu: programmatic dependent launch switch
+extern int g_sm_reserve;   // pe_tapgemm.cu: SMs the persistent grids leave to a concurrent collective
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing
@@ -777,6 +778,8 @@ void pe_debug_epilogue_groups(int groups) { g_dbg_epi_groups = groups; }
 void pe_debug_pdl(int mask) { pe::g_pdl = mask & 3; }
 
 void pe_debug_cta_group(int mode) { g_dbg_cta_group = mode; }
+
+void pe_set_sm_reserve(int sms) { pe::g_sm_reserve = sms > 0 ? sms : 0; }
 
 void pe_debug_conv_halo(int on) {
     g_dbg_conv_halo = on & 1;

@@ -896,6 +896,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
 }  // namespace
 
 int g_pdl = -1;     // programmatic dependent launch (pe_debug_pdl); -1 = not read from the environment yet
+int g_sm_reserve = 0;   // SMs left free by the persistent tap-GEMM grids (pe_set_sm_reserve)
 
 bool pdl_enabled(int kind) {
     if (g_pdl < 0) {
@@ -935,7 +936,10 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
     p.work_m = work.y;
     p.work_total = static_cast<int>(work.x * work.y * work.z);
     // one CTA per SM, or one CTA pair per TPC (the work list then counts pairs of tiles)
-    const int slots = p.cta_group == 2 ? num_sms() / 2 : num_sms();
+    // (minus the SMs set aside for a concurrent collective: a persistent grid that needs EVERY SM would otherwise wait
+    // for the NCCL kernel's CTAs and run its last tiles as a second wave)
+    const int sms = num_sms() - g_sm_reserve > 8 ? num_sms() - g_sm_reserve : num_sms();
+    const int slots = p.cta_group == 2 ? sms / 2 : sms;
     int grid = p.work_total < slots ? p.work_total : slots;
     if (grid < 1) return 0;
     cudaLaunchConfig_t cfg = {};

@@ -67,7 +67,7 @@ class FusedTrainer:
 
     def __init__(self, model, distance_metric="l2", alpha=1.0, epsilon=1e-4, scale_factor=1.0, mode="pose",
                  lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, optimizer="adam", momentum=0.0,
-                 process_group=None, bucket_mb=8):
+                 process_group=None, bucket_mb=8, sm_reserve=None):
         if mode not in ("pose", "position"):
             raise ValueError("training loss mode must be 'pose' or 'position'")
         self.model = model
@@ -78,6 +78,9 @@ class FusedTrainer:
         self.optimizer, self.momentum = optimizer, momentum
         self.pg = process_group
         self.bucket_bytes = bucket_mb << 20
+        # SMs the persistent GEMM grids leave to the NCCL kernels during the backward pass (multi-GPU only)
+        import os
+        self.sm_reserve = int(os.environ.get("PE_B200_SM_RESERVE", "0")) if sm_reserve is None else sm_reserve
         self.t = 0
         self._flat = None
         self.comm_stream = None
@@ -212,7 +215,13 @@ class FusedTrainer:
                 for pid, (o, n) in self.param_offsets.items():
                     if pid not in self.touched:
                         red.ready(o, o + (n + _ALIGN - 1) // _ALIGN * _ALIGN)
-            core.backward(saved, tuple(douts), self.grad_of, self._on_ready if self.t > 0 else None)
+            if self.sm_reserve and self.t > 0:
+                L.pe_set_sm_reserve(self.sm_reserve)
+            try:
+                core.backward(saved, tuple(douts), self.grad_of, self._on_ready if self.t > 0 else None)
+            finally:
+                if self.sm_reserve:
+                    L.pe_set_sm_reserve(0)
             red.wait()
         else:
             core.backward(saved, tuple(douts), self.grad_of)

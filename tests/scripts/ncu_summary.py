@@ -9,7 +9,9 @@ import sys
 WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__grid_size",
+        "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__cluster_dim_x", "launch__grid_size",
         "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic"]
 SCALE_T = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
 SCALE_B = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
