@@ -1148,23 +1148,47 @@ depth_features_bwd_kernel(float* __restrict__ dprod, int ld, const float* __rest
     }
 }
 
+// One thread converts FOUR consecutive pixels of a cropped row: 12 contiguous source bytes (three aligned 32-bit loads
+// when the row start allows it) -> one 128-bit store per colour plane.  ToTensor's x / 255 followed by Normalize's
+// (x - mean) / std with true divisions, like the reference's transform (util/data_utils.py:48-54): bit-identical to
+// torchvision on the same uint8 frame.
 __global__ void preprocess_u8_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int B, int Hs,
                                      int Ws, int crop, float m0, float m1, float m2, float s0, float s1, float s2) {
-    const long long n = (long long)B * crop * crop;
+    const int q = crop >> 2;                                  // 4-pixel groups per row (crop % 4 == 0)
+    const long long n = (long long)B * crop * q;
     const long long gs = (long long)gridDim.x * blockDim.x;
     const int oy = (Hs - crop) / 2, ox = (Ws - crop) / 2;
+    const long long plane = (long long)crop * crop;
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
-        const int x = (int)(i % crop);
-        const int y = (int)((i / crop) % crop);
-        const int b = (int)(i / ((long long)crop * crop));
-        const unsigned char* p = src + (((long long)b * Hs + (y + oy)) * Ws + (x + ox)) * 3;
-        const long long plane = (long long)crop * crop;
-        float* o = dst + (long long)b * 3 * plane + (long long)y * crop + x;
-        // ToTensor's x / 255 followed by Normalize's (x - mean) / std, with true divisions like the reference's
-        // transform (util/data_utils.py:48-54): bit-identical to torchvision on the same uint8 frame
-        o[0] = __fdiv_rn(__fdiv_rn((float)p[0], 255.f) - m0, s0);
-        o[plane] = __fdiv_rn(__fdiv_rn((float)p[1], 255.f) - m1, s1);
-        o[2 * plane] = __fdiv_rn(__fdiv_rn((float)p[2], 255.f) - m2, s2);
+        const int xg = (int)(i % q);
+        const int y = (int)((i / q) % crop);
+        const int b = (int)(i / ((long long)q * crop));
+        const unsigned char* p = src + (((long long)b * Hs + (y + oy)) * Ws + (4 * xg + ox)) * 3;
+        unsigned char px[12];
+        if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+            const unsigned* w = reinterpret_cast<const unsigned*>(p);
+            const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                px[k] = (unsigned char)(w0 >> (8 * k));
+                px[4 + k] = (unsigned char)(w1 >> (8 * k));
+                px[8 + k] = (unsigned char)(w2 >> (8 * k));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) px[k] = p[k];
+        }
+        float* o = dst + (long long)b * 3 * plane + (long long)y * crop + 4 * xg;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float4 v;
+            v.x = __fdiv_rn(__fdiv_rn((float)px[c], 255.f) - mean[c], sd[c]);
+            v.y = __fdiv_rn(__fdiv_rn((float)px[3 + c], 255.f) - mean[c], sd[c]);
+            v.z = __fdiv_rn(__fdiv_rn((float)px[6 + c], 255.f) - mean[c], sd[c]);
+            v.w = __fdiv_rn(__fdiv_rn((float)px[9 + c], 255.f) - mean[c], sd[c]);
+            *reinterpret_cast<float4*>(o + c * plane) = v;
+        }
     }
 }
 
@@ -1476,7 +1500,9 @@ int pe_depth_features_bwd(float* dprod, int ld, const float* aux_pre, const floa
 int pe_preprocess_u8(const unsigned char* src, float* dst, int B, int Hs, int Ws, int crop, const float* mean3,
                      const float* std3, void* stream) {
     PE_REQUIRE(crop <= Hs && crop <= Ws, "preprocess: crop larger than frame");
-    const long long n = (long long)B * crop * crop;
+    PE_REQUIRE(crop % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+               "preprocess: crop must be a multiple of 4 and the output 16-byte aligned");
+    const long long n = (long long)B * crop * (crop / 4);
     preprocess_u8_kernel<<<grid_for(n, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
         src, dst, B, Hs, Ws, crop, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
     PE_LAUNCH_CHECK();

@@ -247,6 +247,33 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const LstmS
         if (!ok) break;
         // ---- dh_rec[:, own units] = dgates_t W_hh[:, own units] ---------------------------------------------
         const float* dgt = p.dg + (long long)t * p.N * G;
+        if (U == 4 && (G & 255) == 0) {
+            // a warp per row, straight from L2 (every CTA reads all of dgates_t; it was written this very step and
+            // sits in L2): lane l owns the gate rows l + 32 i -- coalesced 128-byte loads of the row, conflict-free
+            // 128-bit reads of the resident W_hh column slice (one float4 = the four own units of gate row r)
+            const float4* wt4 = reinterpret_cast<const float4*>(s_wt);
+            for (int n = warp; n < p.N; n += LS_THREADS / 32) {
+                const float* dr = dgt + (long long)n * G;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r0 = 0; r0 < G; r0 += 256) {
+                    float d[8];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) d[v] = __ldcg(dr + r0 + 32 * v + lane);
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const float4 w = wt4[r0 + 32 * v + lane];
+                        acc.x = fmaf(d[v], w.x, acc.x);
+                        acc.y = fmaf(d[v], w.y, acc.y);
+                        acc.z = fmaf(d[v], w.z, acc.z);
+                        acc.w = fmaf(d[v], w.w, acc.w);
+                    }
+                }
+                acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+                if (lane == 0) *reinterpret_cast<float4*>(s_dhr + n * 4) = acc;
+            }
+            __syncthreads();
+            continue;
+        }
         for (int n0 = 0; n0 < p.N; n0 += LS_BROWS) {
             const int nr = min(LS_BROWS, p.N - n0);
             stage_rows(s_dg, dgt + (long long)n0 * G, nr * (G / 4));
