@@ -75,6 +75,14 @@ int pe_conv2d_fwd(const float* x, const float* w_tck, float* y, int B, int H, in
 int pe_conv2d_dgrad(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin, int Cout,
                     int R, int S, int stride, int pad, const float* residual, const unsigned* res_maskbits,
                     void* stream);
+/* dgrad whose output dx is the gradient of a BatchNorm + ReLU activation a = relu(bn(y)) (bn1 -> conv2, bn2 -> conv3 of
+ * a Bottleneck, torchvision resnet.py:143-163): the epilogue also accumulates that BatchNorm's backward sums
+ * bn_sums[2*Cin] += (sum g, sum g * xhat), g = dx * (y * bn_scale + bn_shift > 0), xhat = (y - mean) * invstd, from the
+ * y tile it prefetches by TMA -- pass 1 of the BatchNorm backward (pe_bn_bwd_reduce) without its own launch and without
+ * a second read of dx.  bn_scale / bn_shift are the forward's folded coefficients; the caller zeroes bn_sums. */
+int pe_conv2d_dgrad_bn(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin, int Cout, int R,
+                       int S, int stride, int pad, const float* bn_y, const float* bn_scale, const float* bn_shift,
+                       const float* bn_mean, const float* bn_invstd, double* bn_sums, void* stream);
 int pe_conv2d_wgrad(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin, int Cout,
                     int R, int S, int stride, int pad, void* stream);
 /* OIHW (checkpoint layout, util/model_utils.py:136-141) <-> packed tap-major layouts */

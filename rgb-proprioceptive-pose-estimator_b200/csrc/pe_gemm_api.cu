@@ -202,7 +202,8 @@ static void pick_pipeline(TapParams& p, int ksteps) {
     p.stage_bytes = TG_A_BYTES + (p.bn / (p.cta_group == 2 ? 2 : 1) > 128 ? 32768 : 16384);
     p.stats_cols = p.stats ? (p.n_total + 31) / 32 * 32 : 0;
     // residual tiles are prefetched by TMA (two 16 KB buffers per epilogue group) when the output goes out by TMA
-    p.nres = (p.residual && p.store_mode == TG_STORE_TMA && g_dbg_res_tma) ? 4 : 0;
+    // (bn_bwd mode reads its y tile only at the end of a chunk's work: one buffer per group, requested a chunk ahead)
+    p.nres = (p.residual && p.store_mode == TG_STORE_TMA && (g_dbg_res_tma || p.bn_bwd)) ? (p.bn_bwd ? 2 : 4) : 0;
     const int budget = TG_SMEM_BYTES - (p.stats ? 2 * p.stats_cols * (int)sizeof(float) + 8192 : 0) - p.nres * TG_A_BYTES;
     // Store-bound launches (training-mode conv with batch statistics, wide tile, short K loop) are limited by the
     // epilogue's instruction latency, not by HBM: they run four epilogue groups (16 warps) instead of two.
@@ -271,6 +272,16 @@ static void pick_pipeline_halo(TapParams& p) {
     if (p.stages > 4) p.stages = 4;
     p.b_ring_bytes = p.b_stages * p.b_bytes;
 }
+
+// BatchNorm backward sums fused into a dgrad (TapParams::bn_bwd)
+struct BnBwd {
+    const float* y = nullptr;          // input of the BatchNorm + ReLU whose output gradient the dgrad produces
+    const float* scale = nullptr;      // forward's folded coefficients (ReLU mask: y * scale + shift > 0)
+    const float* shift = nullptr;
+    const float* mean = nullptr;
+    const float* invstd = nullptr;
+    double* sums = nullptr;            // [2][Cin] += (sum g, sum g * xhat)
+};
 
 struct Epilogue {
     const float* bias = nullptr;
@@ -389,10 +400,14 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
 // ---------------------------------------------------------------------------------------------
 static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin,
                            int Cout, int R, int S, int stride, int pad, const float* residual,
-                           const unsigned* res_mask, cudaStream_t stream) {
+                           const unsigned* res_mask, cudaStream_t stream, const BnBwd* bnb = nullptr) {
     if (ensure_error_flag()) return 2;
     PE_REQUIRE(!residual || (R == 1 && S == 1 && stride == 1 && pad == 0),
                "conv_dgrad: the residual epilogue is implemented for 1x1 stride-1 convolutions only");
+    PE_REQUIRE(!bnb || (!residual && bnb->y && bnb->scale && bnb->shift && bnb->mean && bnb->invstd && bnb->sums &&
+                        Cin % 32 == 0),
+               "conv_dgrad: fused BatchNorm backward sums need y, scale, shift, mean, invstd, sums, Cin %% 32 == 0 and "
+               "no residual");
     PE_REQUIRE(!res_mask || (residual && Cin % 32 == 0 && (reinterpret_cast<uintptr_t>(res_mask) & 15) == 0),
                "conv_dgrad: residual mask needs a residual, Cin %% 32 == 0 and a 16-byte aligned mask");
     const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
@@ -432,7 +447,7 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             p.n_taps = t;
             // stride-1 3x3: dy has the shape of dx, tap (r, s) reads dy at (h + pad - r, w + pad - s), i.e. at
             // row 2*pad - r / column 2*pad - s of the haloed tile
-            const bool halo = stride == 1 && !residual && setup_conv_halo(p, B, Ho, Wo, Cout, R, S, pad);
+            const bool halo = stride == 1 && !residual && !bnb && setup_conv_halo(p, B, Ho, Wo, Cout, R, S, pad);
             if (halo) {
                 for (int k = 0; k < t; ++k) {
                     p.tap_dh[k] = (signed char)(p.tap_dh[k] + pad);
@@ -461,11 +476,20 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
             if (make_map(&maps.b[0], w_tkc, dims, strides, bbox)) return 1;
             if (make_nhwc_map(&maps.d, dx, B, H, W, Cin, ph, pw, stride, box)) return 1;
             if (residual && make_nhwc_map(&maps.r, residual, B, H, W, Cin, ph, pw, stride, box)) return 1;
+            if (bnb && make_nhwc_map(&maps.r, bnb->y, B, H, W, Cin, ph, pw, stride, box)) return 1;
             p.n_total = Cin;
             p.store_mode = TG_STORE_TMA;
-            p.residual = residual;
+            p.residual = bnb ? bnb->y : residual;
             p.res_mask = res_mask;
             p.ld_res = Cin;
+            if (bnb) {
+                p.bn_bwd = 1;
+                p.scale = bnb->scale;
+                p.shift = bnb->shift;
+                p.bn_mean = bnb->mean;
+                p.bn_invstd = bnb->invstd;
+                p.stats = bnb->sums;
+            }
             if (halo) {
                 pick_pipeline_halo(p);
                 for (int k = 0; k < t; ++k) PE_REQUIRE(p.tap_b[k] == k, "conv_dgrad halo: taps out of order");
@@ -831,6 +855,20 @@ int pe_conv2d_dgrad(const float* dy, const float* w_tkc, float* dx, int B, int H
                     void* stream) {
     return conv_dgrad_impl(dy, w_tkc, dx, B, H, W, Cin, Cout, R, S, stride, pad, residual, res_maskbits,
                            (cudaStream_t)stream);
+}
+
+int pe_conv2d_dgrad_bn(const float* dy, const float* w_tkc, float* dx, int B, int H, int W, int Cin, int Cout, int R,
+                       int S, int stride, int pad, const float* bn_y, const float* bn_scale, const float* bn_shift,
+                       const float* bn_mean, const float* bn_invstd, double* bn_sums, void* stream) {
+    BnBwd b;
+    b.y = bn_y;
+    b.scale = bn_scale;
+    b.shift = bn_shift;
+    b.mean = bn_mean;
+    b.invstd = bn_invstd;
+    b.sums = bn_sums;
+    return conv_dgrad_impl(dy, w_tkc, dx, B, H, W, Cin, Cout, R, S, stride, pad, nullptr, nullptr, (cudaStream_t)stream,
+                           &b);
 }
 
 int pe_conv2d_wgrad(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin, int Cout,

@@ -125,6 +125,8 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     __shared__ uint32_t s_tmem_base;
     __shared__ __align__(16) float s_scale[TG_MAX_BN];
     __shared__ __align__(16) float s_shift[TG_MAX_BN];
+    __shared__ __align__(16) float s_mean[TG_MAX_BN];      // bn_bwd mode: batch mean / 1/std of the output columns
+    __shared__ __align__(16) float s_istd[TG_MAX_BN];
 
     // broadcast from lane 0: lets ptxas prove the role dispatch below is warp-uniform, which is what allows the
     // producer / MMA warps to keep their addresses and descriptors on the uniform datapath
@@ -559,14 +561,19 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         constexpr int SLOTS = (TG_MAX_BN / 32 + G - 1) / G;      // chunks of one tile a group can own
         const int nbuf = p.nout / G > 0 ? p.nout / G : 1;        // staging buffers per group
         const uint32_t my_stage = stage_base + (p.nout >= G ? grp * nbuf : 0) * TG_A_BYTES;
-        const bool affine = (p.scale != nullptr) || (p.bias != nullptr);
+        // bn_bwd mode (dgrad whose output is the gradient of a BatchNorm + ReLU activation): the TMA-prefetched
+        // "residual" tile holds that BatchNorm's INPUT y and is not added; the statistics pass accumulates the
+        // BatchNorm backward sums  sum g, sum g * xhat  with  g = dx * (y * scale + shift > 0)  instead of sum / sum^2
+        const bool bnb = p.bn_bwd != 0;
+        const bool affine = !bnb && ((p.scale != nullptr) || (p.bias != nullptr));
         uint32_t tile_i = 0, cc = 0;
         bool ok = true;
         // ---- residual tiles by TMA: this group's chunk sequence is prefetched two chunks ahead into its two
         //      16 KB buffers (swizzled like the staging tile, so each thread reads back its own row conflict-free)
         const bool res_tma = p.nres > 0;
         const int res_chunks = (p.bn + 31) >> 5;
-        const uint32_t my_res = res_base + grp * 2 * TG_A_BYTES;
+        const uint32_t rbufs = static_cast<uint32_t>(p.nres / G > 0 ? p.nres / G : 1);   // prefetch buffers per group
+        const uint32_t my_res = res_base + grp * rbufs * TG_A_BYTES;
         uint32_t rq = 0;                      // residual chunks consumed by this group
         int pw = w_first, pc = grp;           // next chunk to prefetch (work item, chunk)
         auto res_issue = [&](uint32_t buf) {  // called by one thread
@@ -583,8 +590,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             }
         };
         if (res_tma && et == 0) {
-            res_issue(0);
-            res_issue(1);
+            for (uint32_t b = 0; b < rbufs; ++b) res_issue(b);
         }
         if (p.stats) {
             for (int cidx = eall; cidx < 2 * p.stats_cols; cidx += EPI_THREADS) s_sum[cidx] = 0.f;
@@ -598,7 +604,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             if (wk.nk > 0) ++tile_i;
 
             // per-tile column constants (everyone is past the previous tile's reads after this barrier)
-            if (affine) {
+            if (affine || bnb) {
                 asm volatile("bar.sync %0, %1;" ::"n"(BAR_ALL), "n"(EPI_THREADS) : "memory");
                 for (int cidx = eall; cidx < p.bn; cidx += EPI_THREADS) {
                     const int col = n_off + cidx;
@@ -610,6 +616,13 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         } else {
                             sh = p.bias[col];
                         }
+                        if (bnb) {
+                            s_mean[cidx] = p.bn_mean[col];
+                            s_istd[cidx] = p.bn_invstd[col];
+                        }
+                    } else if (bnb) {
+                        s_mean[cidx] = 0.f;
+                        s_istd[cidx] = 0.f;
                     }
                     s_scale[cidx] = sc;
                     s_shift[cidx] = sh;
@@ -694,9 +707,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         v[i + 3] = fmaf(v[i + 3], sc4.w, sh4.w);
                     }
                 }
-                if (res_tma) {
-                    const uint32_t buf = rq & 1;
-                    if (!mbar_wait(smem_u32(&s_res_full[grp * 2 + buf]), (rq >> 1) & 1)) {
+                if (res_tma && !bnb) {
+                    const uint32_t buf = rq % rbufs;
+                    if (!mbar_wait(smem_u32(&s_res_full[grp * 2 + buf]), (rq / rbufs) & 1)) {
                         atomicOr(p.error_flag, 32);
                         ok = false;
                         break;
@@ -770,9 +783,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                    if (res_tma) {
-                        // every thread of the group has read residual buffer (rq & 1): refill it two chunks ahead
-                        if (et == 0) res_issue(rq & 1);
+                    if (res_tma && !bnb) {
+                        // every thread of the group has read residual buffer rq % rbufs: refill it `rbufs` chunks ahead
+                        if (et == 0) res_issue(rq % rbufs);
                         ++rq;
                     }
                     const uint32_t rbase = region + row * 128;
@@ -797,16 +810,58 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     if (p.stats) {
                         const int cg = et & 7, rg = et >> 3;
                         float4 sm = make_float4(0.f, 0.f, 0.f, 0.f), sq = sm;
+                        if (bnb) {
+                            // BatchNorm backward sums over the staged dx tile and the prefetched y tile (same swizzled
+                            // layout): g = dx where the activation was positive, xhat = (y - mean) / std
+                            const float4 sc4 = *reinterpret_cast<const float4*>(&s_scale[c * 32 + cg * 4]);
+                            const float4 sh4 = *reinterpret_cast<const float4*>(&s_shift[c * 32 + cg * 4]);
+                            const float4 mu4 = *reinterpret_cast<const float4*>(&s_mean[c * 32 + cg * 4]);
+                            const float4 is4 = *reinterpret_cast<const float4*>(&s_istd[c * 32 + cg * 4]);
+                            // the y tile of this chunk was requested one chunk ago (ONE buffer per group is enough:
+                            // it is consumed only here, at the end of the chunk's work)
+                            const uint32_t ybuf = my_res + (rq % rbufs) * TG_A_BYTES;
+                            if (!mbar_wait(smem_u32(&s_res_full[grp * 2 + (rq % rbufs)]), (rq / rbufs) & 1)) {
+                                atomicOr(p.error_flag, 32);
+                                ok = false;
+                            }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const uint32_t addr = region + (rg * 8 + i) * 128 + ((cg ^ i) << 4);
-                            float4 t;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                                         : "r"(addr));
-                            sm.x += t.x; sm.y += t.y; sm.z += t.z; sm.w += t.w;
-                            sq.x = fmaf(t.x, t.x, sq.x); sq.y = fmaf(t.y, t.y, sq.y);
-                            sq.z = fmaf(t.z, t.z, sq.z); sq.w = fmaf(t.w, t.w, sq.w);
+                            for (int i = 0; i < 8; ++i) {
+                                if (rg * 8 + i < p.m_rows) {          // rows past the box are not written by TMA
+                                    const uint32_t off = (rg * 8 + i) * 128 + ((cg ^ i) << 4);
+                                    float4 t, y;
+                                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                                 : "r"(region + off));
+                                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w)
+                                                 : "r"(ybuf + off));
+                                    const float gx = fmaf(y.x, sc4.x, sh4.x) > 0.f ? t.x : 0.f;
+                                    const float gy = fmaf(y.y, sc4.y, sh4.y) > 0.f ? t.y : 0.f;
+                                    const float gz = fmaf(y.z, sc4.z, sh4.z) > 0.f ? t.z : 0.f;
+                                    const float gw = fmaf(y.w, sc4.w, sh4.w) > 0.f ? t.w : 0.f;
+                                    sm.x += gx; sm.y += gy; sm.z += gz; sm.w += gw;
+                                    sq.x += gx * (y.x - mu4.x) * is4.x;
+                                    sq.y += gy * (y.y - mu4.y) * is4.y;
+                                    sq.z += gz * (y.z - mu4.z) * is4.z;
+                                    sq.w += gw * (y.w - mu4.w) * is4.w;
+                                }
+                            }
+                            // every thread of the group is done with the y buffer: request the next chunk's tile
+                            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                            if (et == 0) res_issue(rq % rbufs);
+                            ++rq;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t addr = region + (rg * 8 + i) * 128 + ((cg ^ i) << 4);
+                                float4 t;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                             : "r"(addr));
+                                sm.x += t.x; sm.y += t.y; sm.z += t.z; sm.w += t.w;
+                                sq.x = fmaf(t.x, t.x, sq.x); sq.y = fmaf(t.y, t.y, sq.y);
+                                sq.z = fmaf(t.z, t.z, sq.z); sq.w = fmaf(t.w, t.w, sq.w);
+                            }
                         }
                         // lanes {l, l^8, l^16, l^24} share cg: fold the four row groups of the warp
 #pragma unroll

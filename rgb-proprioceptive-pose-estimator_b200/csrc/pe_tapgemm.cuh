@@ -94,6 +94,13 @@ struct TapParams {
     // consecutive 128-pixel tiles (work_m counts PAIRS), each CTA loads its own A box and HALF of the B tile
     // (bn / 2 weight rows), the leader issues tcgen05.mma.cta_group::2 with M = 256 for both.
     int cta_group;
+    // bn_bwd (dgrad only): `residual` / maps.r hold the input y of the BatchNorm + ReLU whose OUTPUT gradient this
+    // launch produces; it is not added.  With scale / shift (the forward's folded coefficients), bn_mean / bn_invstd
+    // the statistics pass accumulates that BatchNorm's backward sums into stats[2][n_total] = (sum g, sum g * xhat),
+    // g = dx * (y * scale + shift > 0): bn_bwd_reduce without a second read of dx and without its own launch.
+    int bn_bwd;
+    const float* bn_mean;
+    const float* bn_invstd;
 };
 
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream);

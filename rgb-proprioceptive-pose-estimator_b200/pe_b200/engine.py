@@ -17,6 +17,9 @@ BN_MOMENTUM = 0.1
 # training forward: bn1 + ReLU + max pool + aux branch as one kernel (pe_stem_post_train); False = the three separate
 # kernels (kept for the kernel tests and as the reference the fused one is checked against)
 FUSED_STEM_TAIL = [True]
+# BatchNorm backward pass 1 (sum g, sum g * xhat) of bn1 / bn2 of every Bottleneck inside the epilogue of the dgrad that
+# produces their output gradient (conv2 / conv3 dgrad); False = the stand-alone pe_bn_bwd_reduce launch
+FUSE_BN_REDUCE = [True]
 # test hook: when set to a list, every training-mode convolution appends its raw output (an Act, execution order:
 # stem, then conv1 / conv2 / conv3 / downsample of each block) -- read by the parity tests (tests/model_checks.py)
 CAPTURE_CONV_OUTPUTS = [None]
@@ -29,11 +32,14 @@ def _dev_check(t):
 
 
 class Act:
-    """An NHWC activation: tensor [B*H*W, C] (contiguous) plus its geometry."""
-    __slots__ = ("t", "B", "H", "W", "C")
+    """An NHWC activation: tensor [B*H*W, C] (contiguous) plus its geometry.  `bn` = (BatchNorm index, its input
+    Act) when this activation is relu(bn(y)) without a residual input: the dgrad of its single consumer can then
+    accumulate that BatchNorm's backward sums in its epilogue (pe_conv2d_dgrad_bn)."""
+    __slots__ = ("t", "B", "H", "W", "C", "bn")
 
     def __init__(self, t, B, H, W, C):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.bn = None
 
     @property
     def P(self):
@@ -247,6 +253,8 @@ class TrunkEngine:
         native.account("pe_bn_train_apply", 4 * y.t.numel() * (2 + (residual is not None)) +
                        (4 * maskbits.numel() if maskbits is not None else 0))
         if tape is not None:
+            if relu and residual is None:
+                out.bn = (i, y)
             tape.append(("bn", i, y, out, relu, residual, maskbits))
         return out
 
@@ -396,6 +404,7 @@ class TrunkEngine:
                 done_after_conv[ids[1]] = [p for p in blk.parameters()]
         B = ctx["B"]
         slots = GradSlots()
+        reduced = {}          # BatchNorm index -> the dx tensor whose dgrad already accumulated its backward sums
         pending_aux = None
         dev = self.scale.device
         self.sums.zero_()
@@ -449,8 +458,14 @@ class TrunkEngine:
                     # without a residual input the ReLU mask is recomputed from y (one activation read less)
                     mask_src = out.t if (relu and residual is not None) else None
                     relu_k = int(relu)
-                L.pe_bn_bwd_reduce(P(d1), P(d2), P(mask_src), P(y.t), P(mean), P(invstd), P(sc), P(sh), P(mb),
-                                   P(sums), y.P, y.C, relu_k, st)
+                fused_here = i in reduced
+                if fused_here:
+                    # pass 1 already happened in the epilogue of the dgrad that produced d1
+                    if d1 is not reduced.pop(i) or d2 is not None or mb is not None:
+                        raise native.PeError("internal: fused BatchNorm sums do not match the gradient at hand")
+                else:
+                    L.pe_bn_bwd_reduce(P(d1), P(d2), P(mask_src), P(y.t), P(mean), P(invstd), P(sc), P(sh), P(mb),
+                                       P(sums), y.P, y.C, relu_k, st)
                 dres = None
                 if residual is not None and maskbits is None:
                     dres = torch.empty_like(y.t)
@@ -459,7 +474,8 @@ class TrunkEngine:
                                   y.P, y.C, relu_k, rt, st)
                 E = 4 * y.t.numel()
                 reads = E * (2 + (d2 is not None) + (mask_src is not None)) + (4 * mb.numel() if mb is not None else 0)
-                native.account("pe_bn_bwd_reduce", reads)
+                if not fused_here:
+                    native.account("pe_bn_bwd_reduce", reads)
                 native.account("pe_bn_bwd_apply", reads + E * (1 + (dres is not None)))
                 slots.add(y, dy)
                 if residual is not None:
@@ -485,8 +501,19 @@ class TrunkEngine:
                 if r == 1 and s == 1 and stride == 1 and slots.pending(x) == 1:
                     # the other gradient branch of x (identity / downsample path) is added in the dgrad epilogue
                     (res, res_mask), = slots.pop(x)
-                L.pe_conv2d_dgrad(P(dy), P(self.w_tkc[i]), P(dx), x.B, x.H, x.W, ci, co, r, s, stride, pad, P(res),
-                                  P(res_mask), st)
+                bn_src = x.bn if (FUSE_BN_REDUCE[0] and res is None and ci % 32 == 0 and
+                                  slots.pending(x) == 0) else None
+                if bn_src is not None:
+                    # x = relu(bn(y)) feeds this conv only: its BatchNorm's backward sums ride in this epilogue
+                    ib, yb = bn_src
+                    bsc, bsh, bmean, bistd, _, bsums = self._bn_views(ib, arena)
+                    L.pe_conv2d_dgrad_bn(P(dy), P(self.w_tkc[i]), P(dx), x.B, x.H, x.W, ci, co, r, s, stride, pad,
+                                         P(yb.t), P(bsc), P(bsh), P(bmean), P(bistd), P(bsums), st)
+                    reduced[ib] = dx
+                    native.account("pe_conv2d_dgrad", 4 * x.P * ci)          # the extra read of y
+                else:
+                    L.pe_conv2d_dgrad(P(dy), P(self.w_tkc[i]), P(dx), x.B, x.H, x.W, ci, co, r, s, stride, pad, P(res),
+                                      P(res_mask), st)
                 native.account("pe_conv2d_wgrad", 4 * (x.P * ci + y.P * co + conv.weight.numel()))
                 native.account("pe_conv2d_dgrad", 4 * (x.P * ci * (2 if res is not None else 1) + y.P * co +
                                                        conv.weight.numel()) +

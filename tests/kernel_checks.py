@@ -170,6 +170,35 @@ def check_conv(B, H, W, Cin, Cout, k, stride):
     return out
 
 
+def check_conv_dgrad_bn(B, H, W, Cin, Cout, k, stride):
+    """pe_conv2d_dgrad_bn: dx as the plain dgrad, plus the BatchNorm backward sums of the activation dx belongs to
+    (sum g, sum g * xhat with g = dx * (y * scale + shift > 0)) accumulated in the epilogue from the TMA-prefetched y."""
+    L = native.lib()
+    pad = (k - 1) // 2
+    g = torch.Generator(device=DEV).manual_seed(7 * B + H + Cin + Cout + k + stride)
+    w = tf32(torch.randn(Cout, Cin, k, k, device=DEV, generator=g) / (Cout * k * k) ** 0.5)
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    dy = tf32(torch.randn(B, Cout, Ho, Wo, device=DEV, generator=g))
+    gx = torch.nn.grad.conv2d_input((B, Cin, H, W), w.double(), dy.double(), stride=stride, padding=pad)
+    y = torch.randn(B, H, W, Cin, device=DEV, generator=g)
+    sc = torch.rand(Cin, device=DEV, generator=g) + 0.5
+    sh = torch.randn(Cin, device=DEV, generator=g) * 0.3
+    mean = torch.randn(Cin, device=DEV, generator=g) * 0.2
+    invstd = torch.rand(Cin, device=DEV, generator=g) + 0.5
+    _, tkc = pack(w)
+    dx = torch.full((B, H, W, Cin), float("nan"), device=DEV)
+    sums = torch.zeros(2 * Cin, device=DEV, dtype=torch.float64)
+    L.pe_conv2d_dgrad_bn(P(nhwc(dy)), P(tkc), P(dx), B, H, W, Cin, Cout, k, k, stride, pad, P(y), P(sc), P(sh), P(mean),
+                         P(invstd), P(sums), S())
+    tag = "B%d %dx%d %d->%d k%d s%d" % (B, H, W, Cin, Cout, k, stride)
+    gx_n = nhwc(gx)
+    mask = (torch.addcmul(sh, y, sc) > 0).double()          # same fp32 expression as the kernel's fmaf up to an ulp
+    gm = gx_n * mask
+    ref = torch.cat([gm.sum((0, 1, 2)), (gm * (y.double() - mean.double()) * invstd.double()).sum((0, 1, 2))])
+    return [("conv_dgrad_bn dx " + tag, relerr(dx, gx_n), 1e-4), ("conv_dgrad_bn sums " + tag, relerr(sums, ref), 2e-4)]
+
+
 def check_conv_fused_eval(B, H, W, Cin, Cout, k):
     """eval-mode epilogue: relu(acc*scale + shift + residual)."""
     L = native.lib()
@@ -736,6 +765,9 @@ ALL = [
     lambda: check_stem_tail(3, 1),
     lambda: check_lstm_cell(5, 512),
     lambda: check_loss(37),
+    lambda: check_conv_dgrad_bn(3, 28, 28, 128, 512, 1, 1) + check_conv_dgrad_bn(2, 56, 56, 64, 64, 3, 1),
+    lambda: check_conv_dgrad_bn(5, 14, 14, 256, 1024, 1, 1) + check_conv_dgrad_bn(3, 14, 14, 256, 256, 3, 1),
+    lambda: check_conv_dgrad_bn(2, 28, 28, 256, 256, 3, 2) + check_conv_dgrad_bn(3, 7, 7, 512, 2048, 1, 1),
     lambda: check_adam(100003),
     lambda: check_lstm_seq(20, 32, 512) + check_lstm_seq(3, 5, 64) + check_lstm_seq(10, 128, 512),
     lambda: check_lstm_seq(4, 7, 512, with_state=True) + check_lstm_seq(2, 1, 512),
