@@ -204,7 +204,8 @@ static void pick_pipeline(TapParams& p, int ksteps) {
     // residual tiles are prefetched by TMA (two 16 KB buffers per epilogue group) when the output goes out by TMA
     // (bn_bwd mode reads its y tile only at the end of a chunk's work: one buffer per group, requested a chunk ahead)
     p.nres = (p.residual && p.store_mode == TG_STORE_TMA && (g_dbg_res_tma || p.bn_bwd)) ? (p.bn_bwd ? 2 : 4) : 0;
-    const int budget = TG_SMEM_BYTES - (p.stats ? 2 * p.stats_cols * (int)sizeof(float) + 8192 : 0) - p.nres * TG_A_BYTES;
+    const int budget = TG_SMEM_BYTES - (p.stats ? 2 * p.stats_cols * (int)sizeof(float) + 8192 : 0) -
+                       (p.bn_bwd ? 2 * TG_MAX_BN * (int)sizeof(float) : 0) - p.nres * TG_A_BYTES;
     // Store-bound launches (training-mode conv with batch statistics, wide tile, short K loop) are limited by the
     // epilogue's instruction latency, not by HBM: they run four epilogue groups (16 warps) instead of two.
     // (the residual prefetch buffers are laid out for two groups: residual launches always run two)

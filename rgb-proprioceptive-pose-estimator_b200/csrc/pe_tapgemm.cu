@@ -125,8 +125,6 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     __shared__ uint32_t s_tmem_base;
     __shared__ __align__(16) float s_scale[TG_MAX_BN];
     __shared__ __align__(16) float s_shift[TG_MAX_BN];
-    __shared__ __align__(16) float s_mean[TG_MAX_BN];      // bn_bwd mode: batch mean / 1/std of the output columns
-    __shared__ __align__(16) float s_istd[TG_MAX_BN];
 
     // broadcast from lane 0: lets ptxas prove the role dispatch below is warp-uniform, which is what allows the
     // producer / MMA warps to keep their addresses and descriptors on the uniform datapath
@@ -144,6 +142,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     float* s_sq = s_sum + p.stats_cols;
     // per-tile scratch of the statistics: [group][chunk slot][warp 4][sum 32 | sq 32] (8 KB, only with stats)
     float* s_part = s_sum + 2 * p.stats_cols;
+    // bn_bwd mode: batch mean / 1/std of the tile's output columns (2 x TG_MAX_BN floats behind the 8 KB scratch)
+    float* s_mean = s_part + 2048;
+    float* s_istd = s_mean + TG_MAX_BN;
 
     // ---- one-time setup --------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -983,7 +984,8 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
         // statistics scratch (a violation here would be an out-of-bounds shared-memory access on the device)
         const long long need = (long long)p.stages * p.stage_bytes + p.b_ring_bytes +
                                (long long)(p.store_mode == TG_STORE_TMA ? p.nout + p.nres : 0) * TG_A_BYTES +
-                               (p.stats ? 2ll * p.stats_cols * (long long)sizeof(float) + 8192 : 0);
+                               (p.stats ? 2ll * p.stats_cols * (long long)sizeof(float) + 8192 : 0) +
+                               (p.bn_bwd ? 2ll * TG_MAX_BN * (long long)sizeof(float) : 0);
         PE_REQUIRE(p.stages >= 1 && need <= TG_SMEM_BYTES, "tap-GEMM shared-memory plan of %lld bytes does not fit in %d",
                    need, TG_SMEM_BYTES);
     }

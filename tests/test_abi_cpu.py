@@ -197,3 +197,25 @@ def test_head_descriptor_layout_matches_c():
     import ctypes
     from pe_b200 import native
     assert native.lib()._dll.pe_head_desc_size() == ctypes.sizeof(native.HeadDesc)
+
+
+def test_tapgemm_shared_memory_fits_the_sm():
+    """Static + dynamic shared memory of the tap-GEMM kernels must fit the 227 KB an sm_100 CTA can opt into: a static
+    array added to the kernel once pushed the total over the limit, which only shows on the GPU (cudaFuncSetAttribute
+    -> invalid argument).  Read the static part from the built library, the dynamic part from the header constant."""
+    import re
+    import subprocess
+    from pe_b200 import native
+    native.build()
+    out = subprocess.run(["cuobjdump", "-res-usage", native.LIB_PATH], capture_output=True, text=True).stdout
+    hdr = open(os.path.join(native.CSRC, "pe_tapgemm.cuh")).read()
+    dyn = int(re.search(r"TG_SMEM_BYTES\s*=\s*(\d+)\s*\*\s*1024", hdr).group(1)) * 1024
+    found = 0
+    lines = out.splitlines()
+    for i, line in enumerate(lines):
+        if "tapgemm_kernel" in line and i + 1 < len(lines):
+            m = re.search(r"SHARED:(\d+)", lines[i + 1])
+            assert m, lines[i + 1]
+            found += 1
+            assert int(m.group(1)) + dyn <= 227 * 1024, (line, m.group(1), dyn)
+    assert found >= 4, out[:500]
