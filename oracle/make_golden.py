@@ -1,7 +1,7 @@
 """Generate tests/golden/*.json from the UNMODIFIED reference modules (build container only).
 
 TEST INFRASTRUCTURE.  Run as `python oracle/make_golden.py` where /root/reference exists.  The fixtures
-pin (a) the oracle restatement (tests/test_golden.py, CPU) and (b) the CUDA path (tests/test_models_gpu.py)
+pin (a) the oracle restatement (tests/test_oracle_cpu.py, CPU) and (b) the CUDA path (tests/test_models_gpu.py)
 to what the reference's own code computes, on machines where the reference tree is not available.
 
 Contents

@@ -7,7 +7,7 @@ legs may import this file; the product path (rgb-proprioceptive-pose-estimator_b
 
 Parity pinning: the reference ships no tests or golden vectors for this path, so
 this restatement is pinned against (a) the reference's own modules imported from /root/reference in
-the build container (tests/test_oracle_vs_reference.py, skipped where the reference is absent) and
+the build container or from the shipped copy oracle/_ref (tests/test_oracle_cpu.py, skipped where neither exists) and
 (b) the fixtures under tests/golden/ that oracle/make_golden.py generated from those modules.
 
 Third-party arithmetic that is not under /root/reference (requirements.txt leaves torch/torchvision

@@ -738,7 +738,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                             v[4 * j + 3] += ((mb.w >> bit) & 1u) ? r4.w : 0.f;
                         }
                     }
-                } else if (res_row && row_valid) {
+                } else if (res_row && row_valid && !bnb) {
                     if (p.res_mask) {
                         // masked residual (identity branch of a residual join in backward): the eight float4s of
                         // this chunk sit in one 32-group of the bit mask (ld_res % 32 == 0, col0 % 32 == 0)
