@@ -481,6 +481,24 @@ def train_bench(h, kind, batch, seq, steps, warmup, pk, tf32_peak, main):
     fam_bytes = native.bytes_summary()
     native.enable_timing(False)
     L.check_device()
+    # The production step folds BatchNorm-backward reductions into 32 of the dgrad launches (pe_conv2d_dgrad_bn): that
+    # time is BN work done inside the GEMM kernel.  One more instrumented step with the fusion off gives the family's
+    # time as plain GEMMs (reported next to the production figure, never instead of it).
+    gemm_plain_ms = None
+    if main:
+        from pe_b200 import engine
+        engine.FUSE_BN_REDUCE[0] = False
+        try:
+            step_resident()
+            native.enable_timing(True)
+            step_resident()
+            torch.cuda.synchronize()
+            fam_plain = native.timing_summary()
+            native.enable_timing(False)
+            gemm_plain_ms = sum(v for k, v in fam_plain.items() if k in GEMM_FAMS)
+        finally:
+            engine.FUSE_BN_REDUCE[0] = True
+            native.enable_timing(False)
 
     value = world * frames * steps / (ms / 1e3)
     gemm_ms = sum(v for k, v in fam.items() if k in GEMM_FAMS)
@@ -537,6 +555,13 @@ def train_bench(h, kind, batch, seq, steps, warmup, pk, tf32_peak, main):
                      "launches_per_step": n_gemm,
                      "peak_source": tf32_peak["how"] + " (sustained); burst %.0f" % tf32_peak["burst"],
                      "measured_ms": round(gemm_ms, 3),
+                     "plain_gemm": None if not gemm_plain_ms else {
+                         "measured_ms": round(gemm_plain_ms, 3),
+                         "achieved": TRAIN_GFLOP_PER_FRAME[kind] * frames / 1e3 / (gemm_plain_ms / 1e3),
+                         "frac": TRAIN_GFLOP_PER_FRAME[kind] * frames / 1e3 / (gemm_plain_ms / 1e3) / tf32_peak["sustained"],
+                         "note": "same family with the BatchNorm-backward sums NOT folded into the dgrad epilogues "
+                                 "(one extra instrumented step): the production figure above carries that BN work, "
+                                 "which the step pays back in the pe_bn_bwd_reduce family"},
                      "share_of_step": gemm_ms / total_ms if total_ms else None,
                      "layerwise_bound": {"ms": round(lw_ms, 3), "measured_ms": round(gemm_ms, 3),
                                          "frac": round(lw_ms / gemm_ms, 3) if gemm_ms else None,
