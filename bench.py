@@ -623,6 +623,24 @@ def rollout_bench(h, batches=(1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)):
                         "h2d_bytes_per_step": img_h.numel() * 4 + 28, "d2h_bytes_per_step": 28,
                         "finite": bool(torch.isfinite(pose).all())})
         del est
+    # the reference-facing call itself: model(img, depth, x0bar) with host tensors in rollout mode, as the unchanged
+    # util/learn_utils.rollout() issues it (routed through the same captured step by the mirror)
+    model.rollout = True
+    model.reset_initial_state(1)
+    img_c = torch.randn(1, 1, 3, 224, 224, generator=g)
+    x0_c = torch.randn(1, 1, 7, generator=g)
+    for _ in range(5):
+        model(img_c, None, x0_c)
+    lat = []
+    for _ in range(200):
+        t0 = time.perf_counter()
+        pose = model(img_c, None, x0_c)
+        _ = pose.squeeze().detach().numpy()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    out["module_api_batch1_p50_ms"] = round(statistics.median(lat), 4)
+    out["module_api_batch1_p99_ms"] = round(lat[int(0.99 * len(lat))], 4)
+    model.rollout = False
     # raw uint8 frames at the largest batch (preprocessing inside the graph)
     N = batches[-1]
     est = StreamingEstimator(model, batch_size=N, use_graph=True, raw_hw=256)

@@ -67,21 +67,91 @@ def _inputs(model, img, depth, self_measurement):
     return (img, self_measurement)
 
 
+# The reference's rollout loop (util/learn_utils.py:366-455) calls model(img, depth, x0bar) once per simulator step with
+# one frame.  In that mode (model.rollout set, eval) the mirrors route the call through a CUDA-graph captured step
+# (pe_b200.rollout.StreamingEstimator): the same kernels, one graph launch instead of ~60 kernel launches.
+GRAPH_ROLLOUT = [True]
+GRAPH_ROLLOUT_MAX_FRAMES = 8
+
+
+def _drop_stream(model):
+    object.__setattr__(model, "_stream", None)
+
+
+def _graph_step(model, inputs, state):
+    """One captured rollout step, or None when the call is not eligible (depth input, many frames, a sequence)."""
+    if not GRAPH_ROLLOUT[0] or len(inputs) != 2 or inputs[1] is None:
+        return None
+    img, x0 = inputs
+    seq = bool(getattr(model, "requires_sequence", False))
+    if img.dim() != (5 if seq else 4) or (seq and img.shape[0] != 1) or tuple(img.shape[-3:]) != (3, 224, 224):
+        return None
+    n = img.shape[1] if seq else img.shape[0]
+    if n > GRAPH_ROLLOUT_MAX_FRAMES or img.dtype != torch.float32:
+        return None
+    from pe_b200.functions import compute_device
+    from pe_b200.rollout import StreamingEstimator
+    dev = compute_device(model)
+    cache = getattr(model, "_stream", None) or {}
+    est = cache.get(n)
+    if est is None:
+        # (the constructor calls model.eval(), which drops the cache attribute: it is re-attached below)
+        est = cache[n] = StreamingEstimator(model, batch_size=n, use_graph=True, device=dev)
+    object.__setattr__(model, "_stream", cache)
+
+    def load(dst, src):      # carried LSTM state: copy in unless the model already holds the estimator's own buffers
+        if isinstance(dst, tuple):
+            for d, s_ in zip(dst, src):
+                load(d, s_)
+        elif dst is not None and src is not None and src.data_ptr() != dst.data_ptr():
+            dst.copy_(src, non_blocking=True)
+    if state is not None:
+        load(est.state, state)
+    out = est.step(img, x0)
+    model._core.last_state = est.state
+    return out if isinstance(out, tuple) else (out,)
+
+
 def _run(model, core_cls, inputs, state=None):
     """Shared forward of the five mirrors: build the core lazily, stage host tensors to the compute device (and hand
     the outputs back on the host in that case, as the reference's rollout loop expects), run the kernels."""
     if model._core is None:
         object.__setattr__(model, "_core", core_cls(model))
-    inputs, host = stage_inputs(model, inputs)
-    outs = run_core(model._core, inputs, model.training, state,
-                    inference=bool(getattr(model, "rollout", False)) and not model.training)
+    inference = bool(getattr(model, "rollout", False)) and not model.training
+    host = any(t is not None and torch.is_tensor(t) and not t.is_cuda for t in inputs)
+    outs = _graph_step(model, inputs, state) if inference else None
+    if outs is not None:
+        # the captured step writes into static buffers: hand out copies (a host copy, or a 7-float device clone)
+        outs = tuple(o.cpu() if host else o.clone() for o in outs)
+    else:
+        inputs, host = stage_inputs(model, inputs)
+        outs = run_core(model._core, inputs, model.training, state, inference=inference)
+        if host:
+            outs = tuple(o.cpu() for o in outs)
     if host:
-        outs = tuple(o.cpu() for o in outs)
         native.lib().check_device()       # the host copy synchronised anyway: surface a pipeline timeout right here
     return outs
 
 
-class NaiveEndEffectorStateEstimator(nn.Module):
+class _MirrorBase(nn.Module):
+    """Bookkeeping shared by the five mirrors: anything that can change the weights or their device (switching to
+    train mode, loading a checkpoint, .cuda() / .to()) drops the captured rollout graphs, which hold packed shadows of
+    the weights."""
+
+    def train(self, mode=True):
+        _drop_stream(self)
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        _drop_stream(self)
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        _drop_stream(self)
+        return super().load_state_dict(*args, **kwargs)
+
+
+class NaiveEndEffectorStateEstimator(_MirrorBase):
     """
     One-shot estimator of the other arm's end-effector pose from an image and the active arm's own
     (noisy) pose measurement; mirror of reference models/naive.py:8-127.
@@ -107,6 +177,7 @@ class NaiveEndEffectorStateEstimator(nn.Module):
         self.n_post_hidden = len(post_dims) - 1
         self.rollout = False
         self._core = None
+        self._stream = None
 
     def forward(self, img, depth, self_measurement):
         """img (N,C,H,W), depth ignored, self_measurement (N,7) -> (pre_out (N,7), post_out (N,7))"""
@@ -121,7 +192,7 @@ class NaiveEndEffectorStateEstimator(nn.Module):
         return False
 
 
-class NaiveObjectStateEstimator(nn.Module):
+class NaiveObjectStateEstimator(_MirrorBase):
     """
     One-shot estimator of an object's pose from an eye-in-hand image and the arm's own (noisy) pose
     measurement; mirror of reference models/naive.py:130-367.
@@ -169,6 +240,7 @@ class NaiveObjectStateEstimator(nn.Module):
         self.n_fc = len(fc_dims) - 1
         self.rollout = False
         self._core = None
+        self._stream = None
 
     def forward(self, img, depth, self_measurement):
         """img (N,C,H,W), depth (N,1,H,W) when use_depth else ignored, self_measurement (N,7) -> pose (N,7)"""

@@ -10,7 +10,7 @@ starts from zeros otherwise (models/time_sensitive.py:501-507).
 import torch
 import torch.nn as nn
 
-from models.naive import _check_supported, _inputs, _probe_feature_layers, _run
+from models.naive import _MirrorBase, _check_supported, _inputs, _probe_feature_layers, _run
 from pe_b200.estimators import TDCore, TDOCore, TDOV2Core
 from pe_b200.functions import compute_device
 from util.model_utils import PassThroughParallel, import_resnet
@@ -24,7 +24,7 @@ def _state_2d(t, model):
                                                             dtype=torch.float32).contiguous()
 
 
-class TemporallyDependentStateEstimator(nn.Module):
+class TemporallyDependentStateEstimator(_MirrorBase):
     """
     Estimator of the other arm's end-effector pose with temporal context: trunk (+aux) features ->
     LSTM -> 7-D self estimate; (self estimate - measurement) joins the features -> LSTM -> 7-D pose.
@@ -79,6 +79,7 @@ class TemporallyDependentStateEstimator(nn.Module):
         self.post_out_vec = None
         self.rollout = False
         self._core = None
+        self._stream = None
 
     def forward(self, img, depth, self_measurement):
         """img (S,N,C,H,W), self_measurement (S,N,7) -> (pre_out (S,N,7), post_out (S,N,7))"""
@@ -106,7 +107,7 @@ class TemporallyDependentStateEstimator(nn.Module):
         return True
 
 
-class TemporallyDependentObjectStateEstimator(nn.Module):
+class TemporallyDependentObjectStateEstimator(_MirrorBase):
     """
     The paper's full model: trunk + aux features and the proprioceptive measurement feed one LSTM, then
     Linear(H, H//4) -> Linear(H//4, 7).  Mirror of reference models/time_sensitive.py:277-533.
@@ -161,6 +162,7 @@ class TemporallyDependentObjectStateEstimator(nn.Module):
         self.out_vec = None
         self.rollout = False
         self._core = None
+        self._stream = None
 
     def forward(self, img, depth, self_measurement):
         """img (S,N,C,H,W), self_measurement (S,N,7) -> pose (S,N,7)"""
@@ -183,7 +185,7 @@ class TemporallyDependentObjectStateEstimator(nn.Module):
         return True
 
 
-class TemporallyDependentObjectStateEstimatorV2(nn.Module):
+class TemporallyDependentObjectStateEstimatorV2(_MirrorBase):
     """
     TDO variant with one LSTM per sensor modality: image features (trunk + aux) and the proprioceptive
     measurement each run through their own LSTM; the hidden states are concatenated and fed to
@@ -242,6 +244,7 @@ class TemporallyDependentObjectStateEstimatorV2(nn.Module):
         self.out_vec = None
         self.rollout = False
         self._core = None
+        self._stream = None
 
     def forward(self, img, depth, self_measurement):
         """img (S,N,C,H,W), self_measurement (S,N,7) -> pose (S,N,7)"""

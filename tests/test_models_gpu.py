@@ -297,8 +297,10 @@ def test_fused_head_matches_gemm_head(kind):
     seq = kind in ("td", "tdo")
     n = 3
     res = {}
+    import models.naive as mn
     for fused in (True, False):
         est.FUSED_HEAD[0] = fused
+        mn._drop_stream(model)          # the captured rollout step bakes the head variant in
         try:
             if seq:
                 model.rollout = True
