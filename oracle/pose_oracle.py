@@ -252,6 +252,20 @@ def _bottleneck(x, sd, prefix, stride, training):
     return _rnd(F.relu(out + identity))
 
 
+def _basic_block(x, sd, prefix, stride, training):
+    """torchvision BasicBlock.forward (resnet.py:59-106; ResNet-18/34, reached through import_resnet(18, ...),
+    util/model_utils.py:130-136): two 3x3 convolutions, stride on the first."""
+    identity = x
+    out = _conv(x, sd[prefix + "conv1.weight"], stride=stride, padding=1)
+    out = _rnd(F.relu(_bn(out, sd, prefix + "bn1.", training)))
+    out = _conv(out, sd[prefix + "conv2.weight"], padding=1)
+    out = _bn(out, sd, prefix + "bn2.", training)
+    if prefix + "downsample.0.weight" in sd:
+        identity = _conv(x, sd[prefix + "downsample.0.weight"], stride=stride)
+        identity = _rnd(_bn(identity, sd, prefix + "downsample.1.", training))
+    return _rnd(F.relu(out + identity))
+
+
 def resnet50_forward(sd, prefix, img, training):
     """ResNet._forward_impl (torchvision resnet.py:266-282) with fc = Linear(2048, latent)
     (util/model_utils.py:139-141).  Returns (latent features, post-ReLU bn1 map).
@@ -270,8 +284,9 @@ def resnet50_forward(sd, prefix, img, training):
         # block count read from the checkpoint so that shallower Bottleneck stacks (used by the
         # well-conditioned gradient tests) run through the same code; 3/4/6/3 for ResNet-50
         blocks = len({k[len(prefix):].split(".")[1] for k in sd if k.startswith("%slayer%d." % (prefix, li))})
+        block = _bottleneck if ("%slayer%d.0.conv3.weight" % (prefix, li)) in sd else _basic_block
         for b in range(blocks):
-            x = _bottleneck(x, sd, "%slayer%d.%d." % (prefix, li, b), stride if b == 0 else 1, training)
+            x = block(x, sd, "%slayer%d.%d." % (prefix, li, b), stride if b == 0 else 1, training)
     x = _rnd(torch.flatten(F.adaptive_avg_pool2d(x, 1), 1))
     return _rnd(_linear(x, sd[prefix + "fc.weight"], sd[prefix + "fc.bias"])), early
 

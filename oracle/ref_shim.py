@@ -156,24 +156,24 @@ def build_reference_model(ref, kind, seed=0, **kw):
         if kind == "no":
             return ref.naive.NaiveObjectStateEstimator(
                 object_name=kw.get("object_name", "cube"), hidden_dims=kw.get("hidden_dims", [1024, 256, 64]),
-                num_resnet_layers=50, latent_dim=kw.get("latent_dim", 512), feature_extract=False,
+                num_resnet_layers=kw.get("num_resnet_layers", 50), latent_dim=kw.get("latent_dim", 512), feature_extract=False,
                 feature_layer_nums=(9,), use_depth=kw.get("use_depth", False), use_pretrained=False)
         if kind == "tdo":
             return ref.time_sensitive.TemporallyDependentObjectStateEstimator(
                 object_name=kw.get("object_name", "robot1_eef"), hidden_dim=kw.get("hidden_dim", 512),
-                num_resnet_layers=50, latent_dim=kw.get("latent_dim", 512),
+                num_resnet_layers=kw.get("num_resnet_layers", 50), latent_dim=kw.get("latent_dim", 512),
                 sequence_length=kw.get("sequence_length", 20), feature_extract=False, feature_layer_nums=(9,),
                 use_depth=kw.get("use_depth", False), use_pretrained=False)
         if kind == "tdo_v2":
             return ref.time_sensitive.TemporallyDependentObjectStateEstimatorV2(
                 object_name=kw.get("object_name", "robot1_eef"), img_hidden_dim=kw.get("hidden_dim", 512),
-                proprio_hidden_dim=kw.get("proprio_hidden_dim", 64), num_resnet_layers=50,
+                proprio_hidden_dim=kw.get("proprio_hidden_dim", 64), num_resnet_layers=kw.get("num_resnet_layers", 50),
                 latent_dim=kw.get("latent_dim", 512), sequence_length=kw.get("sequence_length", 20),
                 feature_extract=False, feature_layer_nums=(9,), use_depth=False, use_pretrained=False)
         if kind == "td":
             return ref.time_sensitive.TemporallyDependentStateEstimator(
                 hidden_dim_pre_measurement=kw.get("hidden_dim", 512),
-                hidden_dim_post_measurement=kw.get("hidden_dim", 512), num_resnet_layers=50,
+                hidden_dim_post_measurement=kw.get("hidden_dim", 512), num_resnet_layers=kw.get("num_resnet_layers", 50),
                 latent_dim=kw.get("latent_dim", 1024), sequence_length=kw.get("sequence_length", 10),
                 feature_extract=False, feature_layer_nums=(9,), use_depth=False, use_pretrained=False)
         if kind == "n":
@@ -186,7 +186,7 @@ def build_reference_model(ref, kind, seed=0, **kw):
             try:
                 return ref.naive.NaiveEndEffectorStateEstimator(
                     hidden_dims_pre_measurement=kw.get("hidden_pre", [512]),
-                    hidden_dims_post_measurement=kw.get("hidden_post", [512]), num_resnet_layers=50,
+                    hidden_dims_post_measurement=kw.get("hidden_post", [512]), num_resnet_layers=kw.get("num_resnet_layers", 50),
                     latent_dim=kw.get("latent_dim", 1024), feature_extract=False)
             finally:
                 ref.naive.import_resnet = orig

@@ -403,8 +403,7 @@ static int conv_dgrad_impl(const float* dy, const float* w_tkc, float* dx, int B
                            int Cout, int R, int S, int stride, int pad, const float* residual,
                            const unsigned* res_mask, cudaStream_t stream, const BnBwd* bnb = nullptr) {
     if (ensure_error_flag()) return 2;
-    PE_REQUIRE(!residual || (R == 1 && S == 1 && stride == 1 && pad == 0),
-               "conv_dgrad: the residual epilogue is implemented for 1x1 stride-1 convolutions only");
+    PE_REQUIRE(!residual || stride == 1, "conv_dgrad: the residual epilogue is implemented for stride-1 convolutions");
     PE_REQUIRE(!bnb || (!residual && bnb->y && bnb->scale && bnb->shift && bnb->mean && bnb->invstd && bnb->sums &&
                         Cin % 32 == 0),
                "conv_dgrad: fused BatchNorm backward sums need y, scale, shift, mean, invstd, sums, Cin %% 32 == 0 and "

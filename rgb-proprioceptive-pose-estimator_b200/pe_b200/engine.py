@@ -91,9 +91,12 @@ class TrunkEngine:
         for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
             for blk in layer:
                 ids = {}
-                for k in (1, 2, 3):
+                for k in (1, 2, 3):          # Bottleneck: conv1..conv3; BasicBlock (ResNet-18): conv1, conv2
+                    if not hasattr(blk, "conv%d" % k):
+                        break
                     ids[k] = len(self.convs)
                     self.convs.append((getattr(blk, "conv%d" % k), getattr(blk, "bn%d" % k)))
+                ids["n"] = max(k for k in ids if isinstance(k, int))
                 if blk.downsample is not None:
                     ids["d"] = len(self.convs)
                     self.convs.append((blk.downsample[0], blk.downsample[1]))
@@ -359,20 +362,22 @@ class TrunkEngine:
 
         # ---- bottleneck stages ------------------------------------------------------------------
         for blk, ids in self.blocks:
+            last = ids["n"]                   # the conv whose BatchNorm output joins the identity branch
+            o = x
             if training:
-                o = self._bn_train(self._conv_train(x, ids[1], tape), ids[1], True, None, tape)
-                o = self._bn_train(self._conv_train(o, ids[2], tape), ids[2], True, None, tape)
-                y3 = self._conv_train(o, ids[3], tape)
+                for k in range(1, last):
+                    o = self._bn_train(self._conv_train(o, ids[k], tape), ids[k], True, None, tape)
+                y_last = self._conv_train(o, ids[last], tape)
                 if "d" in ids:
                     idn = self._bn_train(self._conv_train(x, ids["d"], tape), ids["d"], False, None, tape)
                 else:
                     idn = x
-                x = self._bn_train(y3, ids[3], True, idn, tape)
+                x = self._bn_train(y_last, ids[last], True, idn, tape)
             else:
-                o = self._conv_eval(x, ids[1], True, None)
-                o = self._conv_eval(o, ids[2], True, None)
+                for k in range(1, last):
+                    o = self._conv_eval(o, ids[k], True, None)
                 idn = self._conv_eval(x, ids["d"], False, None) if "d" in ids else x
-                x = self._conv_eval(o, ids[3], True, idn)
+                x = self._conv_eval(o, ids[last], True, idn)
 
         # ---- global average pool + fc -----------------------------------------------------------
         fc = self.net.fc
@@ -444,6 +449,12 @@ class TrunkEngine:
                 if residual is not None and maskbits is not None:
                     # residual join: g = D * mask(out > 0) with the mask read as bits; the identity branch gets
                     # (D, bits) instead of a materialised masked copy
+                    if len(entries) == 2 and entries[0][1] is None and entries[1][1] is None:
+                        # two plain branches that no dgrad epilogue could merge (stride-2 3x3 conv1 + downsample of a
+                        # BasicBlock stage transition): one elementwise add
+                        g0, g1 = entries[0][0], entries[1][0]
+                        L.pe_axpby_cols(P(g0), y.C, P(g1), y.C, P(g0), y.C, y.P, y.C, 1.0, 1.0, 0, st)
+                        entries = [(g0, None)]
                     if len(entries) != 1 or entries[0][1] is not None:
                         raise native.PeError("internal: a residual join expects one complete gradient")
                     d1, d2, mb, mask_src, relu_k = entries[0][0], None, maskbits, None, 0
@@ -498,7 +509,7 @@ class TrunkEngine:
                     L.pe_unpack_conv_wgrad(P(tmp), P(gw), co, ci, r, s, 0, st)
                 dx = torch.empty_like(x.t)
                 res = res_mask = None
-                if r == 1 and s == 1 and stride == 1 and slots.pending(x) == 1:
+                if stride == 1 and slots.pending(x) == 1 and ci % 32 == 0:
                     # the other gradient branch of x (identity / downsample path) is added in the dgrad epilogue
                     (res, res_mask), = slots.pop(x)
                 bn_src = x.bn if (FUSE_BN_REDUCE[0] and res is None and ci % 32 == 0 and

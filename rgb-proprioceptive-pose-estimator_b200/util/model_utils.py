@@ -13,12 +13,13 @@ from __future__ import division, print_function
 
 import torch
 import torch.nn as nn
-from torchvision.models.resnet import Bottleneck, ResNet
+from torchvision.models.resnet import BasicBlock, Bottleneck, ResNet
 
 from pe_b200.engine import TrunkEngine
 from pe_b200.functions import trunk_apply
 
-_RESNET_LAYERS = {50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3]}
+_RESNET_LAYERS = {18: [2, 2, 2, 2], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3]}
+_BASIC_BLOCK_NETS = (18,)
 
 
 def set_parameter_requires_grad(model, feature_extracting):
@@ -33,7 +34,7 @@ class PEResNet(ResNet):
     identical random init under the same seed, and identical state_dict keys) with a CUDA-kernel forward."""
 
     def __init__(self, num_layers):
-        super().__init__(Bottleneck, _RESNET_LAYERS[num_layers])
+        super().__init__(BasicBlock if num_layers in _BASIC_BLOCK_NETS else Bottleneck, _RESNET_LAYERS[num_layers])
         self._pe_engine = None
 
     def pe_engine(self, aux_conv=None, aux_trainable=True):
@@ -67,9 +68,8 @@ def import_resnet(num_layers, output_dim, feature_extract=True, use_pretrained=T
     Helper function to load a ResNet model (mirror of util/model_utils.py:116-147).
 
     Args:
-        num_layers (int): ResNet depth.  The accelerated path implements the Bottleneck family
-            (50, 101, 152); 18/34 use BasicBlock and are not on the reference's hot path
-            (scripts/train_model.py:63 hard-codes 50).
+        num_layers (int): ResNet depth: 18 (BasicBlock), 50, 101, 152 (Bottleneck) -- every value of the reference's
+            option set that torchvision can build (scripts/train_model.py:63 hard-codes 50).
         output_dim (int): size of the replaced final fc layer
         feature_extract (bool): freeze everything but the final layer (only with pretrained weights)
         use_pretrained (bool): load ImageNet weights through torchvision (needs network / a local cache)
@@ -80,7 +80,9 @@ def import_resnet(num_layers, output_dim, feature_extract=True, use_pretrained=T
     options = {18, 32, 50, 101, 152}                      # (sic) same set as the reference, :130
     assert num_layers in options, "Invalid layer size specified. Options are: {}".format(options)
     if num_layers not in _RESNET_LAYERS:
-        raise NotImplementedError("the B200 path implements Bottleneck ResNets (50/101/152); got %d" % num_layers)
+        # 32 is in the reference's option set by mistake (meant 34): torchvision has no resnet32 and the reference dies
+        # with an AttributeError there
+        raise NotImplementedError("the B200 path implements ResNet-18 / 50 / 101 / 152; got %d" % num_layers)
     model = PEResNet(num_layers)
     if use_pretrained:
         import torchvision

@@ -151,7 +151,7 @@ def check_conv(B, H, W, Cin, Cout, k, stride):
     dx = torch.full((B, H, W, Cin), float("nan"), device=DEV)
     L.pe_conv2d_dgrad(P(dy_n), P(tkc), P(dx), B, H, W, Cin, Cout, k, k, stride, pad, None, None, S())
     out.append(("conv_dgrad " + tag, relerr(dx, nhwc(gx)), 1e-4))
-    if k == 1 and stride == 1 and Cin % 32 == 0:
+    if stride == 1 and Cin % 32 == 0:
         # residual epilogue: dx = dgrad + res (plain) and dgrad + res * mask (bit mask of a residual join)
         res = torch.randn(B, H, W, Cin, device=DEV, generator=g)
         L.pe_conv2d_dgrad(P(dy_n), P(tkc), P(dx), B, H, W, Cin, Cout, k, k, stride, pad, P(res), None, S())

@@ -31,7 +31,7 @@ CONFIGS = {
 SHALLOW = [False]   # when set, Bottleneck stacks are [1,1,1,1] instead of ResNet-50's [3,4,6,3]
 
 
-def build_model(kind, seed=0, latent=None):
+def build_model(kind, seed=0, latent=None, layers=50):
     import models.naive as mn
     import models.time_sensitive as mt
     import util.model_utils as mu
@@ -42,10 +42,10 @@ def build_model(kind, seed=0, latent=None):
     torch.manual_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
         if kind == "no":
-            return mn.NaiveObjectStateEstimator("cube", list(cfg["hidden"]), 50, cfg["latent"], False, (9,), False,
+            return mn.NaiveObjectStateEstimator("cube", list(cfg["hidden"]), layers, cfg["latent"], False, (9,), False,
                                                 False)
         if kind == "tdo":
-            return mt.TemporallyDependentObjectStateEstimator("robot1_eef", cfg["hidden"], 50, cfg["latent"], 20,
+            return mt.TemporallyDependentObjectStateEstimator("robot1_eef", cfg["hidden"], layers, cfg["latent"], 20,
                                                               feature_extract=False, use_pretrained=False)
         if kind == "tdo_v2":
             return mt.TemporallyDependentObjectStateEstimatorV2("robot1_eef", cfg["hidden"], 64, 50, cfg["latent"], 20,
@@ -81,11 +81,11 @@ def relnorm(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def check_train_step(kind, n=2, s=2, seed=1, verbose=False, latent=None):
+def check_train_step(kind, n=2, s=2, seed=1, verbose=False, latent=None, layers=50):
     """forward (train mode) + loss + backward vs oracle.  Returns rows (name, err, tol)."""
     from models.losses import PoseDistanceLoss
     cfg = CONFIGS[kind]
-    model = build_model(kind, latent=latent)
+    model = build_model(kind, latent=latent, layers=layers)
     orc = oracle_for(kind, model)
     if kind in ("no", "n"):
         img, x0, tgt = po.synthetic_batch(kind, n, seed=seed)
@@ -202,7 +202,7 @@ def oracle_loss_and_grads(orc, kind, img, x0, tgt, lk):
     return (pre.detach(), post.detach()), loss.detach(), grads
 
 
-def check_forced(kind, n=2, s=2, seed=1, verbose=False):
+def check_forced(kind, n=2, s=2, seed=1, verbose=False, layers=50):
     """Full-depth training step against the oracle at the SAME operand precision (TF32 operands, float64 accumulation)
     and on the SAME ReLU masks: the raw convolution outputs the CUDA path saved for its backward pass are teacher-forced
     into the oracle's forward (oracle/pose_oracle.py: tf32_operands, forced_conv_outputs).  Every convolution is still
@@ -212,7 +212,7 @@ def check_forced(kind, n=2, s=2, seed=1, verbose=False):
     from pe_b200 import engine
     cfg = CONFIGS[kind]
     lk = cfg["loss"]
-    model = build_model(kind)
+    model = build_model(kind, layers=layers)
     with torch.no_grad():      # finite loss for the models that ReLU their output (quirk Q2/Q7)
         if kind == "no":
             getattr(model, "fc%d" % (model.n_fc - 1)).module.bias.fill_(0.5)

@@ -679,3 +679,16 @@ def test_loss_curve_at_the_reference_learning_rate():
     tails = [sum(r[-10:]) / 10 for r in refs]
     tail = sum(ours[-10:]) / 10
     assert min(tails) / 1.5 <= tail <= max(tails) * 1.5, (tail, tails)
+
+
+def test_resnet18_trunk():
+    """num_resnet_layers = 18 (BasicBlock trunk, the other depth of the reference's option set torchvision can build):
+    two 3x3 convs per block, the identity / downsample gradient merged in the 3x3 conv1 dgrad epilogue (or summed
+    for the stride-2 stage transitions).  Outputs / loss vs the plain fp32 oracle, every per-parameter gradient vs the
+    TF32-operand teacher-forced oracle."""
+    rows = mc.check_train_step("no", n=4, layers=18)
+    bad = _full_depth_bad(rows, 4)
+    assert not bad, bad
+    rows = mc.check_forced("no", n=4, layers=18, verbose=True) + mc.check_forced("tdo", n=2, layers=18)
+    bad = [(n, e, t) for n, e, t in rows if not e <= t]
+    assert not bad, bad

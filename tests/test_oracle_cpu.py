@@ -185,3 +185,36 @@ def test_teacher_forcing_puts_two_precisions_on_the_same_masks():
     free = max(mc.relnorm(g32[k], g64_free[k]) for k in g32 if g32[k] is not None)
     assert forced <= 5e-3, forced
     assert free > 3 * forced, (free, forced)
+
+
+def test_resnet18_trunk_vs_live_reference():
+    """import_resnet(18, ...) (util/model_utils.py:130-136, BasicBlock trunk): the oracle's restatement and the mirror's
+    seed-0 state_dict against the reference's own NaiveObjectStateEstimator built with num_resnet_layers=18."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not available")
+    import model_checks as mc
+    ref = ref_shim.load()
+    m_ref = ref_shim.build_reference_model(ref, "no", num_resnet_layers=18)
+    mirror = mc.build_model("no", layers=18)
+    sd_ref, sd = m_ref.state_dict(), mirror.state_dict()
+    assert list(sd_ref) == list(sd)
+    for k in sd_ref:
+        assert torch.equal(sd_ref[k], sd[k]), k
+    img, x0, tgt = po.synthetic_batch("no", 2, seed=1)
+    lk = mc.CONFIGS["no"]["loss"]
+    with torch.no_grad():          # keep the ReLU'd quaternion alive (quirk Q2/Q7)
+        getattr(m_ref, "fc%d" % (m_ref.n_fc - 1)).module.bias.fill_(0.5)
+    orc = po.OracleEstimator("no", m_ref.state_dict())
+    m_ref.train()
+    with ref_shim.quiet():
+        out = m_ref(img, None, x0)
+    loss = ref.losses.PoseDistanceLoss(**lk)(out, tgt)
+    loss.backward()
+    out_o, loss_o, grads = orc.loss_and_grads(img, x0, tgt, lk)
+    assert mc.rel(out_o, out) <= 1e-5
+    assert abs(float(loss_o) - float(loss)) <= 1e-5 * abs(float(loss))
+    named = dict(m_ref.named_parameters())
+    for k in ("feature_net.module.conv1.weight", "feature_net.module.layer2.0.downsample.0.weight",
+              "feature_net.module.layer4.1.conv2.weight", "fc0.module.weight"):
+        assert mc.relnorm(grads[k], named[k].grad) <= 1e-3, k
