@@ -50,8 +50,8 @@ def _probe_feature_layers(owner, feature_net, feature_layer_nums, wrap):
 
 def _check_supported(feature_layer_nums, use_depth):
     if feature_layer_nums is not None and tuple(feature_layer_nums) != (9,):
-        raise NotImplementedError("the B200 path implements the reference's only configuration, "
-                                  "feature_layer_nums=(9,) (scripts/train_model.py:65); got %r"
+        raise NotImplementedError("the B200 path implements the configuration the reference's scripts use, "
+                                  "feature_layer_nums=(9,) (scripts/train_model.py:65), or None; got %r"
                                   % (feature_layer_nums,))
     if use_depth and feature_layer_nums is None:
         # the reference multiplies depth features into the aux features only (models/naive.py:324-330)
