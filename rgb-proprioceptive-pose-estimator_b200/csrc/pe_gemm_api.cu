@@ -183,23 +183,32 @@ static int pick_bn(int n_total, long long m_tiles = 1 << 20) {
     return bn;
 }
 
-static int g_dbg_cta_group = 0;       // 0: automatic, 1: never pair CTAs, 2: pair whenever the launch allows it
-// CTA pairs (tcgen05 cta_group::2, M = 256): per MMA a lone CTA reads 128 A rows + bn B rows from shared memory and TMA
-// writes as many -- at bn = 256 that is 24 KB per 128-cycle instruction, 1.5x what the shared-memory port moves, which
-// is where the measured 185 cycles per instruction come from.  In a pair each CTA holds its own A box and HALF of the
-// weight tile: 16 KB per instruction, back under the port's rate, and half the L2 -> SM weight traffic.  Used for
-// the wide tiles when the launch has at least one tile per SM (measured on B200, 256 frames: 14x14 256->1024 forward
-// 97 -> 69 us, 7x7 512->2048 81 -> 58 us, 3x3 256->256 @14 91 -> 82 us = 720 TFLOP/s; no gain at 128 or 64 columns).
+static int g_dbg_cta_group = 0;       // 0: automatic, 1: never pair CTAs, 2: pair whenever the launch allows it,
+                                      // 3: automatic, 256-column tiles only (the rule before the ring was deepened)
+// CTA pairs (tcgen05 cta_group::2, M = 256): each CTA keeps its own 128-pixel A box and HALF of the weight tile, and ONE
+// MMA warp issues for both SMs.  The tensor pipe itself is not the limit of a lone CTA (tests/probe_mma_rate.cu: 128 /
+// 64 / 48 clk per 128 x {256, 128, 64} x 8 TF32 instruction straight from shared memory); the operand ring is: a stage's
+// MMAs retire long before its slot has made the round trip commit -> producer -> TMA -> full barrier, so the rate is
+// (MMAs held by the ring) / (round trip).  A pair holds the same MMAs in 2/3 .. 5/6 of the bytes -> a deeper ring out of
+// the same shared memory, half the L2 -> SM weight traffic and half the issue / barrier rounds per SM.  Used whenever the
+// launch has at least one tile per SM (measured on B200, 256 frames: 14x14 256->1024 forward 97 -> 69 us, 3x3 256->256
+// @14 91 -> 82 us; with B regions sized by the rows really loaded also 56x56 64->64 3x3 196 -> 167 us, 28x28 128->128
+// 3x3 114 -> 100 us: profiles/layers_r02b.txt).
 static bool want_pair(const TapParams& p, long long m_tiles, int n_tiles) {
     if (p.mode != 0 || p.conv_halo || g_dbg_flags || g_dbg_cta_group == 1 || (p.bn % 32) || m_tiles < 2) return false;
     if (g_dbg_cta_group == 2) return true;
-    return p.bn == 256 && m_tiles * n_tiles >= (long long)num_sms();
+    return (p.bn == 256 || g_dbg_cta_group != 3) && m_tiles * n_tiles >= (long long)num_sms();
 }
 
 // Split the 216 KB of dynamic shared memory between the operand ring and the store staging buffers.
 // Long reductions want ring depth, short ones (1x1 convs) are bound by the epilogue's store pipeline.
 static void pick_pipeline(TapParams& p, int ksteps) {
-    p.stage_bytes = TG_A_BYTES + (p.bn / (p.cta_group == 2 ? 2 : 1) > 128 ? 32768 : 16384);
+    // B region: the weight (mode 1: X) rows this CTA loads per stage, in whole 32-row swizzle atoms.  Narrow tiles get
+    // a DEEPER ring out of the same shared memory: their per-stage MMA time (4 x 48 clk at 64 columns) is far below the
+    // slot round trip (commit -> producer -> TMA -> full barrier, ~1000 clk), so throughput ~ stages / round trip
+    // (measured, 56x56 64->64 3x3: 308 / 239 / 209 us at 2 / 3 / 4 stages; tests/probe_narrow3x3.py).
+    const int bn_cta = p.bn / (p.cta_group == 2 ? 2 : 1);
+    p.stage_bytes = TG_A_BYTES + (g_dbg_flags & 2048 ? (bn_cta > 128 ? 32768 : 16384) : (bn_cta + 31) / 32 * 4096);
     p.stats_cols = p.stats ? (p.n_total + 31) / 32 * 32 : 0;
     // residual tiles are prefetched by TMA (two 16 KB buffers per epilogue group) when the output goes out by TMA
     // (bn_bwd mode reads its y tile only at the end of a chunk's work: one buffer per group, requested a chunk ahead)

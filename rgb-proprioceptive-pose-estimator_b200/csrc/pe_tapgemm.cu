@@ -241,14 +241,16 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                         ok = false;
                         break;
                     }
-                    mbar_arrive_expect_tx_elect(smem_u32(&s_full[s]), a_bytes);
-                    tma_load_4d_elect(smem_base + s * p.stage_bytes, &maps.a[0], smem_u32(&s_full[s]), ch * TG_BK,
-                                      o.w0 + p.halo_dw, o.h0 + p.halo_dh, o.n0);
+                    // (probe flags 4 / 8: the A / B loads are skipped -- timing experiments on garbage operands)
+                    mbar_arrive_expect_tx_elect(smem_u32(&s_full[s]), (p.dbg_flags & 4) ? 0u : a_bytes);
+                    if (!(p.dbg_flags & 4))
+                        tma_load_4d_elect(smem_base + s * p.stage_bytes, &maps.a[0], smem_u32(&s_full[s]), ch * TG_BK,
+                                          o.w0 + p.halo_dw, o.h0 + p.halo_dh, o.n0);
                     if (++s == static_cast<uint32_t>(p.stages)) {
                         s = 0;
                         ph ^= 1;
                     }
-                    for (int t = 0; t < p.n_taps; t += p.b_taps) {
+                    for (int t = 0; t < p.n_taps && !(p.dbg_flags & 8); t += p.b_taps) {
                         if (!mbar_wait_warp(smem_u32(&s_bempty[sb]), phb ^ 1, spin)) {
                             atomicOr(p.error_flag, 1);
                             ok = false;
@@ -479,7 +481,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                     tc_fence_after();
                     const uint64_t ad0 = ah_desc0 + ((smem_base + s * p.stage_bytes) >> 4);
                     for (int t = 0; t < p.n_taps; t += p.b_taps) {
-                        if (!mbar_wait_warp(smem_u32(&s_bfull[sb]), phb, spin)) {
+                        if (!(p.dbg_flags & 8) && !mbar_wait_warp(smem_u32(&s_bfull[sb]), phb, spin)) {
                             atomicOr(p.error_flag, 4);
                             ok = false;
                             break;
@@ -497,7 +499,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                                 accf = 1u;
                             }
                         }
-                        tc_commit_elect(smem_u32(&s_bempty[sb]));
+                        if (!(p.dbg_flags & 8)) tc_commit_elect(smem_u32(&s_bempty[sb]));
                         if (++sb == static_cast<uint32_t>(p.b_stages)) {
                             sb = 0;
                             phb ^= 1;

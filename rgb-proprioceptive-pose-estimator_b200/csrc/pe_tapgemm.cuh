@@ -23,7 +23,7 @@ namespace pe {
 constexpr int TG_BM = 128;                     // tile rows  (TMEM lanes)
 constexpr int TG_BK = 32;                      // tf32 elements per k-step (128 B swizzle span)
 constexpr int TG_MAX_BN = 256;                 // tile columns (TMEM columns per accumulator)
-constexpr int TG_STAGES = 6;                    // maximum ring depth (runtime: TapParams::stages)
+constexpr int TG_STAGES = 8;                    // maximum ring depth (runtime: TapParams::stages)
 constexpr int TG_A_BYTES = TG_BM * 128;        // 16 KB
 constexpr int TG_B_BYTES = TG_MAX_BN * 128;    // 32 KB (16 KB when bn <= 128: TapParams::stage_bytes)
 constexpr int TG_SMEM_BYTES = 223 * 1024;       // ring (stages x 32|48 KB) + store staging (nout x 16 KB)
@@ -73,7 +73,7 @@ struct TapParams {
     int stages, nout;         // smem split: ring depth and number of 16 KB store-staging buffers
     int epi_groups;           // 2 or 4 epilogue groups of 4 warps; group g drains the 32-column chunks c with c % G == g
     int nres;                 // 16 KB residual tiles prefetched by TMA for the epilogue (0 or 4: two per group)
-    int stage_bytes;          // 16 KB (A) + 16 or 32 KB (B)
+    int stage_bytes;          // 16 KB (A) + the B rows of one stage in whole 4 KB atoms
     int stats_cols;           // columns of the CTA-wide statistics scratch (n_total rounded up to 32; 0 = none)
     int dbg_flags;            // 1: skip TMA store issue, 2: skip staging write + store, 4: skip A loads, 8: skip B loads
     // mode 2 (haloed wgrad): pixel tile box_w x box_h x box_n (box_w % 8 == 0), halo tile halo_w x halo_h x box_n

@@ -729,6 +729,40 @@ def check_conv_halo_path(*args):
     return rows
 
 
+def forced_pairs(fn):
+    """Run a check with CTA pairs (tcgen05 cta_group::2) forced on every launch that allows them: the checks' shapes are
+    too small for the automatic rule (one tile per SM), the production step runs most conv launches paired."""
+    def run():
+        L = native.lib()
+        L.pe_debug_cta_group(2)
+        try:
+            return [("[pairs] " + n, e, t) for n, e, t in fn()]
+        finally:
+            L.pe_debug_cta_group(0)
+    return run
+
+
+PAIRS = [forced_pairs(f) for f in (
+    lambda: check_conv(2, 56, 56, 64, 64, 1, 1),
+    lambda: check_conv(2, 56, 56, 64, 64, 3, 1),
+    lambda: check_conv(2, 56, 56, 64, 256, 1, 1),
+    lambda: check_conv(2, 56, 56, 256, 64, 1, 1),
+    lambda: check_conv(3, 28, 28, 128, 128, 3, 1),
+    lambda: check_conv(2, 56, 56, 128, 128, 3, 2),
+    lambda: check_conv(3, 28, 28, 256, 512, 1, 2),
+    lambda: check_conv(4, 14, 14, 256, 256, 3, 1),
+    lambda: check_conv(2, 14, 14, 1024, 256, 1, 1),
+    lambda: check_conv(5, 7, 7, 512, 2048, 1, 1),
+    lambda: check_conv(3, 7, 7, 512, 512, 3, 1),
+    lambda: check_conv_fused_eval(3, 14, 14, 256, 1024, 1) + check_conv_fused_eval(2, 28, 28, 128, 512, 1)
+    + check_conv_fused_eval(2, 56, 56, 64, 64, 3),
+    lambda: check_conv_dgrad_bn(3, 28, 28, 128, 512, 1, 1) + check_conv_dgrad_bn(2, 56, 56, 64, 64, 3, 1),
+    lambda: check_conv_dgrad_bn(5, 14, 14, 256, 1024, 1, 1) + check_conv_dgrad_bn(3, 28, 28, 128, 128, 3, 1),
+    lambda: check_conv_dgrad_bn(2, 56, 56, 128, 128, 3, 2) + check_conv_dgrad_bn(2, 56, 56, 64, 256, 1, 1),
+    lambda: check_linear(300, 512, 256) + check_linear(1000, 2048, 3680, relu=True) + check_linear(129, 256, 64)
+    + check_linear(640, 128, 512),
+)]
+
 ALL = [
     lambda: check_linear(128, 128, 32, bias=False),
     lambda: check_linear(128, 128, 256),

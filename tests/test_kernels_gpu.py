@@ -22,3 +22,15 @@ def test_kernel_check(idx):
     assert not bad, bad
     from pe_b200 import native
     native.lib().check_device()
+
+
+@pytest.mark.parametrize("idx", range(len(kc.PAIRS)))
+def test_kernel_check_cta_pairs(idx):
+    """The same checks with tcgen05 cta_group::2 forced (64-, 128- and 256-column tiles, stride 2, fused BatchNorm
+    statistics / BatchNorm-backward sums / residual epilogues): the production step runs these launches paired."""
+    rows = kc.PAIRS[idx]()
+    torch.cuda.synchronize()
+    bad = [(n, e, t) for n, e, t in rows if not e <= t]
+    assert not bad, bad
+    from pe_b200 import native
+    native.lib().check_device()
