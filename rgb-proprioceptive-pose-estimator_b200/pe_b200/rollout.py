@@ -138,3 +138,69 @@ class StreamingEstimator:
             self.graph.replay()
             outs = self.outs
         return outs if len(outs) > 1 else outs[0]
+
+
+class PipelinedEstimator:
+    """Large-batch rollout step with the host -> device copy of the frames overlapped with the trunk: the batch is cut
+    into chunks of `chunk` episodes, each a CUDA-graph `StreamingEstimator` with its own input / LSTM-state / output
+    buffers; chunk i + 1 is copied on a side stream while chunk i computes.  Episodes are independent (SURVEY 8e:
+    rollout = replicas), so the result is the one-shot step's, row for row.  Pays from ~512 frames per step on, where
+    the 150 KB .. 600 KB per frame of PCIe traffic is a third of the step (bench.py rollout sweep)."""
+
+    def __init__(self, model, batch_size, chunk=256, device=None, raw_hw=None):
+        if batch_size % chunk:
+            raise native.PeError("PipelinedEstimator: batch_size %d is not a multiple of chunk %d" % (batch_size, chunk))
+        self.N, self.chunk = batch_size, chunk
+        self.parts = [StreamingEstimator(model, chunk, use_graph=True, device=device, raw_hw=raw_hw)
+                      for _ in range(batch_size // chunk)]
+        self.dev = self.parts[0].dev
+        self.seq = self.parts[0].seq
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.landed = [torch.cuda.Event() for _ in self.parts]
+        self.consumed = [torch.cuda.Event() for _ in self.parts]
+        self.outs = None
+
+    def reset(self):
+        for p in self.parts:
+            p.reset()
+
+    def _step(self, frames, self_measurement, raw):
+        c = self.chunk
+        cur = torch.cuda.current_stream(self.dev)
+        frames = frames.reshape(self.N, *frames.shape[-3:])
+        x0 = self_measurement.reshape(self.N, 7)
+        self.copy_stream.wait_stream(cur)          # device-resident inputs may still be in flight on the caller's stream
+        with torch.cuda.stream(self.copy_stream):
+            for i, p in enumerate(self.parts):
+                self.copy_stream.wait_event(self.consumed[i])      # the previous step has read this chunk's buffers
+                dst = p.raw if raw else p.img
+                dst.copy_(frames[i * c:(i + 1) * c].reshape(dst.shape), non_blocking=True)
+                p.x0.copy_(x0[i * c:(i + 1) * c].reshape(p.x0.shape), non_blocking=True)
+                self.landed[i].record(self.copy_stream)
+        L, st, P = native.lib(), native.stream_ptr(), native.ptr
+        for i, p in enumerate(self.parts):
+            cur.wait_event(self.landed[i])
+            o = p._run()
+            self.consumed[i].record(cur)
+            o = o if isinstance(o, tuple) else (o,)
+            if self.outs is None:
+                lead = (1, self.N) if self.seq else (self.N,)
+                self.outs = tuple(torch.empty(*lead, 8, device=self.dev) for _ in o)
+            for dst, src in zip(self.outs, o):
+                d2 = dst.view(self.N, 8)[i * c:(i + 1) * c]
+                s2 = src.reshape(c, src.shape[-1])
+                L.pe_copy_cols(P(s2), s2.stride(0), P(d2), 8, c, 7, 0, st)
+        outs = tuple(t[..., :7] for t in self.outs)
+        return outs if len(outs) > 1 else outs[0]
+
+    @torch.no_grad()
+    def step(self, img, self_measurement):
+        if self.parts[0].raw is not None:
+            raise native.PeError("this estimator was built for raw frames: call step_raw")
+        return self._step(img, self_measurement, False)
+
+    @torch.no_grad()
+    def step_raw(self, frames_u8, self_measurement):
+        if self.parts[0].raw is None:
+            raise native.PeError("construct PipelinedEstimator(..., raw_hw=256) to feed raw frames")
+        return self._step(frames_u8, self_measurement, True)

@@ -108,6 +108,22 @@ def test_config1_naive_object_cube_batch8():
     assert not bad, bad
 
 
+@pytest.mark.parametrize("kind", ["no", "tdo"])
+def test_full_depth_gradients_with_cta_pairs_forced(kind):
+    """The production step (256 frames) runs nearly every conv launch on CTA pairs (tcgen05 cta_group::2); the small
+    test batches never reach the automatic rule (one tile per SM).  Same full-depth teacher-forced gradient check with
+    pairs forced on every launch that allows them."""
+    from pe_b200 import native
+    L = native.lib()
+    L.pe_debug_cta_group(2)
+    try:
+        rows = mc.check_forced(kind, n=4 if kind == "no" else 2, verbose=True)
+    finally:
+        L.pe_debug_cta_group(0)
+    bad = [(n, e, t) for n, e, t in rows if not e <= t]
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("kind", ["no", "tdo", "td", "n", "tdo_v2"])
 def test_full_depth_gradients_teacher_forced(kind):
     """Every per-parameter gradient of the FULL [3,4,6,3] trunk + head, all five estimators, within 1e-2
@@ -485,6 +501,34 @@ def test_streaming_estimator_raw_frames():
         a = raw_est.step_raw(raw.pin_memory(), x0.pin_memory()).clone()
         b = ref_est.step(img.cuda(), x0.cuda()).clone()
         assert mc.rel(a, b) <= 1e-5, (t, mc.rel(a, b))
+
+
+@pytest.mark.parametrize("kind,raw", [("tdo", False), ("tdo", True), ("td", False), ("no", False)])
+def test_pipelined_estimator_matches_one_shot_step(kind, raw):
+    """PipelinedEstimator (chunks of the batch copied on a side stream while the previous chunk computes, one CUDA graph
+    per chunk, LSTM state per chunk) == the one-shot StreamingEstimator step, row for row, over carried state."""
+    from pe_b200.rollout import PipelinedEstimator, StreamingEstimator
+    mc.SHALLOW[0] = True
+    model = mc.build_model(kind).cuda().eval()
+    hw = 256 if raw else None
+    pipe = PipelinedEstimator(model, batch_size=12, chunk=4, raw_hw=hw)
+    ref = StreamingEstimator(model, batch_size=12, use_graph=False, raw_hw=hw)
+    pipe.reset()
+    ref.reset()
+    g = torch.Generator().manual_seed(5)
+    for t in range(3):
+        if raw:
+            frames = torch.randint(0, 256, (12, 256, 256, 3), dtype=torch.uint8, generator=g).pin_memory()
+        else:
+            frames = torch.randn(12, 3, 224, 224, generator=g).pin_memory()
+        x0 = torch.randn(12, 7, generator=g).pin_memory()
+        a = pipe.step_raw(frames, x0) if raw else pipe.step(frames, x0)
+        b = ref.step_raw(frames, x0) if raw else ref.step(frames, x0)
+        a = a if isinstance(a, tuple) else (a,)
+        b = b if isinstance(b, tuple) else (b,)
+        for u, v in zip(a, b):
+            assert u.shape == v.shape
+            assert mc.rel(u.float().cpu(), v.float().cpu()) <= 2e-3, (kind, t, mc.rel(u.cpu(), v.cpu()))
 
 
 @pytest.mark.parametrize("kind", ["no", "tdo"])
