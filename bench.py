@@ -351,7 +351,7 @@ def measure_tf32_peak(dev, seconds=1.5):
 
 
 GEMM_FAMS = ("pe_conv2d_fwd", "pe_conv2d_dgrad", "pe_conv2d_dgrad_bn", "pe_conv2d_wgrad", "pe_linear_fwd",
-             "pe_linear_wgrad")
+             "pe_linear_wgrad", "pe_stem_conv_fwd", "pe_stem_conv_wgrad")
 HBM_FAMS = ("pe_bn_train_apply", "pe_bn_bwd_reduce", "pe_bn_bwd_apply", "pe_adam_step")
 
 

@@ -99,6 +99,20 @@ int pe_pack_block_elems(void);
 /* 7x7/2 stem (Cin = 3): NCHW image -> im2col rows [B*Ho*Wo][ldc], columns ordered (c, r, s) like OIHW */
 int pe_im2col_stem(const float* img_nchw, float* col, int B, int C, int H, int W, int R, int S, int stride,
                    int pad, int ldc, int round_tf32, void* stream);
+/* The same stem (torchvision resnet.py:197 conv1 = Conv2d(3, 64, 7, stride 2, padding 3), reached from
+ * models/naive.py:316 / models/time_sensitive.py:185,472) WITHOUT the im2col matrix: the 7x7/2 convolution is a 4x4/1
+ * convolution over the 2x2 space-to-depth image (12 channels); four horizontally adjacent taps are 48 contiguous floats
+ * of that NHWC tensor, so the tap-GEMM reads its operand through a TMA view with overlapping pixel rows.
+ *   pe_stem_s2d_pack     img NCHW (3,H,W) -> s2d [B][H/2+3][W/2+3][12] (zero border written), optionally TF32-rounded
+ *   pe_stem_pack_weight  OIHW [Cout][3][7][7] -> [4][Cout][64];  pe_stem_unpack_wgrad: the inverse for the gradient
+ *   pe_stem_conv_fwd     y [B*(H/2)*(W/2)][Cout] = conv1(img) with the conv epilogues of pe_conv2d_fwd
+ *   pe_stem_conv_wgrad   dw [4][Cout][64] from s2d and dy                                                       */
+int pe_stem_s2d_pack(const float* img_nchw, float* s2d, int B, int H, int W, int round_tf32, void* stream);
+int pe_stem_pack_weight(const float* w_oihw, float* w_s2d, int Cout, int round_tf32, void* stream);
+int pe_stem_unpack_wgrad(const float* dw_s2d, float* dw_oihw, int Cout, void* stream);
+int pe_stem_conv_fwd(const float* s2d, const float* w_s2d, float* y, int B, int H, int W, int Cout, const float* scale,
+                     const float* shift, int relu, int round_out, double* stats, void* stream);
+int pe_stem_conv_wgrad(const float* s2d, const float* dy, float* dw_s2d, int B, int H, int W, int Cout, void* stream);
 
 /* ---- dense layers: nn.Linear / nn.LSTM projections (models/naive.py:274,343-345,
  *      models/time_sensitive.py:126-131,418-423) -------------------------------------------------

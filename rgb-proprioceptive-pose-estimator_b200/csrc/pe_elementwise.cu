@@ -494,6 +494,69 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ tck, float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// space-to-depth stem operand (pe_stem_conv_fwd / pe_stem_conv_wgrad, pe_gemm_api.cu)
+// ---------------------------------------------------------------------------------------------
+// img NCHW (3 channels) -> s2d [B][H/2 + 3][W/2 + 3][12], channel k = a * 6 + b * 3 + c holds img[c][2 I + a][2 J + b]
+// at padded position (I + 2, J + 2); the border (2 top / left, 1 bottom / right) is written as zeros.  One thread per
+// s2d pixel: six coalesced 64-bit loads, three 128-bit stores.
+__global__ void __launch_bounds__(EW_THREADS)
+stem_s2d_pack_kernel(const float* __restrict__ img, float* __restrict__ s2d, int B, int H, int W, int round_out) {
+    pdl_sync();
+    const int Hs = H / 2 + 3, Ws = W / 2 + 3;
+    const long long n = (long long)B * Hs * Ws;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int jp = (int)(i % Ws);
+        const long long r = i / Ws;
+        const int ip = (int)(r % Hs);
+        const int b = (int)(r / Hs);
+        const int I = ip - 2, J = jp - 2;
+        float v[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) v[k] = 0.f;
+        if (I >= 0 && I < H / 2 && J >= 0 && J < W / 2) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const float2 t = *reinterpret_cast<const float2*>(
+                        img + (((long long)b * 3 + c) * H + (2 * I + a)) * W + 2 * J);
+                    v[a * 6 + c] = round_out ? round_tf32(t.x) : t.x;
+                    v[a * 6 + 3 + c] = round_out ? round_tf32(t.y) : t.y;
+                }
+        }
+        float* o = s2d + i * 12;
+        st4(o, make_float4(v[0], v[1], v[2], v[3]));
+        st4(o + 4, make_float4(v[4], v[5], v[6], v[7]));
+        st4(o + 8, make_float4(v[8], v[9], v[10], v[11]));
+    }
+}
+
+// conv1 weight OIHW [Cout][3][7][7]  <->  [4 filter rows U][Cout][64]: column V * 12 + a * 6 + b * 3 + c of row U holds
+// w[co][c][2 U + a - 1][2 V + b - 1] (zero where an index is -1, and in columns 48..63).  dir = 0 packs (rounding to
+// TF32 on request), dir = 1 scatters a gradient in the packed layout back to OIHW.
+__global__ void __launch_bounds__(EW_THREADS)
+stem_weight_kernel(float* __restrict__ w_oihw, float* __restrict__ w_s2d, int Cout, int dir, int round_out) {
+    pdl_sync();
+    const int n = 4 * Cout * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int k = i & 63;
+        const int co = (i >> 6) % Cout;
+        const int U = i / (64 * Cout);
+        const int V = k / 12, rem = k % 12;
+        const int a = rem / 6, bq = (rem % 6) / 3, c = rem % 3;
+        const int r = 2 * U + a - 1, q = 2 * V + bq - 1;
+        const bool valid = k < 48 && r >= 0 && q >= 0;
+        if (dir == 0) {
+            float v = valid ? w_oihw[((co * 3 + c) * 7 + r) * 7 + q] : 0.f;
+            w_s2d[i] = round_out ? round_tf32(v) : v;
+        } else if (valid) {
+            w_oihw[((co * 3 + c) * 7 + r) * 7 + q] = w_s2d[i];
+        }
+    }
+}
+
 // One block per output row (b, ho): the R input rows of every channel it needs are staged (zero padded,
 // TF32-rounded) in shared memory, then written out as Wo im2col rows with 128-bit coalesced stores.
 // blockDim = (ldc/4, rows in flight); thread x owns the same four k columns for every row.
@@ -1301,6 +1364,30 @@ int pe_unpack_conv_wgrad(const float* dw_tck, float* dw_oihw, int Cout, int Cin,
     const long long n = (long long)Cout * Cin * R * S;
     PE_LAUNCH(unpack_wgrad_kernel, grid_for(n, EW_THREADS * 4), EW_THREADS, 0, dw_tck, dw_oihw, Cout, Cin, R * S,
               accumulate);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_stem_s2d_pack(const float* img_nchw, float* s2d, int B, int H, int W, int round_tf32, void* stream) {
+    PE_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem s2d: image %d x %d must have even sides", H, W);
+    PE_REQUIRE((reinterpret_cast<uintptr_t>(img_nchw) & 7) == 0 && (reinterpret_cast<uintptr_t>(s2d) & 15) == 0,
+               "stem s2d: image / output pointers must be 8- / 16-byte aligned");
+    const long long n = (long long)B * (H / 2 + 3) * (W / 2 + 3);
+    PE_LAUNCH(stem_s2d_pack_kernel, grid_for(n, EW_THREADS), EW_THREADS, 0, img_nchw, s2d, B, H, W, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_stem_pack_weight(const float* w_oihw, float* w_s2d, int Cout, int round_tf32, void* stream) {
+    PE_LAUNCH(stem_weight_kernel, grid_for(4ll * Cout * 64, EW_THREADS), EW_THREADS, 0, const_cast<float*>(w_oihw), w_s2d,
+              Cout, 0, round_tf32);
+    PE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pe_stem_unpack_wgrad(const float* dw_s2d, float* dw_oihw, int Cout, void* stream) {
+    PE_LAUNCH(stem_weight_kernel, grid_for(4ll * Cout * 64, EW_THREADS), EW_THREADS, 0, dw_oihw, const_cast<float*>(dw_s2d),
+              Cout, 1, 0);
     PE_LAUNCH_CHECK();
     return 0;
 }

@@ -113,6 +113,20 @@ static int make_nhwc_map(CUtensorMap* m, const float* base, int N, int H, int W,
     return make_map(m, base + ((long long)ph * W + pw) * C, dims, strides, box, mn_major);
 }
 
+// Activation view with explicit pixel strides (in elements): the space-to-depth stem reads its operand through a map
+// whose pixel stride (12 floats) is SMALLER than the channel extent (48 floats) -- every "pixel row" of the map is the
+// sliding window of four consecutive 12-channel pixels; channel coordinates >= c_extent are zero-filled by TMA.
+struct XGeom {
+    int c_extent;
+    long long sw, sh, sn;
+};
+static int make_xgeom_map(CUtensorMap* m, const float* base, int N, int H, int W, const XGeom& g, const int box[4],
+                          bool mn_major = false) {
+    const long long dims[4] = {g.c_extent, W, H, N};
+    const long long strides[3] = {g.sw, g.sh, g.sn};
+    return make_map(m, base, dims, strides, box, mn_major);
+}
+
 // Pick a (bw, bh, bn) pixel box with bw*bh*bn <= target that tiles (W, H, N) with the fewest boxes.
 // exact=true: bw*bh*bn == target exactly (boxes may overhang the tensor; TMA zero-fills), needed when
 // the box rows are the reduction dimension (wgrad) and every shared-memory row must be defined.
@@ -326,16 +340,17 @@ static int fill_taps_fwd(TapParams& p, int R, int S, int stride, int pad) {
 // ---------------------------------------------------------------------------------------------
 static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, int H, int W, int Cin,
                          int Cout, int R, int S, int stride, int pad, const Epilogue& ep,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const XGeom* xg = nullptr) {
     if (ensure_error_flag()) return 2;
     PE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "conv channels must be multiples of 4 (Cin=%d Cout=%d)", Cin, Cout);
+    PE_REQUIRE(!xg || (stride == 1 && pad == 0 && !ep.residual), "conv_fwd: strided views need stride 1, no padding");
     const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
     TapMaps maps;
     TapParams p;
     init_params(p);
     p.mode = 0;
     p.bn = pick_bn(Cout, ((long long)B * Ho * Wo + TG_BM - 1) / TG_BM);
-    const bool halo = stride == 1 && !ep.residual && setup_conv_halo(p, B, H, W, Cin, R, S, pad);
+    const bool halo = stride == 1 && !ep.residual && !xg && setup_conv_halo(p, B, H, W, Cin, R, S, pad);
     if (!halo) {
         choose_box(Wo, Ho, B, TG_BM, &p.box_w, &p.box_h, &p.box_n);
         p.m_rows = p.box_w * p.box_h * p.box_n;
@@ -360,6 +375,8 @@ static int conv_fwd_impl(const float* x, const float* w_tck, float* y, int B, in
     if (halo) {
         const int hbox[4] = {TG_BK, p.halo_w, p.halo_h, 1};
         if (make_nhwc_map(&maps.a[0], x, B, H, W, Cin, 0, 0, 1, hbox)) return 1;
+    } else if (xg) {
+        if (make_xgeom_map(&maps.a[0], x, B, H, W, *xg, box)) return 1;
     } else if (stride == 1) {
         if (make_nhwc_map(&maps.a[0], x, B, H, W, Cin, 0, 0, 1, box)) return 1;
     } else {
@@ -547,7 +564,7 @@ static int g_dbg_wgrad_halo = 1;      // 0: one tap per work item (mode 1) every
 // Stride-1 multi-tap wgrad with a haloed X tile (tap-GEMM mode 2): the dY pixel tile and the X tile (+halo) are
 // fetched ONCE per tap group instead of once per tap; every tap accumulates into its own TMEM columns.
 static int conv_wgrad_halo_impl(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin,
-                                int Cout, int R, int S, int pad, cudaStream_t stream) {
+                                int Cout, int R, int S, int pad, cudaStream_t stream, const XGeom* xg = nullptr) {
     const int Ho = H + 2 * pad - R + 1, Wo = W + 2 * pad - S + 1;
     TapMaps maps;
     TapParams p;
@@ -597,7 +614,11 @@ static int conv_wgrad_halo_impl(const float* x, const float* dy, float* dw_tck, 
     const int abox[4] = {32, p.box_w, p.box_h, p.box_n};
     const int bbox[4] = {32, p.halo_w, p.halo_h, p.box_n};
     if (make_nhwc_map(&maps.a[0], dy, B, Ho, Wo, Cout, 0, 0, 1, abox, true)) return 1;
-    if (make_nhwc_map(&maps.b[0], x, B, H, W, Cin, 0, 0, 1, bbox, true)) return 1;
+    if (xg) {
+        if (make_xgeom_map(&maps.b[0], x, B, H, W, *xg, bbox, true)) return 1;
+    } else if (make_nhwc_map(&maps.b[0], x, B, H, W, Cin, 0, 0, 1, bbox, true)) {
+        return 1;
+    }
     p.m_total = Cout;
     p.n_total = Cin;
     p.out = dw_tck;
@@ -614,11 +635,14 @@ static int conv_wgrad_halo_impl(const float* x, const float* dy, float* dw_tck, 
 }
 
 static int conv_wgrad_impl(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin,
-                           int Cout, int R, int S, int stride, int pad, cudaStream_t stream) {
+                           int Cout, int R, int S, int stride, int pad, cudaStream_t stream, const XGeom* xg = nullptr) {
     if (ensure_error_flag()) return 2;
     PE_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0, "conv channels must be multiples of 4");
-    if (g_dbg_wgrad_halo && stride == 1 && R * S > 1 && Cin % 32 == 0 && Cout % 32 == 0)
-        return conv_wgrad_halo_impl(x, dy, dw_tck, B, H, W, Cin, Cout, R, S, pad, stream);
+    PE_REQUIRE(!xg || (stride == 1 && pad == 0 && R * S > 1 && Cin % 32 == 0 && Cout % 32 == 0 &&
+                       (H - R + 1) % 8 == 0 && (W - S + 1) % 8 == 0),
+               "conv_wgrad: strided views go through the haloed multi-tap path (stride 1, no padding, 8 x 8 tiles)");
+    if ((g_dbg_wgrad_halo || xg) && stride == 1 && R * S > 1 && Cin % 32 == 0 && Cout % 32 == 0)
+        return conv_wgrad_halo_impl(x, dy, dw_tck, B, H, W, Cin, Cout, R, S, pad, stream, xg);
     const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
     TapMaps maps;
     TapParams p;
@@ -883,6 +907,40 @@ int pe_conv2d_dgrad_bn(const float* dy, const float* w_tkc, float* dx, int B, in
 int pe_conv2d_wgrad(const float* x, const float* dy, float* dw_tck, int B, int H, int W, int Cin, int Cout,
                     int R, int S, int stride, int pad, void* stream) {
     return conv_wgrad_impl(x, dy, dw_tck, B, H, W, Cin, Cout, R, S, stride, pad, (cudaStream_t)stream);
+}
+
+// ---- space-to-depth stem (torchvision resnet.py:197 conv1 = Conv2d(3, 64, 7, stride 2, pad 3)) ---------------------
+// out(ho, wo) = sum_{u, v in 0..7} in(2 ho + u - 4, 2 wo + v - 4) w8[u][v]   (w8 = the 7x7 filter behind a zero row and
+// column) = a 4 x 4 stride-1 convolution over the 2 x 2 space-to-depth image (12 channels).  Four horizontally adjacent
+// taps are 48 CONTIGUOUS floats of that NHWC tensor, so the A operand of filter row U is a TMA box over a view whose
+// pixel stride is 12 floats and whose channel extent is 48 (64 with TMA's zero fill): conv1 becomes the tap-GEMM's
+// ordinary conv mode with 4 taps x 64 channels -- no im2col matrix (2 GB per 256-frame step) in HBM.
+static XGeom stem_geom(int H, int W) {
+    XGeom g;
+    g.c_extent = 48;
+    g.sw = 12;
+    g.sh = 12ll * (W / 2 + 3);
+    g.sn = g.sh * (H / 2 + 3);
+    return g;
+}
+
+int pe_stem_conv_fwd(const float* s2d, const float* w_s2d, float* y, int B, int H, int W, int Cout, const float* scale,
+                     const float* shift, int relu, int round_out, double* stats, void* stream) {
+    PE_REQUIRE(H % 2 == 0 && W % 2 == 0 && H >= 16 && W >= 16, "stem: image %d x %d must have even sides", H, W);
+    Epilogue ep;
+    ep.scale = scale;
+    ep.shift = shift;
+    ep.relu = relu;
+    ep.round_out = round_out;
+    ep.stats = stats;
+    const XGeom g = stem_geom(H, W);
+    return conv_fwd_impl(s2d, w_s2d, y, B, H / 2 + 3, W / 2, 64, Cout, 4, 1, 1, 0, ep, (cudaStream_t)stream, &g);
+}
+
+int pe_stem_conv_wgrad(const float* s2d, const float* dy, float* dw_s2d, int B, int H, int W, int Cout, void* stream) {
+    PE_REQUIRE(H % 16 == 0 && W % 16 == 0, "stem wgrad: image %d x %d must have sides that are multiples of 16", H, W);
+    const XGeom g = stem_geom(H, W);
+    return conv_wgrad_impl(s2d, dy, dw_s2d, B, H / 2 + 3, W / 2, 64, Cout, 4, 1, 1, 0, (cudaStream_t)stream, &g);
 }
 
 int pe_linear_fwd(const float* x, int ldx, const float* w, int ldw, const float* bias, const float* scale, float* y,

@@ -20,6 +20,10 @@ FUSED_STEM_TAIL = [True]
 # BatchNorm backward pass 1 (sum g, sum g * xhat) of bn1 / bn2 of every Bottleneck inside the epilogue of the dgrad that
 # produces their output gradient (conv2 / conv3 dgrad); False = the stand-alone pe_bn_bwd_reduce launch
 FUSE_BN_REDUCE = [True]
+# 7x7/2 stem as a 4x4/1 convolution over the 2x2 space-to-depth image (pe_stem_conv_fwd / pe_stem_conv_wgrad: the
+# tap-GEMM reads a TMA view with overlapping pixel rows, no im2col matrix in HBM); False = im2col + GEMM (the path for
+# image sides that are not multiples of 16, kept under test)
+STEM_S2D = [True]
 # test hook: when set to a list, every training-mode convolution appends its raw output (an Act, execution order:
 # stem, then conv1 / conv2 / conv3 / downsample of each block) -- read by the parity tests (tests/model_checks.py)
 CAPTURE_CONV_OUTPUTS = [None]
@@ -136,6 +140,7 @@ class TrunkEngine:
             if i == 0:
                 self.w_tck.append(torch.zeros(co, 160, **f32))   # stem: [64][160] im2col-ordered, zero padded
                 self.w_tkc.append(None)
+                self.w_stem_s2d = torch.zeros(4, co, 64, **f32)  # stem, space-to-depth form: [filter row][Cout][64]
             else:
                 self.w_tck.append(torch.empty(r * s, co, ci, **f32))
                 self.w_tkc.append(torch.empty(r * s, ci, co, **f32))
@@ -156,6 +161,12 @@ class TrunkEngine:
         self._packed_version = None
         self._eval_version = None
 
+    def _stem_s2d_ok(self, H=224, W=224):
+        c1 = self.net.conv1
+        co, ci, r, s = c1.weight.shape
+        return (STEM_S2D[0] and (ci, r, s) == (3, 7, 7) and c1.stride[0] == 2 and c1.padding[0] == 3 and co % 32 == 0
+                and H % 16 == 0 and W % 16 == 0)
+
     def pack_weights(self, need_dgrad, force=False):
         """Refresh the TF32-rounded packed shadows if any weight changed since the last call."""
         ver = (_params_version(self._weights()), need_dgrad)
@@ -165,7 +176,9 @@ class TrunkEngine:
         w0 = self.convs[0][0].weight
         _dev_check(w0)
         co, ci, r, s = w0.shape
-        L.pe_copy_cols(P(w0), ci * r * s, P(self.w_tck[0]), 160, co, ci * r * s, self.round_tf32, st)
+        if self._stem_s2d_ok():
+            L.pe_stem_pack_weight(P(w0), P(self.w_stem_s2d), co, self.round_tf32, st)
+        self._stem_col_packed = False      # the im2col-ordered shadow is refreshed on demand (fallback path only)
         # all bottleneck convs in one launch; the pointer table is rebuilt only when a parameter moved
         key = (tuple(c.weight.data_ptr() for c, _ in self.convs[1:]), need_dgrad)
         if self._pack_key != key:
@@ -303,14 +316,34 @@ class TrunkEngine:
             tape = None
         dev = img.device
 
-        # ---- stem: im2col + GEMM (+BN1, ReLU), 3x3/2 max pool, aux branch -------------------------
-        col = torch.empty(B * Ho * Wo, 160, device=dev, dtype=torch.float32)
-        L.pe_im2col_stem(P(img), P(col), B, Cimg, H, W, r, s, stride, pad, 160, self.round_tf32, st)
+        # ---- stem: conv1 (+BN1, ReLU), 3x3/2 max pool, aux branch ---------------------------------
+        # conv1's operand: the zero-bordered space-to-depth image (162 MB at 256 frames) read through an overlapping TMA
+        # view, or -- for image sides that are not multiples of 16 -- the im2col matrix (2 GB) + a plain GEMM
+        s2d = self._stem_s2d_ok(H, W)
+        if s2d:
+            col = torch.empty(B, H // 2 + 3, W // 2 + 3, 12, device=dev, dtype=torch.float32)
+            L.pe_stem_s2d_pack(P(img), P(col), B, H, W, self.round_tf32, st)
+
+            def stem_gemm(scale, shift, relu, rnd, stats):
+                L.pe_stem_conv_fwd(P(col), P(self.w_stem_s2d), P(y0.t), B, H, W, 64, P(scale), P(shift), relu, rnd,
+                                   P(stats), st)
+        else:
+            if not self._stem_col_packed:
+                w0 = conv1.weight
+                L.pe_copy_cols(P(w0), w0[0].numel(), P(self.w_tck[0]), 160, w0.shape[0], w0[0].numel(), self.round_tf32,
+                               st)
+                self._stem_col_packed = True
+            col = torch.empty(B * Ho * Wo, 160, device=dev, dtype=torch.float32)
+            L.pe_im2col_stem(P(img), P(col), B, Cimg, H, W, r, s, stride, pad, 160, self.round_tf32, st)
+
+            def stem_gemm(scale, shift, relu, rnd, stats):
+                L.pe_linear_fwd(P(col), 160, P(self.w_tck[0]), 160, P(shift), P(scale), P(y0.t), 64, y0.P, 64, 160, relu,
+                                0, rnd, P(stats), st)
         y0 = Act(torch.empty(B * Ho * Wo, 64, device=dev, dtype=torch.float32), B, Ho, Wo, 64)
         if training:
             self.stats.zero_()
-            L.pe_linear_fwd(P(col), 160, P(self.w_tck[0]), 160, None, None, P(y0.t), 64, y0.P, 64, 160, 0, 0, 0,
-                            P(self._bn_views(0)[4]), st)
+            stem_gemm(None, None, 0, 0, self._bn_views(0)[4])
+            native.account("pe_stem_conv_fwd" if s2d else "pe_linear_fwd", 4 * (col.numel() + y0.t.numel()))
             if CAPTURE_CONV_OUTPUTS[0] is not None:
                 CAPTURE_CONV_OUTPUTS[0].append(y0)
             if tape is not None:
@@ -320,8 +353,7 @@ class TrunkEngine:
         else:
             self.prepare_eval()
             sc, sh = self._bn_views(0)[:2]
-            L.pe_linear_fwd(P(col), 160, P(self.w_tck[0]), 160, P(sh), P(sc), P(y0.t), 64, y0.P, 64, 160, 1, 0,
-                            self.round_tf32, None, st)
+            stem_gemm(sc, sh, 1, self.round_tf32, None)
             a1 = y0
             del col
         Hp, Wp = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
@@ -569,9 +601,16 @@ class TrunkEngine:
                 conv1 = self.net.conv1
                 co, ci, r, s = conv1.weight.shape
                 k = ci * r * s
-                tmp = torch.empty(co, 160, device=dev, dtype=torch.float32)
-                L.pe_linear_wgrad(P(col), 160, P(dy), co, P(tmp), 160, y0.P, co, 160, st)
-                L.pe_copy_cols(P(tmp), 160, P(grad_of(conv1.weight)), k, co, k, 0, st)
+                if col.dim() == 4:      # space-to-depth operand [B][H/2+3][W/2+3][12]
+                    Hi, Wi = 2 * (col.shape[1] - 3), 2 * (col.shape[2] - 3)
+                    tmp = torch.empty(4, co, 64, device=dev, dtype=torch.float32)
+                    L.pe_stem_conv_wgrad(P(col), P(dy), P(tmp), col.shape[0], Hi, Wi, co, st)
+                    L.pe_stem_unpack_wgrad(P(tmp), P(grad_of(conv1.weight)), co, st)
+                    native.account("pe_stem_conv_wgrad", 4 * (col.numel() + y0.t.numel()))
+                else:
+                    tmp = torch.empty(co, 160, device=dev, dtype=torch.float32)
+                    L.pe_linear_wgrad(P(col), 160, P(dy), co, P(tmp), 160, y0.P, co, 160, st)
+                    L.pe_copy_cols(P(tmp), 160, P(grad_of(conv1.weight)), k, co, k, 0, st)
                 if on_ready is not None:
                     ps = [conv1.weight, self.net.bn1.weight, self.net.bn1.bias]
                     if self.aux_conv is not None and self.aux_trainable:

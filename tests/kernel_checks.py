@@ -238,6 +238,50 @@ def check_stem(B):
     return out
 
 
+def check_stem_s2d(B, H=224, W=224):
+    """7x7/2 stem as a 4x4/1 convolution over the space-to-depth image (no im2col matrix): operand pack, weight pack /
+    gradient unpack round trip, forward with batch statistics, fused eval epilogue, weight gradient."""
+    L = native.lib()
+    g = torch.Generator(device=DEV).manual_seed(5 + B + H)
+    img = tf32(torch.randn(B, 3, H, W, device=DEV, generator=g))
+    w = tf32(torch.randn(64, 3, 7, 7, device=DEV, generator=g) / 12.0)
+    Ho, Wo, Hs, Ws = H // 2, W // 2, H // 2 + 3, W // 2 + 3
+    s2d = torch.full((B, Hs, Ws, 12), float("nan"), device=DEV)
+    L.pe_stem_s2d_pack(P(img), P(s2d), B, H, W, 0, S())
+    ref_s2d = torch.zeros(B, Hs, Ws, 12, device=DEV)
+    blk = img.reshape(B, 3, Ho, 2, Wo, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Ho, Wo, 12)    # (a, b, c) fastest
+    ref_s2d[:, 2:2 + Ho, 2:2 + Wo] = blk
+    tag = "B%d %dx%d" % (B, H, W)
+    out = [("stem s2d pack " + tag, relerr(s2d, ref_s2d), 0.0)]
+    w_s2d = torch.full((4, 64, 64), float("nan"), device=DEV)
+    L.pe_stem_pack_weight(P(w), P(w_s2d), 64, 0, S())
+    back = torch.zeros(64, 3, 7, 7, device=DEV)
+    L.pe_stem_unpack_wgrad(P(w_s2d), P(back), 64, S())
+    out.append(("stem weight pack/unpack round trip " + tag, relerr(back, w), 0.0))
+    out.append(("stem weight pack zero columns " + tag, float(w_s2d[:, :, 48:].abs().max()), 0.0))
+    wd = w.double().requires_grad_(True)
+    yd = F.conv2d(img.double(), wd, stride=2, padding=3)
+    y_ref = nhwc(yd.detach()).reshape(-1, 64)
+    y = torch.full((B * Ho * Wo, 64), float("nan"), device=DEV)
+    stats = torch.zeros(128, device=DEV, dtype=torch.float64)
+    L.pe_stem_conv_fwd(P(s2d), P(w_s2d), P(y), B, H, W, 64, None, None, 0, 0, P(stats), S())
+    out.append(("stem conv fwd (s2d) " + tag, relerr(y, y_ref), 1e-4))
+    out.append(("stem conv fwd stats " + tag, relerr(stats, torch.cat([y_ref.sum(0), (y_ref * y_ref).sum(0)])), 1e-4))
+    sc = torch.rand(64, device=DEV, generator=g) + 0.5
+    sh = torch.randn(64, device=DEV, generator=g)
+    L.pe_stem_conv_fwd(P(s2d), P(w_s2d), P(y), B, H, W, 64, P(sc), P(sh), 1, 0, None, S())
+    out.append(("stem conv fwd fused eval " + tag, relerr(y, (y_ref * sc.double() + sh.double()).clamp_min(0)), 1e-4))
+    if H % 16 == 0 and W % 16 == 0:
+        dy = tf32(torch.randn(B, 64, Ho, Wo, device=DEV, generator=g))
+        gw, = torch.autograd.grad(yd, wd, dy.double())
+        dw_s2d = torch.full((4, 64, 64), float("nan"), device=DEV)
+        L.pe_stem_conv_wgrad(P(s2d), P(nhwc(dy)), P(dw_s2d), B, H, W, 64, S())
+        dw = torch.zeros(64, 3, 7, 7, device=DEV)
+        L.pe_stem_unpack_wgrad(P(dw_s2d), P(dw), 64, S())
+        out.append(("stem conv wgrad (s2d) " + tag, relerr(dw, gw), 1e-4))
+    return out
+
+
 def check_bn(Pn, C, relu=True, residual=True):
     L = native.lib()
     g = torch.Generator(device=DEV).manual_seed(C + Pn)
@@ -761,6 +805,7 @@ PAIRS = [forced_pairs(f) for f in (
     lambda: check_conv_dgrad_bn(2, 56, 56, 128, 128, 3, 2) + check_conv_dgrad_bn(2, 56, 56, 64, 256, 1, 1),
     lambda: check_linear(300, 512, 256) + check_linear(1000, 2048, 3680, relu=True) + check_linear(129, 256, 64)
     + check_linear(640, 128, 512),
+    lambda: check_stem_s2d(2),
 )]
 
 ALL = [
@@ -790,6 +835,7 @@ ALL = [
     lambda: check_conv_halo_path(3, 28, 28, 128, 128, 3, 1),
     lambda: check_conv_fused_eval(2, 28, 28, 128, 512, 1),
     lambda: check_stem(2),
+    lambda: check_stem_s2d(2) + check_stem_s2d(3, 64, 96),
     lambda: check_bn(6272, 64),
     lambda: check_bn(1000, 256, relu=False, residual=False),
     lambda: check_bn(98, 2048),

@@ -352,6 +352,46 @@ def test_streaming_estimator_graph_with_fused_head():
         assert mc.rel(a, b) <= 1e-5, mc.rel(a, b)
 
 
+def test_space_to_depth_stem_matches_im2col_stem():
+    """conv1 as a 4x4/1 convolution over the space-to-depth image read through an overlapping TMA view
+    (pe_stem_conv_fwd / pe_stem_conv_wgrad, no im2col matrix) gives the same loss, gradients (conv1's weight included)
+    and BatchNorm buffers as im2col + GEMM.  The two sum conv1's 147 products in a different order; the 1e-7 difference
+    of the first layer flips a few ReLU masks downstream, and a flipped mask is an O(1) change of that element's
+    gradient: the loss agrees to 1e-4, BatchNorm buffers to 1e-3 (the re-rounding of every activation to TF32
+    amplifies the first layer's 1e-7 layer by layer: 1e-5 at layer3, 1.2e-4 at layer4 with 4 frames), eval outputs to 5e-3, the gradients of this shallow
+    trunk only to 0.2 (sanity bound; measured up to 6e-2).  The tight gradient checks of the stem are the
+    kernel check (fp64 reference, 1e-4) and the teacher-forced full-depth tests (common masks, 1e-2)."""
+    from models.losses import PoseDistanceLoss
+    from pe_b200 import engine
+    mc.SHALLOW[0] = True
+    img, x0, tgt = po.synthetic_batch("no", 4, seed=12)
+    img, x0, tgt = img.cuda(), x0.cuda(), tgt.cuda()
+    crit = PoseDistanceLoss(distance_metric="l2", alpha=0.5, mode="pose")
+    res = {}
+    for s2d in (False, True):
+        engine.STEM_S2D[0] = s2d
+        try:
+            model = mc.build_model("no").cuda().train()
+            with torch.no_grad():
+                getattr(model, "fc%d" % (model.n_fc - 1)).module.bias.fill_(0.5)
+            loss = crit(model(img, None, x0), tgt)
+            loss.backward()
+            model.eval()
+            with torch.no_grad():
+                ev = model(img, None, x0).clone()
+            res[s2d] = (float(loss), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None},
+                        {n: b.clone() for n, b in model.named_buffers()}, ev)
+        finally:
+            engine.STEM_S2D[0] = True
+    assert abs(res[True][0] - res[False][0]) <= 1e-4 * abs(res[False][0])
+    assert res[True][1].keys() == res[False][1].keys()
+    for n, g in res[False][1].items():
+        assert mc.relnorm(res[True][1][n], g) <= 0.2, (n, mc.relnorm(res[True][1][n], g))
+    for n, b in res[False][2].items():
+        assert mc.relnorm(res[True][2][n].float(), b.float()) <= 1e-3, n
+    assert mc.rel(res[True][3], res[False][3]) <= 5e-3
+
+
 def test_fused_stem_tail_matches_separate_kernels():
     """The one-pass stem tail (bn1 + ReLU + max pool + aux branch, pe_stem_post_train; bn1's output never written)
     gives the same loss, gradients and BN buffers as bn_train_apply + maxpool + aux as three kernels.  Tolerance
@@ -633,9 +673,11 @@ def test_latent_dims_that_are_not_multiples_of_four(kind, latent):
     fwd, grads, struct = _split(rows)
     bad = [(n, e) for n, e, t in fwd if not e <= max(t, 5e-3)] + [(n, e) for n, e, t in struct if e != 0.0]
     assert not bad, bad
-    # head-side gradients are well conditioned: the trunk fc (the layer whose shadows needed the padding) to 2e-2
+    # the trunk fc is the layer whose shadows needed the padding: a layout error there is an O(1) error.  Against the
+    # PLAIN fp32 oracle its gradient carries the TF32 operand error of a 3-frame batch (measured 1.5e-2 .. 2.4e-2
+    # depending on the summation order of the stem): 4e-2
     fc = [e for n, e in grads if ".fc.weight" in n or ".fc.bias" in n]
-    assert fc and max(fc) <= 2e-2, fc
+    assert fc and max(fc) <= 4e-2, fc
 
 
 @pytest.mark.parametrize("kind", ["tdo", "no"])
