@@ -69,16 +69,23 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh, int lddh, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// pose loss: one block, rows strided over threads, warp-shuffle + smem reduction, no atomics
+// pose loss: rows strided over the threads of ONE block -- or, from 4096 rows on, of a thread-block cluster of 8 CTAs
+// whose partial sums CTA 0 collects through distributed shared memory in rank order; warp-shuffle + smem reduction, no
+// atomics, so the result is deterministic for a given row count
 // ---------------------------------------------------------------------------------------------
+constexpr int POSE_LOSS_CLUSTER = 8;
+constexpr long long POSE_LOSS_CLUSTER_ROWS = 4096;
+
 __global__ void __launch_bounds__(256)
 pose_loss_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ truth, int ldt, long long n,
                  int metric, int mode, float alpha, float epsilon, float scale, float* __restrict__ loss,
                  float* __restrict__ dpred, int lddp, float* __restrict__ val) {
     pdl_sync();
     __shared__ float red[3][8];
+    __shared__ float part[4];                 // this CTA's partial sums (read by CTA 0 of the cluster)
+    const unsigned nctas = gridDim.x;         // 1, or the cluster size (the grid is exactly one cluster)
     float acc_loss = 0.f, acc_pos = 0.f, acc_ang = 0.f;
-    for (long long r = threadIdx.x; r < n; r += blockDim.x) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)nctas * blockDim.x) {
         const float* p = pred + r * ldp;
         const float* t = truth + r * ldt;
         const float d0 = p[0] - t[0], d1 = p[1] - t[1], d2 = p[2] - t[2];
@@ -157,19 +164,42 @@ pose_loss_kernel(const float* __restrict__ pred, int ldp, const float* __restric
         red[2][warp] = acc_ang;
     }
     __syncthreads();
+    float a = 0.f, b = 0.f, c = 0.f;
     if (threadIdx.x == 0) {
-        float a = 0.f, b = 0.f, c = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
             a += red[0][w];
             b += red[1][w];
             c += red[2][w];
         }
+        part[0] = a;
+        part[1] = b;
+        part[2] = c;
+    }
+    if (nctas > 1) {
+        // partial sums of the other CTAs through distributed shared memory, summed in rank order
+        cluster_sync_all();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            for (unsigned rk = 1; rk < nctas; ++rk) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(part)), "r"(rk));
+                float pa, pb, pc;
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pa) : "r"(remote) : "memory");
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pb) : "r"(remote + 4) : "memory");
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pc) : "r"(remote + 8) : "memory");
+                a += pa;
+                b += pb;
+                c += pc;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (loss) loss[0] = scale * a;
         if (val) {
             val[0] = b;
             val[1] = c;
         }
     }
+    if (nctas > 1) cluster_sync_all();        // nobody's shared memory disappears while CTA 0 is still reading it
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -278,8 +308,24 @@ int pe_pose_loss(const float* pred, int ldp, const float* truth, int ldt, long l
                  void* stream) {
     PE_REQUIRE(metric >= 0 && metric <= 3, "pose_loss: metric %d invalid", metric);
     PE_REQUIRE(mode == 0 || mode == 1, "pose_loss: mode %d invalid", mode);
-    PE_LAUNCH(pose_loss_kernel, 1, 256, 0, pred, ldp, truth, ldt, n, metric, mode, alpha, epsilon, scale, loss, dpred,
-              lddp, val);
+    if (n >= POSE_LOSS_CLUSTER_ROWS) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(POSE_LOSS_CLUSTER);
+        cfg.blockDim = dim3(256);
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = POSE_LOSS_CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pose_loss_kernel, pred, ldp, truth, ldt, n, metric, mode, alpha, epsilon,
+                                         scale, loss, dpred, lddp, val));
+    } else {
+        PE_LAUNCH(pose_loss_kernel, 1, 256, 0, pred, ldp, truth, ldt, n, metric, mode, alpha, epsilon, scale, loss, dpred,
+                  lddp, val);
+    }
     PE_LAUNCH_CHECK();
     return 0;
 }

@@ -845,6 +845,7 @@ ALL = [
     lambda: check_stem_tail(3, 1),
     lambda: check_lstm_cell(5, 512),
     lambda: check_loss(37),
+    lambda: check_loss(4096) + check_loss(20011),      # thread-block-cluster reduction (>= 4096 rows)
     lambda: check_conv_dgrad_bn(3, 28, 28, 128, 512, 1, 1) + check_conv_dgrad_bn(2, 56, 56, 64, 64, 3, 1),
     lambda: check_conv_dgrad_bn(5, 14, 14, 256, 1024, 1, 1) + check_conv_dgrad_bn(3, 14, 14, 256, 256, 3, 1),
     lambda: check_conv_dgrad_bn(2, 28, 28, 256, 256, 3, 2) + check_conv_dgrad_bn(3, 7, 7, 512, 2048, 1, 1),
