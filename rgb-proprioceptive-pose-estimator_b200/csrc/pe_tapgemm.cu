@@ -1,7 +1,8 @@
 // tcgen05 / TMEM / TMA tap-GEMM kernel (see pe_tapgemm.cuh for the contract).
 //
 // Persistent, warp-specialised: one CTA per SM walks the (n-tile, m-tile, z) work list round-robin.
-//   warp 0        TMA producer   : runs ahead through a 2-6 stage smem ring, across tile boundaries
+//   warp 0        TMA producer   : runs ahead through a 2-8 stage smem ring, across tile boundaries (the ring
+//                                  depth is what bounds narrow tiles: DESIGN 3.1)
 //   warp 1        MMA issuer     : tcgen05.mma into one of TWO 256-column TMEM accumulators, so tile i+1
 //                                  accumulates while tile i is drained (mode 2: all 512 columns hold one set of
 //                                  per-tap accumulators)
