@@ -51,7 +51,8 @@ void pe_debug_min_bn(int bn);
 void pe_debug_wgrad_halo(int mode);
 /* debug: 0 = epilogue reads residual rows with plain global loads instead of TMA-prefetched tiles */
 void pe_debug_residual_tma(int on);
-/* debug: force the number of epilogue warp groups of the tap-GEMM (2 or 4); 0 = automatic */
+/* debug: force the number of epilogue warp groups of the tap-GEMM (2 or 4); 0 = automatic; 6 = automatic without the
+ * four-group rule for residual-prefetch dgrads on CTA pairs */
 void pe_debug_epilogue_groups(int groups);
 /* debug: haloed-tile path for 3x3 stride-1 forward / dgrad with <= 128 input channels (0 = per-tap boxes) */
 void pe_debug_conv_halo(int on);

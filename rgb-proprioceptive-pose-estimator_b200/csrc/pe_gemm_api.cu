@@ -185,7 +185,7 @@ static void init_params(TapParams& p) {
 static int g_dbg_max_bn = 256;
 static int g_dbg_res_tma = 1;
 static int g_dbg_min_bn = 32;         // narrowest tile the small-launch heuristic of pick_bn may choose
-static int g_dbg_epi_groups = 0;      // 0 = automatic, 2 / 4 = forced
+static int g_dbg_epi_groups = 0;      // 0 = automatic, 2 / 4 = forced, 6 = automatic without the residual-launch rule
 // Tile width.  Wide tiles halve the operand traffic per MMA, but a launch with only a handful of tiles (rollout at
 // batch 1: 49-3136 pixels per image) would leave most SMs idle behind one long serial K loop: there the width is
 // halved (down to 64) until the tile count reaches half the SM count.
@@ -231,14 +231,22 @@ static void pick_pipeline(TapParams& p, int ksteps) {
                        (p.bn_bwd ? 2 * TG_MAX_BN * (int)sizeof(float) : 0) - p.nres * TG_A_BYTES;
     // Store-bound launches (training-mode conv with batch statistics, wide tile, short K loop) are limited by the
     // epilogue's instruction latency, not by HBM: they run four epilogue groups (16 warps) instead of two.
-    // (the residual prefetch buffers are laid out for two groups: residual launches always run two)
     p.epi_groups = (!p.residual && (g_dbg_epi_groups == 4 ||
                                     (g_dbg_epi_groups == 0 && p.stats && p.store_mode == TG_STORE_TMA &&
                                      p.bn >= 128 && ksteps < 24))) ? 4 : 2;
+    // The dgrads that add a TMA-prefetched residual tile (conv1 of every block: short K loop, 128 KB read + 128 KB
+    // written per tile) are epilogue-bound as well: on CTA pairs (whose 32 KB stages leave the room) they run four groups
+    // with ONE residual and ONE staging buffer each instead of two groups with two -- when the K loop is at most four
+    // steps, because the extra staging buffers leave the ring two stages (measured, 256 frames: 56x56 256->64 377 -> 337
+    // us, 56x56 256->128 399 -> 341, 28x28 512->128 203 -> 175; with 8 or 16 k-steps 28x28 512->256 205 -> 220, 7x7
+    // 2048->512 73 -> 94: those keep two groups; pe_debug_epilogue_groups(6) = the old rule everywhere)
+    if (p.residual && p.nres == 4 && !p.bn_bwd && p.cta_group == 2 && ksteps <= 4 &&
+        (g_dbg_epi_groups == 0 || g_dbg_epi_groups == 4))
+        p.epi_groups = 4;
     // (the staging buffers are split evenly between the epilogue groups)
     int nout = (p.store_mode == TG_STORE_TMA) ? (p.epi_groups == 4 ? 4 : (ksteps >= 24 ? 2 : 4)) : 0;
-    if (p.nres && p.bn > 128) nout = 2;
-    if (g_dbg_nout > 0 && p.store_mode == TG_STORE_TMA) nout = g_dbg_nout;
+    if (p.nres && p.bn > 128 && p.epi_groups != 4) nout = 2;
+    if (g_dbg_nout > 0 && p.store_mode == TG_STORE_TMA && !(p.epi_groups == 4 && g_dbg_nout < 4)) nout = g_dbg_nout;
     int stages = (budget - nout * TG_A_BYTES) / p.stage_bytes;
     if (stages > TG_STAGES) stages = TG_STAGES;
     if (g_dbg_stages > 0 && g_dbg_stages < stages) stages = g_dbg_stages;

@@ -56,6 +56,8 @@ def main():
                 L.pe_debug_cta_group(2)
             elif f == 4000:
                 L.pe_debug_epilogue_groups(4)
+            elif f == 4006:
+                L.pe_debug_epilogue_groups(6)
             elif f == 2002:
                 L.pe_debug_epilogue_groups(2)
             elif f == 2000:
