@@ -632,6 +632,7 @@ static int conv_wgrad_halo_impl(const float* x, const float* dy, float* dw_tck, 
     p.out = dw_tck;
     p.out_tap_stride = (long long)Cout * Cin;
     p.ldo = Cin;
+    p.m64 = (Cout <= 64 && !(g_dbg_flags & 4096)) ? 1 : 0;
     const int mt = (Cout + TG_BM - 1) / TG_BM, nt = (Cin + p.bn - 1) / p.bn;
     const int ks = pick_ksplit(mt * nt * p.n_groups, p.pt_total, 2);
     p.ksplit = ks;

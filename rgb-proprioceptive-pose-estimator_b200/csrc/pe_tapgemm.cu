@@ -390,7 +390,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
     } else if (warp == 1) {
         // =============================== MMA issuer ==========================================
         // Convergent warp, uniform descriptors, one elected lane per tcgen05.mma / tcgen05.commit.
-        const uint32_t idesc = make_idesc_tf32(TG_BM * CG, p.bn, p.mode != 0, p.mode != 0);
+        // (m64: a weight gradient with at most 64 output channels issues M = 64 instructions -- they retire in 32 clk at 64
+        //  columns where the zero-padded M = 128 form takes 48, and read half the A rows; tests/probe_mma_rate.cu)
+        const uint32_t idesc = make_idesc_tf32(p.m64 ? 64 : TG_BM * CG, p.bn, p.mode != 0, p.mode != 0);
         // K-major: LBO unused (16 B), SBO = 8 rows * 128 B.  MN-major: LBO = one 32-wide
         // atom column (32 k-rows * 128 B), SBO = 4 k-rows * 128 B (128B_BASE32B atoms).
         const uint32_t a_lbo = p.dbg_a_lbo >= 0 ? p.dbg_a_lbo : (p.mode ? 4096 : 16);
@@ -557,7 +559,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         const int ew = warp - 2;           // 0..7
         const int grp = ew >> 2;           // epilogue group
         const int q = warp & 3;            // TMEM lane quarter this warp may read
-        const int row = q * 32 + lane;     // tile row == TMEM lane
+        // tile row == TMEM lane; an M = 64 accumulator keeps rows 16 q .. 16 q + 15 in the first 16 lanes of each 32-lane
+        // quarter (the other lanes get a row index past every bound and store nothing)
+        const int row = p.m64 ? (lane < 16 ? q * 16 + lane : TG_BM) : q * 32 + lane;
         const int et = (ew & 3) * 32 + lane;      // 0..127 within the group
         const int eall = ew * 32 + lane;          // 0..EPI_THREADS-1 over all groups
         const int bar_id = 1 + grp;               // named barriers 1..G: one per group; G+1: all epilogue threads

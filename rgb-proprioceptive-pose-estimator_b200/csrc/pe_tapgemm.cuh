@@ -78,6 +78,7 @@ struct TapParams {
     int dbg_flags;            // 1: skip TMA store issue, 2: skip staging write + store, 4: skip A loads, 8: skip B loads
     // mode 2 (haloed wgrad): pixel tile box_w x box_h x box_n (box_w % 8 == 0), halo tile halo_w x halo_h x box_n
     int tg_taps, n_groups;    // taps per work item (tg_taps * bn <= 512 TMEM columns), number of tap groups
+    int m64;                  // modes 1 / 2 with m_total <= 64: tcgen05.mma M = 64 (rows 16 q + i in lane 32 q + i)
     int halo_w, halo_h;       // box_w + S - 1, box_h + R - 1
     int halo_dw, halo_dh;     // halo origin relative to the pixel tile origin (-pad)
     int a_atom_bytes, b_atom_bytes;   // bytes between 32-channel atoms of the dY / X tiles in a stage

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) probe_kernel(Result* res, float* dump_ss,
     // exactly representable small integers
     for (int i = tid; i < 128 * 32; i += 128) {
         int r = i >> 5, k = i & 31;
-        A[sw128(r, k)] = (float)(((r * 7 + k * 3) % 13) - 6);
+        A[sw128(r, k)] = (float)(((r * 37 + k * 11) % 127) - 63);
     }
     for (int i = tid; i < 256 * 32; i += 128) {
         int r = i >> 5, k = i & 31;
@@ -231,7 +231,7 @@ int main() {
     cudaMemcpy(ss.data(), dss, ss.size() * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(ts.data(), dts, ts.size() * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(m64.data(), dm64, m64.size() * 4, cudaMemcpyDeviceToHost);
-    auto Af = [](int r, int k) { return (float)(((r * 7 + k * 3) % 13) - 6); };
+    auto Af = [](int r, int k) { return (float)(((r * 37 + k * 11) % 127) - 63); };
     auto Bf = [](int r, int k) { return (float)(((r * 5 + k * 11) % 9) - 4); };
     int bad_ss = 0, bad_ts = 0;
     for (int m = 0; m < 128; ++m)
