@@ -24,12 +24,17 @@ struct TileOrigin {
     int w0, h0, n0;
 };
 
+// n / d for a divisor prepared by launch_tapgemm (TapParams::fd_*), 0 <= n < 2^31
+__device__ __forceinline__ int fast_div(int n, const unsigned (&fd)[2]) {
+    return fd[0] ? static_cast<int>(__umulhi(static_cast<unsigned>(n), fd[0]) >> fd[1]) : n;
+}
+
 __device__ __forceinline__ TileOrigin tile_origin(const TapParams& p, int t) {
     TileOrigin o;
-    int tw = t % p.tiles_w;
-    int r = t / p.tiles_w;
-    int th = r % p.tiles_h;
-    int tn = r / p.tiles_h;
+    const int r = fast_div(t, p.fd_tiles_w);
+    const int tw = t - r * p.tiles_w;
+    const int tn = fast_div(r, p.fd_tiles_h);
+    const int th = r - tn * p.tiles_h;
     o.w0 = tw * p.box_w;
     o.h0 = th * p.box_h;
     o.n0 = tn * p.box_n;
@@ -44,14 +49,14 @@ struct Work {
 
 __device__ __forceinline__ Work decode_work(const TapParams& p, int w) {
     Work k;
-    k.nt = w % p.work_n;
-    const int r = w / p.work_n;
-    k.mt = r % p.work_m;
-    k.z = r / p.work_m;
+    const int r = fast_div(w, p.fd_work_n);
+    k.nt = w - r * p.work_n;
+    k.z = fast_div(r, p.fd_work_m);
+    k.mt = r - k.z * p.work_m;
     k.tap = 0;
     if (p.mode == 0) {
         const int ktotal = p.n_taps * p.chunks;
-        const int per = (ktotal + p.ksplit - 1) / p.ksplit;
+        const int per = p.k_per;
         k.k_begin = k.z * per;
         k.nk = max(0, min(ktotal, k.k_begin + per) - k.k_begin);
     } else if (p.mode == 1) {
@@ -59,14 +64,14 @@ __device__ __forceinline__ Work decode_work(const TapParams& p, int w) {
         // so the dY / X tiles they share are served from L2 instead of being re-read from HBM per tap
         k.tap = k.z % p.n_taps;
         const int split = k.z / p.n_taps;
-        const int per = (p.pt_total + p.ksplit - 1) / p.ksplit;
+        const int per = p.k_per;
         k.k_begin = split * per;
         k.nk = max(0, min(p.pt_total, k.k_begin + per) - k.k_begin);
     } else {
         // haloed wgrad: z = split * n_groups + tap group; `tap` is the first tap of the group
         k.tap = (k.z % p.n_groups) * p.tg_taps;
         const int split = k.z / p.n_groups;
-        const int per = (p.pt_total + p.ksplit - 1) / p.ksplit;
+        const int per = p.k_per;
         k.k_begin = split * per;
         k.nk = max(0, min(p.pt_total, k.k_begin + per) - k.k_begin);
     }
@@ -567,6 +572,10 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
         const int bar_id = 1 + grp;               // named barriers 1..G: one per group; G+1: all epilogue threads
         constexpr int BAR_ALL = G + 1;
         constexpr int SLOTS = (TG_MAX_BN / 32 + G - 1) / G;      // chunks of one tile a group can own
+        // this thread's pixel inside a conv tile (row -> (dw, dh, dn)): the same for every tile
+        const int row_dw = p.mode == 0 ? row % p.box_w : 0;
+        const int row_dh = p.mode == 0 ? (row / p.box_w) % p.box_h : 0;
+        const int row_dn = p.mode == 0 ? (row / p.box_w) / p.box_h : 0;
         const int nbuf = p.nout / G > 0 ? p.nout / G : 1;        // staging buffers per group
         const uint32_t my_stage = stage_base + (p.nout >= G ? grp * nbuf : 0) * TG_A_BYTES;
         // bn_bwd mode (dgrad whose output is the gradient of a BatchNorm + ReLU activation): the TMA-prefetched
@@ -653,11 +662,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             TileOrigin o = {0, 0, 0};
             if (p.mode == 0) {
                 o = tile_origin(p, wk.mt);
-                const int dw = row % p.box_w;
-                const int r2 = row / p.box_w;
-                const int dh = r2 % p.box_h;
-                const int dn = r2 / p.box_h;
-                const int wq = o.w0 + dw, hq = o.h0 + dh, nq = o.n0 + dn;
+                const int wq = o.w0 + row_dw, hq = o.h0 + row_dh, nq = o.n0 + row_dn;
                 row_valid = (row < p.m_rows) && (wq < p.out_w) && (hq < p.out_h) && (nq < p.out_n);
                 row_lin = (static_cast<long long>(nq) * p.out_h + hq) * p.out_w + wq;
             } else {
@@ -784,7 +789,7 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
                 }
                 // ---- store ---------------------------------------------------------------------
                 if (p.store_mode == TG_STORE_TMA) {
-                    const uint32_t region = my_stage + (cc % nbuf) * TG_A_BYTES;
+                    const uint32_t region = my_stage + (nbuf == 2 ? (cc & 1u) : (cc % nbuf)) * TG_A_BYTES;
                     // the store issued from this buffer `nbuf` chunks ago must have finished reading it
                     if (et == 0) {
                         if (nbuf >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -999,6 +1004,23 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
     p.work_n = work.x;
     p.work_m = work.y;
     p.work_total = static_cast<int>(work.x * work.y * work.z);
+    {
+        // multiply-shift division by the work-list constants: m = ceil(2^(31 + ceil(log2 d)) / d), exact for n < 2^31
+        auto fast_div_of = [](unsigned (&fd)[2], int d) {
+            fd[0] = fd[1] = 0;
+            if (d <= 1) return;
+            unsigned l = 0;
+            while ((1u << l) < static_cast<unsigned>(d)) ++l;
+            fd[0] = static_cast<unsigned>(((1ull << (31 + l)) + d - 1) / d);
+            fd[1] = l - 1;
+        };
+        fast_div_of(p.fd_work_n, p.work_n);
+        fast_div_of(p.fd_work_m, p.work_m);
+        fast_div_of(p.fd_tiles_w, p.tiles_w);
+        fast_div_of(p.fd_tiles_h, p.tiles_h);
+        const int ks = p.ksplit > 0 ? p.ksplit : 1;
+        p.k_per = ((p.mode == 0 ? p.n_taps * p.chunks : p.pt_total) + ks - 1) / ks;
+    }
     // one CTA per SM, or one CTA pair per TPC (the work list then counts pairs of tiles)
     // (minus the SMs set aside for a concurrent collective: a persistent grid that needs EVERY SM would otherwise wait
     // for the NCCL kernel's CTAs and run its last tiles as a second wave)

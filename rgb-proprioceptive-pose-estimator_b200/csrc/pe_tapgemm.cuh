@@ -52,6 +52,11 @@ struct TapParams {
     int ksplit;               // K splits (conv: gridDim.z; wgrad: per tap)
     int pt_total;             // wgrad: number of 32-pixel tiles
     int work_n, work_m, work_total;  // persistent work list: (n tile, m tile, z), n fastest
+    // Division by the run-time constants of the work list without the ~25-instruction integer-divide sequence (every
+    // warp of the CTA decodes every work item: for short-K tiles the divisions were a fifth of all stall samples):
+    // q = umulhi(n, mul) >> shr for 0 <= n < 2^31 (mul == 0: divisor 1).  Filled by launch_tapgemm.
+    unsigned fd_work_n[2], fd_work_m[2], fd_tiles_w[2], fd_tiles_h[2];
+    int k_per;                // k-steps (mode 0) / pixel tiles (modes 1, 2) per K split
     int m_total, n_total;     // logical output extents (wgrad rows; columns in both modes)
     signed char tap_dw[TG_MAX_TAPS], tap_dh[TG_MAX_TAPS], tap_map[TG_MAX_TAPS], tap_b[TG_MAX_TAPS];
     int store_mode;
