@@ -24,6 +24,14 @@ def main():
             from pe_b200 import native
             native.lib().pe_debug_pdl(0)
             argv.remove(a)
+        elif a.startswith("--epi-groups="):
+            from pe_b200 import native
+            native.lib().pe_debug_epilogue_groups(int(a.split("=")[1]))
+            argv.remove(a)
+        elif a.startswith("--cta-group="):
+            from pe_b200 import native
+            native.lib().pe_debug_cta_group(int(a.split("=")[1]))
+            argv.remove(a)
         elif a.startswith("--min-bn="):
             from pe_b200 import native
             native.lib().pe_debug_min_bn(int(a.split("=")[1]))
