@@ -620,8 +620,9 @@ tapgemm_kernel(const __grid_constant__ TapMaps maps, const __grid_constant__ Tap
             const uint32_t aph = p.mode == 2 ? (tile_i & 1) : ((tile_i >> 1) & 1);
             if (wk.nk > 0) ++tile_i;
 
-            // per-tile column constants (everyone is past the previous tile's reads after this barrier)
-            if (affine || bnb) {
+            // per-tile column constants (everyone is past the previous tile's reads after this barrier); with a single
+            // column tile (work_n == 1: every tile has the same columns) they are loaded for the first tile only
+            if ((affine || bnb) && (p.work_n > 1 || w == w_first)) {
                 asm volatile("bar.sync %0, %1;" ::"n"(BAR_ALL), "n"(EPI_THREADS) : "memory");
                 for (int cidx = eall; cidx < p.bn; cidx += EPI_THREADS) {
                     const int col = n_off + cidx;
