@@ -4,8 +4,20 @@ across ranks, gradients SUMMED with NCCL in backward-ordered buckets on a side s
 The reference's own nn.DataParallel wrappers are single-process pass-throughs on <= 1 device and wrong
 on more; the only exchange step of the path is the gradient all-reduce below.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+# measurement probe (profiles/ddp_overlap_*): PE_B200_SKIP_ALLREDUCE=1 drops the collective itself (the per-bucket
+# optimizer update still runs on the communication stream), so step time with / without it = the EXPOSED share of the
+# gradient all-reduce.  The gradients are then per-rank: never set it outside that measurement.
+_SKIP_ALLREDUCE = os.environ.get("PE_B200_SKIP_ALLREDUCE", "0") == "1"
+
+
+class _Done:
+    def wait(self):
+        return True
 
 
 def shard_range(n, rank, world):
@@ -46,7 +58,8 @@ class BucketedAllReduce:
             ev = torch.cuda.current_stream().record_event()
             self.stream.wait_event(ev)
             with torch.cuda.stream(self.stream):
-                w = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                w = _Done() if _SKIP_ALLREDUCE else dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group,
+                                                                   async_op=True)
                 if self.after is not None:
                     w.wait()                  # stream-level dependency on the collective, the host does not block
                     self.after(lo, hi)

@@ -10,6 +10,8 @@ Multi-GPU: one process per GPU, batch (naive) or episodes (sequence models) shar
 gradients summed (not averaged: the loss is a sum over samples, models/losses.py:75,128) with NCCL in
 backward-ordered buckets on a side stream; BatchNorm statistics stay per GPU.
 """
+import os
+
 import torch
 
 from . import native
@@ -67,7 +69,7 @@ class FusedTrainer:
 
     def __init__(self, model, distance_metric="l2", alpha=1.0, epsilon=1e-4, scale_factor=1.0, mode="pose",
                  lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, optimizer="adam", momentum=0.0,
-                 process_group=None, bucket_mb=8, sm_reserve=None):
+                 process_group=None, bucket_mb=32, sm_reserve=None):
         if mode not in ("pose", "position"):
             raise ValueError("training loss mode must be 'pose' or 'position'")
         self.model = model
@@ -77,9 +79,12 @@ class FusedTrainer:
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.optimizer, self.momentum = optimizer, momentum
         self.pg = process_group
-        self.bucket_bytes = bucket_mb << 20
+        # All-reduce bucket size.  Measured on 8 x B200, config 2 (profiles/ddp_overlap_r02c.txt): 8 MB buckets 34.92
+        # ms/step, 32 MB 33.55, one all-reduce after the backward pass 33.41 (no collective at all: 33.92 on another box).
+        # Every NCCL kernel in flight takes SMs from the persistent one-CTA-per-SM GEMM grids, whose last tiles then run as a
+        # second wave: a few large buckets overlap almost as much and disturb far less than many small ones.
+        self.bucket_bytes = int(os.environ.get("PE_B200_BUCKET_MB", bucket_mb)) << 20
         # SMs the persistent GEMM grids leave to the NCCL kernels during the backward pass (multi-GPU only)
-        import os
         self.sm_reserve = int(os.environ.get("PE_B200_SM_RESERVE", "0")) if sm_reserve is None else sm_reserve
         self.t = 0
         self._flat = None
