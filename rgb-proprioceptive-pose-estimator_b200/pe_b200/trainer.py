@@ -151,7 +151,7 @@ class FusedTrainer:
 
         Multi-GPU: from the second step on, every all-reduce bucket is followed on the communication stream by the
         optimizer update of exactly that arena range, so reducing and updating the head / layer4 / layer3 buckets
-        overlaps the backward pass of the earlier layers; only the last (stem-side, <= bucket_mb) bucket is exposed."""
+        overlaps the backward pass of the earlier layers; the last (stem-side) bucket's reduce + update is exposed."""
         if self._flat is None:
             self._flatten()
         self._fused_update = self.reducer is not None and self.t > 0
