@@ -36,6 +36,9 @@ void pe_debug_flags(int flags);
 /* CTA pairs (tcgen05 cta_group::2, 256-row MMAs over two SMs): 0 automatic (wide tiles of large launches), 1 never,
  * 2 whenever the launch allows it */
 void pe_debug_cta_group(int mode);
+/* test hook (host only): n / d as the tap-GEMM's divide-free work-list decode computes it (multiply-shift by constants
+ * prepared per launch); exact for 0 <= n < 2^31, d >= 1 */
+int pe_debug_fast_div(int n, int d);
 /* Number of SMs the persistent tap-GEMM grids leave unused (0 = none).  The data-parallel trainer sets it during the
  * backward pass, while NCCL gradient all-reduce kernels share the GPU: a one-CTA-per-SM grid that needs every SM
  * would wait for the collective's CTAs and finish with a straggler wave. */

@@ -845,6 +845,14 @@ void pe_debug_pdl(int mask) { pe::g_pdl = mask & 3; }
 
 void pe_debug_cta_group(int mode) { g_dbg_cta_group = mode; }
 
+int pe_debug_fast_div(int n, int d) {
+    // host-side replay of the kernel's divide-free work-list decode (fast_div in pe_tapgemm.cu) for the CPU tests
+    unsigned fd[2];
+    pe::fast_div_of(fd, d);
+    if (!fd[0]) return n;
+    return static_cast<int>(((static_cast<unsigned long long>(static_cast<unsigned>(n)) * fd[0]) >> 32) >> fd[1]);
+}
+
 void pe_set_sm_reserve(int sms) { pe::g_sm_reserve = sms > 0 ? sms : 0; }
 
 void pe_debug_conv_halo(int on) {

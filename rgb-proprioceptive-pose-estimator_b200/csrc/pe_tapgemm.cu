@@ -975,6 +975,17 @@ bool pdl_enabled(int kind) {
     return (g_pdl & kind) != 0;
 }
 
+// Multiply-shift division by a launch constant (TapParams::fd_*, fast_div() in the kernel): m = ceil(2^(31 + l) / d) with
+// l = ceil(log2 d), q = umulhi(n, m) >> (l - 1), exact for 0 <= n < 2^31; {0, 0} encodes d <= 1.
+void fast_div_of(unsigned (&fd)[2], int d) {
+    fd[0] = fd[1] = 0;
+    if (d <= 1) return;
+    unsigned l = 0;
+    while ((1u << l) < static_cast<unsigned>(d)) ++l;
+    fd[0] = static_cast<unsigned>(((1ull << (31 + l)) + d - 1) / d);
+    fd[1] = l - 1;
+}
+
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
@@ -1006,15 +1017,6 @@ int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t st
     p.work_m = work.y;
     p.work_total = static_cast<int>(work.x * work.y * work.z);
     {
-        // multiply-shift division by the work-list constants: m = ceil(2^(31 + ceil(log2 d)) / d), exact for n < 2^31
-        auto fast_div_of = [](unsigned (&fd)[2], int d) {
-            fd[0] = fd[1] = 0;
-            if (d <= 1) return;
-            unsigned l = 0;
-            while ((1u << l) < static_cast<unsigned>(d)) ++l;
-            fd[0] = static_cast<unsigned>(((1ull << (31 + l)) + d - 1) / d);
-            fd[1] = l - 1;
-        };
         fast_div_of(p.fd_work_n, p.work_n);
         fast_div_of(p.fd_work_m, p.work_m);
         fast_div_of(p.fd_tiles_w, p.tiles_w);

@@ -109,6 +109,7 @@ struct TapParams {
     const float* bn_invstd;
 };
 
+void fast_div_of(unsigned (&fd)[2], int d);   // multiply-shift constants of TapParams::fd_* for the divisor d
 int launch_tapgemm(const TapMaps& maps, TapParams& p, dim3 work, cudaStream_t stream);
 
 }  // namespace pe

@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
 
 # entry points whose int return value is a VALUE, not a status code
 _VALUE_RETURNING = ("pe_version", "pe_device_error", "pe_pack_block_elems", "pe_head_desc_size",
-                    "pe_lstm_seq_supported")
+                    "pe_lstm_seq_supported", "pe_debug_fast_div")
 
 
 class PeError(RuntimeError):

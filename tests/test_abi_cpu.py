@@ -219,3 +219,20 @@ def test_tapgemm_shared_memory_fits_the_sm():
             found += 1
             assert int(m.group(1)) + dyn <= 227 * 1024, (line, m.group(1), dyn)
     assert found >= 4, out[:500]
+
+
+def test_divide_free_work_decode_constants():
+    """The tap-GEMM decodes its persistent work list with multiply-shift divisions by constants prepared per launch
+    (pe_tapgemm.cu: fast_div_of / fast_div).  pe_debug_fast_div replays the kernel's formula on the host with the
+    launcher's own constants: it must equal n // d for every divisor the planner can produce and every n < 2^31."""
+    import random
+    L = native.lib()
+    rng = random.Random(7)
+    divisors = list(range(1, 1200)) + [2 ** k for k in range(1, 21)] + [2 ** k + 1 for k in range(1, 21)] + \
+        [rng.randrange(1, 1 << 22) for _ in range(300)]
+    for d in divisors:
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1, 2 ** 31 - d, 2 ** 30] + \
+            [rng.randrange(0, 1 << 31) for _ in range(20)]
+        for n in ns:
+            if 0 <= n < 2 ** 31:
+                assert L.pe_debug_fast_div(n, d) == n // d, (n, d)
