@@ -236,3 +236,58 @@ def test_divide_free_work_decode_constants():
         for n in ns:
             if 0 <= n < 2 ** 31:
                 assert L.pe_debug_fast_div(n, d) == n // d, (n, d)
+
+
+def test_space_to_depth_stem_identity():
+    """The arithmetic behind pe_stem_s2d_pack / pe_stem_pack_weight / pe_stem_conv_fwd, restated in plain torch on the
+    CPU: conv1 = Conv2d(3, 64, 7, stride 2, padding 3) (torchvision resnet.py:197) equals a 4-tap GEMM whose operand row
+    for output pixel (ho, wo) and filter row U is the 48 contiguous floats (+ 16 that multiply zero weights) starting at
+    pixel (ho + U, wo) of the zero-bordered space-to-depth tensor [H/2 + 3][W/2 + 3][12], channel a * 6 + b * 3 + c =
+    img[c][2 I + a][2 J + b], against weights [U][co][V * 12 + a * 6 + b * 3 + c] = w[co][c][2 U + a - 1][2 V + b - 1]."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    B, H, W, Co = 2, 32, 48, 8
+    img = torch.randn(B, 3, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Co, 3, 7, 7, generator=g, dtype=torch.float64)
+    ref = F.conv2d(img, w, stride=2, padding=3)                                   # [B, Co, H/2, W/2]
+    Ho, Wo, Hs, Ws = H // 2, W // 2, H // 2 + 3, W // 2 + 3
+    s2d = torch.zeros(B, Hs, Ws, 12, dtype=torch.float64)
+    s2d[:, 2:2 + Ho, 2:2 + Wo] = img.reshape(B, 3, Ho, 2, Wo, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Ho, Wo, 12)
+    w_s2d = torch.zeros(4, Co, 64, dtype=torch.float64)
+    for U in range(4):
+        for V in range(4):
+            for a in range(2):
+                for b in range(2):
+                    r, q = 2 * U + a - 1, 2 * V + b - 1
+                    if r >= 0 and q >= 0:
+                        w_s2d[U, :, V * 12 + a * 6 + b * 3:V * 12 + a * 6 + b * 3 + 3] = w[:, :, r, q]
+    assert float(w_s2d[:, :, 48:].abs().max()) == 0.0
+    flat = torch.cat([s2d.reshape(B, -1), torch.zeros(B, 64, dtype=torch.float64)], dim=1)   # rows overlap: 48 B pixel stride
+    out = torch.zeros(B, Ho, Wo, Co, dtype=torch.float64)
+    for U in range(4):
+        for ho in range(Ho):
+            for wo in range(Wo):
+                start = ((ho + U) * Ws + wo) * 12
+                row = flat[:, start:start + 64].clone()
+                row[:, 48:] = 0.0                       # channel coordinates >= 48 are zero-filled by TMA
+                out[:, ho, wo] += row @ w_s2d[U].T
+    assert float((out.permute(0, 3, 1, 2) - ref).abs().max()) <= 1e-10
+
+
+def test_stem_operand_choice():
+    """The engine takes the space-to-depth stem for the reference's 7x7/2 conv1 and image sides that are multiples of 16
+    (the constructor hard-wires 224, models/naive.py:216) and falls back to im2col + GEMM otherwise."""
+    import contextlib
+    import io
+    import models.naive as mn
+    from pe_b200 import engine
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = mn.NaiveObjectStateEstimator("cube", [64], 50, 32, False, (9,), False, False)
+    eng = m.feature_net.module.pe_engine(None, True)
+    assert eng._stem_s2d_ok(224, 224) and eng._stem_s2d_ok(256, 320)
+    assert not eng._stem_s2d_ok(230, 224) and not eng._stem_s2d_ok(224, 200)
+    engine.STEM_S2D[0] = False
+    try:
+        assert not eng._stem_s2d_ok(224, 224)
+    finally:
+        engine.STEM_S2D[0] = True
